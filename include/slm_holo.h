@@ -1,0 +1,113 @@
+/* libslmholo -- C ABI of the B200 hologram-synthesis engine.
+ *
+ * Drop-in boundary for the Gerchberg-Saxton / gradient-descent phase-retrieval path of
+ * pranislav/Spatial_Light_Modulator_Module.  The reference has no FFI: its "operator API" is
+ * the Python functions of src/algorithms.py and their helpers.  Each entry point below names the
+ * reference code it replaces (paths relative to the reference root); the Python package
+ * spatial_light_modulator_module_b200 binds them with ctypes.
+ *
+ * Conventions
+ *   - return 0 on success, a negative code otherwise; slm_last_error() describes the failure.
+ *     Nothing is thrown across the ABI.
+ *   - "device" pointers are valid on the context's device; "host" pointers are ordinary memory
+ *     read before the call returns.  Planes are row-major [batch][H][W].
+ *   - complex<R>/real<R>: R = float for SLM_PREC_F32 contexts, double for SLM_PREC_F64 ones.
+ *   - all work is enqueued on the context's stream; only slm_read_curves synchronises.
+ *   - a context is not thread-safe; no device allocation happens after slm_ctx_create.
+ */
+#ifndef SLM_HOLO_H
+#define SLM_HOLO_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct slm_ctx slm_ctx;
+
+enum { SLM_PREC_F32 = 0, SLM_PREC_F64 = 1 };
+enum { SLM_OK = 0, SLM_ERR_ARG = -1, SLM_ERR_SHAPE = -2, SLM_ERR_CUDA = -3, SLM_ERR_ALLOC = -4 };
+/* 8-bit conversions of the reference */
+enum { SLM_QUANT_ROUND_WRAP = 1,   /* wavefront_correction.py:458-459 convert_2pi_hologram_to_int_hologram */
+       SLM_QUANT_PIL_FLOAT = 2,    /* display_holograms.py:253-258,265 mask_hologram (.npy branch)         */
+       SLM_QUANT_FLOOR = 3,        /* move_traps.py:135-138 display_hologram; show_hologram.py:9-11         */
+       SLM_QUANT_PREVIEW = 5 };    /* generate_hologram_sequence.py:29 fromarray(expected).convert("L")    */
+
+const char* slm_last_error(void);
+int slm_version(void);
+/* Line lengths (H and W) the kernels are built for; returns the count, fills up to `cap`. */
+int slm_supported_lengths(int* out, int cap);
+
+/* One context per (device, stream, plane shape, precision); owns twiddles and the two field
+ * workspaces for up to `max_batch` planes and `max_loops_hint` iterations (grown on demand
+ * before any launch).  `cuda_stream` is a cudaStream_t (NULL = default stream). */
+int slm_ctx_create(slm_ctx** out, int device, int H, int W, int max_batch, int precision, void* cuda_stream);
+void slm_ctx_destroy(slm_ctx* ctx);
+size_t slm_ctx_workspace_bytes(const slm_ctx* ctx);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+long long slm_ctx_launch_count(const slm_ctx* ctx);
+
+/* scipy.fft.fft2 / ifft2 (algorithms.py:2; forward unnormalised, inverse scaled 1/(H*W)).
+ * in/out: device complex<R> [batch][H][W]; may alias. */
+int slm_fft2(slm_ctx* ctx, int batch, const void* in, void* out, int inverse);
+
+/* gerchberg_saxton(demanded_output, args) -- algorithms.py:10-49.
+ *   target_u8      device uint8 target, or NULL when the target is not 8-bit, in which case
+ *   target_real    device real<R> target and
+ *   amp_real       device real<R> |sqrt(target)| (algorithms.py:21,33) are used
+ *   amp_lut        host double[256]: np.sqrt(np.arange(256,dtype=uint8)) (float16-rounded)
+ *   norm           host double[batch]: np.amax(target) per plane (algorithms.py:23)
+ *   inc_amp        device real<R> [H][W] sqrt(illumination) or NULL = uniform (algorithms.py:14-19)
+ *   phasor0        device complex<R> B of iteration 0 (algorithms.py:30) or NULL = compute
+ *                  A = ifft2(amplitude) on the device (algorithms.py:27), in complex64 when
+ *                  setup_c64 != 0 (what numpy does for <=16-bit / float32 targets), else in R
+ *   hologram_out   device double: angle(A) (algorithms.py:48)
+ *   expected_out   device double or NULL: expected_outcome (algorithms.py:36-37)
+ * Error curves / iteration counts stay in the context until slm_read_curves. */
+int slm_gs_run(slm_ctx* ctx, int batch, const uint8_t* target_u8, const void* target_real, const void* amp_real,
+               const double* amp_lut, const double* norm, const void* inc_amp, const void* phasor0, int setup_c64,
+               int max_loops, double tolerance, double* hologram_out, double* expected_out);
+
+/* gradient_descent(demanded_output, args) -- algorithms.py:60-112 (+ dEdX_complex :179-185).
+ *   x              device complex<R> [batch][H][W]: the initial guess (algorithms.py:75), updated in place
+ *   mask_lut       host double[256]: 1 + white_attention*g/255 for g = 0..255 as numpy computes it
+ *                  (uint8 wrap for an int white_attention); mask_real for non-8-bit targets
+ *   lr_schedule    host double[max_loops]: args.learning_rate in force during iteration k
+ *                  (doubling rule algorithms.py:103-104 applied by the caller) */
+int slm_gd_run(slm_ctx* ctx, int batch, const uint8_t* target_u8, const void* target_real, const void* mask_real,
+               const double* mask_lut, const double* norm, const void* inc_amp, void* x, const double* lr_schedule,
+               int max_loops, double tolerance, double* hologram_out, double* expected_out);
+
+/* make_initial_guess("fourier", ...) -- algorithms.py:154-157: inc_amp * exp(1j*angle(ifft2(sqrt(T)))) */
+int slm_fourier_guess(slm_ctx* ctx, int batch, const uint8_t* target_u8, const void* amp_real, const double* amp_lut,
+                      const void* inc_amp, int setup_c64, void* x_out);
+
+/* error_evolution and its length per plane (algorithms.py:25,39,93) of the last run.
+ * err: host double[batch][max_loops]; iters: host int[batch].  Synchronises the stream. */
+int slm_read_curves(slm_ctx* ctx, int batch, int max_loops, double* err, int* iters);
+
+/* show_expected_outcome numeric part -- generate_hologram.py:24-29:
+ * |fft2(exp(1j*h))|^2 / max * norm.  hologram/out: device double; norm: host double[batch]. */
+int slm_expected_outcome(slm_ctx* ctx, int batch, const double* hologram, const double* norm, double* out);
+
+/* wfc.deflect_2pi -- wavefront_correction.py:440-449: (konst*(sy*i + sx*j)) % 2pi,
+ * konst = 2*pi*px/lambda, sy = sin(y_angle*u), sx = sin(x_angle*u) evaluated by the caller. */
+int slm_deflect_phase(slm_ctx* ctx, int H, int W, double konst, double sy, double sx, double* out);
+/* lens -- generate_hologram.py:189-203: k*(1-sqrt(1+r^2/f2)) % 2pi, k = 2*pi*f/lambda, f2 = f**2;
+ * trunc_u8 reproduces the reference's uint8 store (values 0..6). */
+int slm_lens_phase(slm_ctx* ctx, int H, int W, double px, double k, double f2, int trunc_u8, double* out);
+/* deflect_hologram / add_lens -- generate_hologram.py:178-186: (a + b) % 2pi; b is one plane of
+ * `plane` elements broadcast over the n elements of a. */
+int slm_add_mod2pi(slm_ctx* ctx, const double* a, const double* b, double* out, long long n, long long plane);
+/* mask add + 8-bit conversion, mode = SLM_QUANT_*; mask (one plane, broadcast) may be NULL. */
+int slm_quantize(slm_ctx* ctx, const double* phase, const double* mask, double ct2pi, int mode, uint8_t* out,
+                 long long n, long long plane);
+/* mask_hologram image branch -- display_holograms.py:259-265 */
+int slm_quantize_grey(slm_ctx* ctx, const uint8_t* grey, const double* mask, double ct2pi, uint8_t* out,
+                      long long n, long long plane);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,44 @@
+// Thin indirection between the kernel sources and the CUDA toolchain.
+//
+// Product build (nvcc, sm_100a): every macro maps 1:1 onto the CUDA construct it names.
+// Host-emulation build (-DSLM_EMULATE, g++ only; tests/emu): the same kernel SOURCE is run
+// on the CPU with one fibre per CUDA thread (tests/emu/emu_runtime.h) so index arithmetic,
+// barriers and reductions can be checked without a GPU.  The emulation library is test
+// infrastructure; the Python package never loads it.
+#pragma once
+
+#ifdef SLM_EMULATE
+#include "emu_runtime.h"
+#else
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SLM_HD __host__ __device__ __forceinline__
+#define SLM_DEV __device__ __forceinline__
+#define SLM_GLOBAL __global__
+#define SLM_LAUNCH_BOUNDS(t, b) __launch_bounds__(t, b)
+// dynamic shared memory of the running CTA
+#define SLM_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define SLM_STATIC_SMEM __shared__
+#define SLM_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define SLM_RESTRICT __restrict__
+
+namespace slm {
+template <typename T> SLM_DEV T ld_ro(const T* p) { return __ldg(p); }     // immutable during the launch
+template <typename T> SLM_DEV T ld_cg(const T* p) { return __ldcg(p); }    // streamed plane data (L2 only)
+template <typename T> SLM_DEV void st_cg(T* p, T v) { __stcg(p, v); }
+SLM_DEV void fence_device() { __threadfence(); }
+SLM_DEV unsigned atomic_inc_wrap(unsigned* p, unsigned limit) { return atomicInc(p, limit); }
+SLM_DEV float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+SLM_DEV double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+SLM_DEV void sync_cta() { __syncthreads(); }
+// IEEE operations that must not be contracted into FMAs (bit parity with numpy)
+SLM_DEV double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+SLM_DEV double add_rn(double a, double b) { return __dadd_rn(a, b); }
+SLM_DEV double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+SLM_DEV double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+SLM_DEV double sqrt_rn(double a) { return __dsqrt_rn(a); }
+SLM_DEV float rsqrt_fast(float a) { return rsqrtf(a); }
+SLM_DEV double rsqrt_fast(double a) { return rsqrt(a); }
+}  // namespace slm
+#endif

@@ -1,0 +1,116 @@
+// Analytic holograms, modulo-2pi composition and the 8-bit SLM quantisers (sm_100a).
+//
+// These are the reference's float64 scalar expressions evaluated one pixel per thread.  Every
+// operation is an explicitly rounded IEEE double operation in the reference's order (no FMA
+// contraction), so results are bit-identical to numpy's.
+#pragma once
+#include "engine_types.h"
+#include "passes.cuh"
+
+namespace slm {
+
+#define SLM_TWO_PI 6.283185307179586   // float(2*np.pi)
+
+// Python / numpy `a % b` for floats with b > 0 (npy_divmod): fmod, then move into [0, b)
+SLM_DEV double py_mod(double a, double b) {
+    double m = fmod(a, b);
+    if (m != 0.0) { if (m < 0.0) m = add_rn(m, b); }
+    else m = copysign(0.0, b);
+    return m;
+}
+
+// wavefront_correction.py:440-449 (deflect_2pi): const * (sin(y*u)*i + sin(x*u)*j) % 2pi
+SLM_GLOBAL void deflect_kernel(double* out, int H, int W, double konst, double sy, double sx) {
+    const long long n = (long long)H * W;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(p / W), j = (int)(p % W);
+        const double ph = mul_rn(konst, add_rn(mul_rn(sy, (double)i), mul_rn(sx, (double)j)));
+        out[p] = py_mod(ph, SLM_TWO_PI);
+    }
+}
+
+// generate_hologram.py:189-203 (lens): k * (1 - sqrt(1 + r^2/f^2)) % 2pi with
+// r = px*sqrt((i-h/2)^2 + (j-w/2)^2), k = 2*pi*f/lambda; `trunc` reproduces the uint8 store (:192,:202)
+SLM_GLOBAL void lens_kernel(double* out, int H, int W, double px, double k, double f2, int trunc_u8) {
+    const long long n = (long long)H * W;
+    const double hh = (double)H / 2.0, hw = (double)W / 2.0;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(p / W), j = (int)(p % W);
+        const double di = sub_rn((double)i, hh), dj = sub_rn((double)j, hw);
+        const double r = mul_rn(px, sqrt_rn(add_rn(mul_rn(di, di), mul_rn(dj, dj))));
+        const double q = div_rn(mul_rn(r, r), f2);
+        double ph = py_mod(mul_rn(k, sub_rn(1.0, sqrt_rn(add_rn(1.0, q)))), SLM_TWO_PI);
+        if (trunc_u8) ph = (double)(unsigned char)(long long)ph;
+        out[p] = ph;
+    }
+}
+
+// generate_hologram.py:181,186: (hologram + addend) % (2*pi).  `b` is one plane broadcast over the batch.
+SLM_GLOBAL void add_mod2pi_kernel(const double* a, const double* b, double* out, long long n, long long plane) {
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x)
+        out[p] = py_mod(add_rn(a[p], b[p % plane]), SLM_TWO_PI);
+}
+
+// astype(np.uint8) of a float64 on x86: convert to a wide integer, keep the low byte
+SLM_DEV unsigned char wrap_u8(double v) { return (unsigned char)(long long)v; }
+// PIL fromarray(float64) -> mode "F" (float32) -> convert("L"): clamp to [0,255], truncate
+SLM_DEV unsigned char pil_f_to_l(double v) {
+    const float f = (float)v;
+    if (f <= 0.0f) return 0;
+    if (f >= 255.0f) return 255;
+    return (unsigned char)f;
+}
+
+enum QuantMode {
+    QUANT_Q1 = 1,   // np.round(h*ct2pi/2pi).astype(uint8)            wavefront_correction.py:458-459
+    QUANT_Q2 = 2,   // ((h+mask)%2pi)/2pi*ct2pi -> PIL F -> L          display_holograms.py:253-258,265
+    QUANT_Q3 = 3,   // ((h[+mask])%2pi*ct2pi/2pi).astype(uint8)        move_traps.py:135-138, show_hologram.py:9-11
+    QUANT_PREVIEW = 5,   // PIL fromarray(float64).convert("L")        generate_hologram_sequence.py:29
+};
+SLM_GLOBAL void quantize_kernel(const double* h, const double* mask, double ct2pi, int mode, unsigned char* out,
+                                long long n, long long plane) {
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        double v = h[p];
+        unsigned char q;
+        if (mode == QUANT_Q1) {
+            q = wrap_u8(rint(div_rn(mul_rn(v, ct2pi), SLM_TWO_PI)));
+        } else if (mode == QUANT_Q2) {
+            if (mask) v = add_rn(v, mask[p % plane]);
+            q = pil_f_to_l(mul_rn(div_rn(py_mod(v, SLM_TWO_PI), SLM_TWO_PI), ct2pi));
+        } else if (mode == QUANT_Q3) {
+            if (mask) v = add_rn(v, mask[p % plane]);
+            q = wrap_u8(div_rn(mul_rn(py_mod(v, SLM_TWO_PI), ct2pi), SLM_TWO_PI));
+        } else {
+            q = pil_f_to_l(v);
+        }
+        out[p] = q;
+    }
+}
+// display_holograms.py:259-264: (int16(grey) + mask/2pi*ct2pi) % ct2pi -> PIL F -> L
+SLM_GLOBAL void quantize_grey_kernel(const unsigned char* g, const double* mask, double ct2pi, unsigned char* out,
+                                     long long n, long long plane) {
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        const double m = mul_rn(div_rn(mask[p % plane], SLM_TWO_PI), ct2pi);
+        out[p] = pil_f_to_l(py_mod(add_rn((double)g[p], m), ct2pi));
+    }
+}
+
+// initial guess "fourier" (algorithms.py:154-157): inc * exp(1j*angle(A)) from the setup field
+template <typename R, typename RA>
+SLM_GLOBAL void phasor_field_kernel(const cpx<RA>* A, const R* inc, cpx<R>* x, long long n, long long plane) {
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        cpx<RA> z = unit_phasor(A[p]);
+        R s = inc ? inc[p % plane] : (R)1;
+        cpx<R> o; o.x = (R)z.x * s; o.y = (R)z.y * s;
+        x[p] = o;
+    }
+}
+
+// complex<R> <-> complex128 / real conversions at the boundary (numpy hands over complex128)
+template <typename TS, typename TD>
+SLM_GLOBAL void convert_kernel(const TS* in, TD* out, long long n) {
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x)
+        out[p] = (TD)in[p];
+}
+
+}  // namespace slm

@@ -1,0 +1,396 @@
+// libslmholo: context, pass scheduling and the C ABI (include/slm_holo.h).
+//
+// Scheduling of one run (all launches on the context's stream, no host synchronisation):
+//   GS  (algorithms.py:10-49):  setup -> row pass -> max pre-pass -> { col pass, row pass } * loops
+//                               -> final row pass (hologram) -> intensity pass (expected_outcome)
+//   GD  (algorithms.py:60-112): row pass -> { max pre-pass, col pass, row pass } * loops
+//                               -> final row pass (last update + hologram) -> intensity pass
+// Planes whose loop condition has failed (tolerance) are skipped by every later pass, so a batch
+// needs no host round trip per iteration.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/slm_holo.h"
+#include "elementwise.cuh"
+#include "engine_types.h"
+
+using namespace slm;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define SLM_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) return fail(SLM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+#define SLM_TRY(expr)                                                                           \
+    do {                                                                                        \
+        int r_ = (expr);                                                                        \
+        if (r_ != 0) return r_ < -1000 ? fail(SLM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString((cudaError_t)(-r_ - 1000))) : r_; \
+    } while (0)
+
+struct slm_ctx {
+    int device = 0, H = 0, W = 0, max_batch = 0, prec = 0;
+    cudaStream_t stream = nullptr;
+    const LineTable *row = nullptr, *col = nullptr;       // precision of the context
+    const LineTable *row32 = nullptr, *col32 = nullptr;   // complex64 setup path
+    void *X = nullptr, *Y = nullptr;
+    void *tw_row = nullptr, *tw_col = nullptr, *tw_row32 = nullptr, *tw_col32 = nullptr;
+    PlaneStats* stats = nullptr;
+    Partial* partial = nullptr;
+    unsigned* counter = nullptr;
+    double *err_curve = nullptr, *lr = nullptr, *norm = nullptr;
+    void* lut = nullptr;
+    float* lut32 = nullptr;
+    int loops_cap = 0, tiles = 0;
+    size_t bytes = 0;
+    long long launches = 0;
+    std::vector<void*> owned;
+};
+
+static size_t real_size(int prec) { return prec == PREC_F64 ? 8 : 4; }
+
+static int dev_alloc(slm_ctx* c, void** p, size_t n) {
+    SLM_CUDA(cudaMalloc(p, n ? n : 16));
+    c->owned.push_back(*p);
+    c->bytes += n;
+    return 0;
+}
+
+// exp(-2 pi i q / N), q in [0, N), evaluated in extended precision
+static int make_twiddles(slm_ctx* c, int N, int prec, void** out) {
+    std::vector<double> td(2 * (size_t)N);
+    std::vector<float> tf(2 * (size_t)N);
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    for (int q = 0; q < N; ++q) {
+        // exact octant symmetry is not needed; long double sin/cos are accurate to < 1 ulp of double
+        const long double ang = -two_pi * (long double)q / (long double)N;
+        td[2 * q] = (double)cosl(ang); td[2 * q + 1] = (double)sinl(ang);
+        tf[2 * q] = (float)cosl(ang); tf[2 * q + 1] = (float)sinl(ang);
+    }
+    const size_t bytes = 2 * (size_t)N * real_size(prec);
+    SLM_TRY(dev_alloc(c, out, bytes));
+    SLM_CUDA(cudaMemcpy(*out, prec == PREC_F64 ? (const void*)td.data() : (const void*)tf.data(), bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int ensure_loops(slm_ctx* c, int max_loops) {
+    if (max_loops <= c->loops_cap) return 0;
+    int cap = c->loops_cap ? c->loops_cap : 256;
+    while (cap < max_loops) cap *= 2;
+    SLM_CUDA(cudaStreamSynchronize(c->stream));
+    SLM_TRY(dev_alloc(c, (void**)&c->err_curve, (size_t)c->max_batch * cap * sizeof(double)));
+    SLM_TRY(dev_alloc(c, (void**)&c->lr, (size_t)cap * sizeof(double)));
+    c->loops_cap = cap;
+    return 0;
+}
+
+extern "C" const char* slm_last_error(void) { return g_err.c_str(); }
+extern "C" int slm_version(void) { return 100; }
+extern "C" int slm_supported_lengths(int* out, int cap) { return supported_lengths(out, cap); }
+
+extern "C" void slm_ctx_destroy(slm_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (void* p : c->owned) cudaFree(p);
+    delete c;
+}
+
+extern "C" int slm_ctx_create(slm_ctx** out, int device, int H, int W, int max_batch, int precision, void* stream) {
+    if (!out || max_batch < 1 || (precision != PREC_F32 && precision != PREC_F64)) return fail(SLM_ERR_ARG, "slm_ctx_create: bad argument");
+    const LineTable* row = find_line_table(W, precision);
+    const LineTable* col = find_line_table(H, precision);
+    if (!row || !col) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "unsupported plane shape %dx%d: rows and columns must be one of the built line lengths", H, W);
+        return fail(SLM_ERR_SHAPE, buf);
+    }
+    if (H % row->rows_per_cta != 0 || W % col->cols_per_cta != 0) return fail(SLM_ERR_SHAPE, "plane shape not divisible by the CTA tile");
+    SLM_CUDA(cudaSetDevice(device));
+    slm_ctx* c = new slm_ctx;
+    c->device = device; c->H = H; c->W = W; c->max_batch = max_batch; c->prec = precision;
+    c->stream = (cudaStream_t)stream;
+    c->row = row; c->col = col;
+    c->row32 = find_line_table(W, PREC_F32); c->col32 = find_line_table(H, PREC_F32);
+    row->prepare(); col->prepare(); c->row32->prepare(); c->col32->prepare();
+    const size_t plane = (size_t)H * W, cs = 2 * real_size(precision);
+    int rc = 0;
+    auto A = [&](void** p, size_t n) { if (!rc) rc = dev_alloc(c, p, n); };
+    A(&c->X, (size_t)max_batch * plane * cs);
+    A(&c->Y, (size_t)max_batch * plane * cs);
+    c->tiles = W / col->cols_per_cta;
+    const int tiles32 = W / c->col32->cols_per_cta;
+    const int tmax = c->tiles > tiles32 ? c->tiles : tiles32;
+    A((void**)&c->stats, (size_t)max_batch * sizeof(PlaneStats));
+    A((void**)&c->partial, (size_t)max_batch * tmax * sizeof(Partial));
+    A((void**)&c->counter, (size_t)max_batch * sizeof(unsigned));
+    A((void**)&c->norm, (size_t)max_batch * sizeof(double));
+    A(&c->lut, 256 * real_size(precision));
+    A((void**)&c->lut32, 256 * sizeof(float));
+    if (!rc) rc = make_twiddles(c, W, precision, &c->tw_row);
+    if (!rc) rc = make_twiddles(c, H, precision, &c->tw_col);
+    if (!rc && precision == PREC_F64) { rc = make_twiddles(c, W, PREC_F32, &c->tw_row32); if (!rc) rc = make_twiddles(c, H, PREC_F32, &c->tw_col32); }
+    if (!rc && precision == PREC_F32) { c->tw_row32 = c->tw_row; c->tw_col32 = c->tw_col; }
+    if (!rc) rc = ensure_loops(c, 256);
+    if (!rc && cudaMemset(c->counter, 0, (size_t)max_batch * sizeof(unsigned)) != cudaSuccess) rc = fail(SLM_ERR_CUDA, "cudaMemset(counter)");
+    if (!rc && cudaMemset(c->stats, 0, (size_t)max_batch * sizeof(PlaneStats)) != cudaSuccess) rc = fail(SLM_ERR_CUDA, "cudaMemset(stats)");
+    if (rc) { std::string keep = g_err; slm_ctx_destroy(c); g_err = keep; return rc; }
+    *out = c;
+    return 0;
+}
+
+extern "C" size_t slm_ctx_workspace_bytes(const slm_ctx* c) { return c ? c->bytes : 0; }
+extern "C" long long slm_ctx_launch_count(const slm_ctx* c) { return c ? c->launches : 0; }
+
+static int check_batch(slm_ctx* c, int batch, const char* who) {
+    if (!c) return fail(SLM_ERR_ARG, std::string(who) + ": null context");
+    if (batch < 1 || batch > c->max_batch) return fail(SLM_ERR_ARG, std::string(who) + ": batch exceeds the context's max_batch");
+    SLM_CUDA(cudaSetDevice(c->device));
+    return 0;
+}
+
+// host LUT (double[256]) -> device R[256] and float[256]
+static int upload_lut(slm_ctx* c, const double* lut) {
+    float f[256]; double d[256];
+    for (int i = 0; i < 256; ++i) { f[i] = (float)lut[i]; d[i] = lut[i]; }
+    SLM_CUDA(cudaMemcpyAsync(c->lut32, f, sizeof f, cudaMemcpyHostToDevice, c->stream));
+    if (c->prec == PREC_F64) SLM_CUDA(cudaMemcpyAsync(c->lut, d, sizeof d, cudaMemcpyHostToDevice, c->stream));
+    else SLM_CUDA(cudaMemcpyAsync(c->lut, f, sizeof f, cudaMemcpyHostToDevice, c->stream));
+    SLM_CUDA(cudaStreamSynchronize(c->stream));     // the staging arrays live on this stack frame
+    return 0;
+}
+
+static int begin_run(slm_ctx* c, int batch, const double* norm, int max_loops) {
+    SLM_TRY(ensure_loops(c, max_loops));
+    SLM_CUDA(cudaMemsetAsync(c->stats, 0, (size_t)batch * sizeof(PlaneStats), c->stream));
+    if (norm) SLM_CUDA(cudaMemcpyAsync(c->norm, norm, (size_t)batch * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+static const int kEwThreads = 256;
+static unsigned ew_blocks(long long n) { long long b = (n + kEwThreads - 1) / kEwThreads; return (unsigned)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b)); }
+
+// A = ifft2(amplitude) into c->Y (algorithms.py:27 / :155); returns the RowSource that reads it
+static int setup_field(slm_ctx* c, int batch, const uint8_t* T8, const void* amp_real, int setup_c64, int* source) {
+    const bool f32path = (c->prec == PREC_F32) || setup_c64;
+    const LineTable* row = f32path ? c->row32 : c->row;
+    const LineTable* col = f32path ? c->col32 : c->col;
+    PlainRowArgs ra{};
+    ra.B = batch; ra.H = c->H; ra.inverse = 1; ra.out = c->X;
+    ra.tw = f32path ? c->tw_row32 : c->tw_row;
+    if (T8) { ra.input = IN_LUT_U8; ra.T8 = T8; ra.lut = f32path ? (const void*)c->lut32 : (const void*)c->lut; }
+    else {
+        if (!amp_real) return fail(SLM_ERR_ARG, "setup: neither target_u8 nor amp_real given");
+        ra.input = IN_REAL; ra.in = amp_real;
+        if (f32path && c->prec == PREC_F64) {   // narrow the float64 plane the way scipy's _asfarray does for float32 data
+            const long long n = (long long)batch * c->H * c->W;
+            SLM_LAUNCH((convert_kernel<double, float>), dim3(ew_blocks(n)), dim3(kEwThreads), 0, c->stream,
+                       static_cast<const double*>(amp_real), static_cast<float*>(c->Y), n);
+            c->launches++;
+            ra.in = c->Y;
+        }
+    }
+    SLM_TRY(row->row_plain(ra, c->stream)); c->launches++;
+    PlainColArgs ca{};
+    ca.B = batch; ca.W = c->W; ca.output = OUT_COMPLEX; ca.inverse = 1; ca.scale = 1.0 / ((double)c->H * c->W);
+    ca.in = c->X; ca.out = c->Y; ca.tw = f32path ? c->tw_col32 : c->tw_col;
+    SLM_TRY(col->col_plain(ca, c->stream)); c->launches++;
+    *source = f32path ? ROW_FROM_A32 : ROW_FROM_A;
+    return 0;
+}
+
+static PlainColArgs stats_args(slm_ctx* c, int batch, int output, void* out) {
+    PlainColArgs a{};
+    a.B = batch; a.W = c->W; a.output = output; a.inverse = 0; a.scale = 1.0;
+    a.in = c->X; a.out = out; a.norm = c->norm; a.stats = c->stats; a.partial = c->partial; a.counter = c->counter;
+    a.tw = c->tw_col;
+    return a;
+}
+
+extern "C" int slm_fft2(slm_ctx* c, int batch, const void* in, void* out, int inverse) {
+    SLM_TRY(check_batch(c, batch, "slm_fft2"));
+    if (!in || !out) return fail(SLM_ERR_ARG, "slm_fft2: null plane");
+    PlainRowArgs ra{};
+    ra.B = batch; ra.H = c->H; ra.input = IN_COMPLEX; ra.inverse = inverse; ra.in = in; ra.out = c->X; ra.tw = c->tw_row;
+    SLM_TRY(c->row->row_plain(ra, c->stream)); c->launches++;
+    PlainColArgs ca{};
+    ca.B = batch; ca.W = c->W; ca.output = OUT_COMPLEX; ca.inverse = inverse;
+    ca.scale = inverse ? 1.0 / ((double)c->H * c->W) : 1.0;
+    ca.in = c->X; ca.out = out; ca.tw = c->tw_col;
+    SLM_TRY(c->col->col_plain(ca, c->stream)); c->launches++;
+    return 0;
+}
+
+extern "C" int slm_gs_run(slm_ctx* c, int batch, const uint8_t* T8, const void* Treal, const void* amp_real,
+                          const double* amp_lut, const double* norm, const void* inc_amp, const void* phasor0,
+                          int setup_c64, int max_loops, double tolerance, double* hologram_out, double* expected_out) {
+    SLM_TRY(check_batch(c, batch, "slm_gs_run"));
+    if (max_loops < 1) return fail(SLM_ERR_ARG, "slm_gs_run: max_loops must be >= 1 (the reference raises UnboundLocalError for 0)");
+    if (!norm || !hologram_out) return fail(SLM_ERR_ARG, "slm_gs_run: norm and hologram_out are required");
+    if (T8 ? !amp_lut : !(Treal && amp_real)) return fail(SLM_ERR_ARG, "slm_gs_run: give target_u8 + amp_lut, or target_real + amp_real");
+    SLM_TRY(begin_run(c, batch, norm, max_loops));
+    if (T8) SLM_TRY(upload_lut(c, amp_lut));
+
+    RowArgs ra{};
+    ra.B = batch; ra.H = c->H; ra.Y = c->Y; ra.X = c->X; ra.inc = inc_amp; ra.stats = c->stats;
+    ra.inv_hw = 1.0 / ((double)c->H * c->W); ra.hologram = hologram_out; ra.tw = c->tw_row;
+    if (phasor0) { ra.source = ROW_FROM_FIELD; ra.field = phasor0; }
+    else {
+        int src = 0;
+        SLM_TRY(setup_field(c, batch, T8, amp_real, setup_c64, &src));
+        ra.source = src; ra.A32 = c->Y; ra.field = c->Y;
+    }
+    SLM_TRY(c->row->row_pass(ALG_GS, ra, c->stream)); c->launches++;
+    // exact scale of iteration 0 so the one-pass error of later iterations is well conditioned
+    SLM_TRY(c->col->col_plain(stats_args(c, batch, OUT_STATS, nullptr), c->stream)); c->launches++;
+
+    ColArgs ca{};
+    ca.B = batch; ca.W = c->W; ca.X = c->X; ca.Y = c->Y; ca.T8 = T8; ca.Treal = Treal; ca.plane2 = amp_real;
+    ca.lut = c->lut; ca.norm = c->norm; ca.stats = c->stats; ca.partial = c->partial; ca.counter = c->counter;
+    ca.err_curve = c->err_curve; ca.max_loops = max_loops; ca.tolerance = tolerance;
+    ca.inv_hw = ra.inv_hw; ca.tw = c->tw_col;
+    ra.source = ROW_FROM_Y;
+    for (int k = 0; k < max_loops; ++k) {
+        SLM_TRY(c->col->col_pass(ALG_GS, ca, c->stream)); c->launches++;
+        if (k + 1 < max_loops) { SLM_TRY(c->row->row_pass(ALG_GS, ra, c->stream)); c->launches++; }
+    }
+    ra.final_pass = 1;
+    SLM_TRY(c->row->row_pass(ALG_GS, ra, c->stream)); c->launches++;
+    if (expected_out) { SLM_TRY(c->col->col_plain(stats_args(c, batch, OUT_INTENSITY_GS, expected_out), c->stream)); c->launches++; }
+    return 0;
+}
+
+extern "C" int slm_gd_run(slm_ctx* c, int batch, const uint8_t* T8, const void* Treal, const void* mask_real,
+                          const double* mask_lut, const double* norm, const void* inc_amp, void* x,
+                          const double* lr_schedule, int max_loops, double tolerance, double* hologram_out,
+                          double* expected_out) {
+    SLM_TRY(check_batch(c, batch, "slm_gd_run"));
+    if (max_loops < 1) return fail(SLM_ERR_ARG, "slm_gd_run: max_loops must be >= 1 (the reference raises UnboundLocalError for 0)");
+    if (!norm || !hologram_out || !x || !lr_schedule) return fail(SLM_ERR_ARG, "slm_gd_run: norm, x, lr_schedule and hologram_out are required");
+    if (T8 ? !mask_lut : !(Treal && mask_real)) return fail(SLM_ERR_ARG, "slm_gd_run: give target_u8 + mask_lut, or target_real + mask_real");
+    SLM_TRY(begin_run(c, batch, norm, max_loops));
+    SLM_CUDA(cudaMemcpyAsync(c->lr, lr_schedule, (size_t)max_loops * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (T8) SLM_TRY(upload_lut(c, mask_lut));
+
+    RowArgs ra{};
+    ra.B = batch; ra.H = c->H; ra.Y = c->Y; ra.X = c->X; ra.x = x; ra.inc = inc_amp; ra.stats = c->stats; ra.lr = c->lr;
+    ra.inv_hw = 1.0 / ((double)c->H * c->W); ra.hologram = hologram_out; ra.tw = c->tw_row;
+    ra.source = ROW_FROM_FIELD;
+    SLM_TRY(c->row->row_pass(ALG_GD, ra, c->stream)); c->launches++;
+
+    ColArgs ca{};
+    ca.B = batch; ca.W = c->W; ca.X = c->X; ca.Y = c->Y; ca.T8 = T8; ca.Treal = Treal; ca.plane2 = mask_real;
+    ca.lut = c->lut; ca.norm = c->norm; ca.stats = c->stats; ca.partial = c->partial; ca.counter = c->counter;
+    ca.err_curve = c->err_curve; ca.max_loops = max_loops; ca.tolerance = tolerance;
+    ca.inv_hw = ra.inv_hw; ca.tw = c->tw_col;
+    const PlainColArgs sa = stats_args(c, batch, OUT_STATS, nullptr);
+    ra.source = ROW_FROM_Y;
+    for (int k = 0; k < max_loops; ++k) {
+        SLM_TRY(c->col->col_plain(sa, c->stream)); c->launches++;            // amax(output_unnormed), algorithms.py:86
+        SLM_TRY(c->col->col_pass(ALG_GD, ca, c->stream)); c->launches++;
+        if (k + 1 < max_loops) { SLM_TRY(c->row->row_pass(ALG_GD, ra, c->stream)); c->launches++; }
+    }
+    ra.final_pass = 1;
+    SLM_TRY(c->row->row_pass(ALG_GD, ra, c->stream)); c->launches++;
+    if (expected_out) { SLM_TRY(c->col->col_plain(stats_args(c, batch, OUT_INTENSITY_GD, expected_out), c->stream)); c->launches++; }
+    return 0;
+}
+
+extern "C" int slm_fourier_guess(slm_ctx* c, int batch, const uint8_t* T8, const void* amp_real, const double* amp_lut,
+                                 const void* inc_amp, int setup_c64, void* x_out) {
+    SLM_TRY(check_batch(c, batch, "slm_fourier_guess"));
+    if (!x_out || (T8 && !amp_lut)) return fail(SLM_ERR_ARG, "slm_fourier_guess: bad argument");
+    if (T8) SLM_TRY(upload_lut(c, amp_lut));
+    int src = 0;
+    SLM_TRY(setup_field(c, batch, T8, amp_real, setup_c64, &src));
+    const long long plane = (long long)c->H * c->W, n = plane * batch;
+    const dim3 grid(ew_blocks(n)), block(kEwThreads);
+    if (c->prec == PREC_F32)
+        SLM_LAUNCH((phasor_field_kernel<float, float>), grid, block, 0, c->stream, static_cast<const cpx<float>*>(c->Y),
+                   static_cast<const float*>(inc_amp), static_cast<cpx<float>*>(x_out), n, plane);
+    else if (src == ROW_FROM_A32)
+        SLM_LAUNCH((phasor_field_kernel<double, float>), grid, block, 0, c->stream, static_cast<const cpx<float>*>(c->Y),
+                   static_cast<const double*>(inc_amp), static_cast<cpx<double>*>(x_out), n, plane);
+    else
+        SLM_LAUNCH((phasor_field_kernel<double, double>), grid, block, 0, c->stream, static_cast<const cpx<double>*>(c->Y),
+                   static_cast<const double*>(inc_amp), static_cast<cpx<double>*>(x_out), n, plane);
+    c->launches++;
+    SLM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int slm_read_curves(slm_ctx* c, int batch, int max_loops, double* err, int* iters) {
+    SLM_TRY(check_batch(c, batch, "slm_read_curves"));
+    if (max_loops < 1 || max_loops > c->loops_cap) return fail(SLM_ERR_ARG, "slm_read_curves: max_loops does not match the last run");
+    std::vector<PlaneStats> st(batch);
+    SLM_CUDA(cudaMemcpyAsync(st.data(), c->stats, (size_t)batch * sizeof(PlaneStats), cudaMemcpyDeviceToHost, c->stream));
+    if (err) SLM_CUDA(cudaMemcpyAsync(err, c->err_curve, (size_t)batch * max_loops * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SLM_CUDA(cudaStreamSynchronize(c->stream));
+    if (iters) for (int b = 0; b < batch; ++b) iters[b] = st[b].iters;
+    return 0;
+}
+
+extern "C" int slm_expected_outcome(slm_ctx* c, int batch, const double* hologram, const double* norm, double* out) {
+    SLM_TRY(check_batch(c, batch, "slm_expected_outcome"));
+    if (!hologram || !norm || !out) return fail(SLM_ERR_ARG, "slm_expected_outcome: null argument");
+    SLM_TRY(begin_run(c, batch, norm, 1));
+    PlainRowArgs ra{};
+    ra.B = batch; ra.H = c->H; ra.input = IN_PHASE; ra.inverse = 0; ra.in = hologram; ra.out = c->X; ra.tw = c->tw_row;
+    SLM_TRY(c->row->row_plain(ra, c->stream)); c->launches++;
+    SLM_TRY(c->col->col_plain(stats_args(c, batch, OUT_STATS, nullptr), c->stream)); c->launches++;
+    SLM_TRY(c->col->col_plain(stats_args(c, batch, OUT_INTENSITY_PREVIEW, out), c->stream)); c->launches++;
+    return 0;
+}
+
+#define SLM_EW_PROLOGUE(who)                                              \
+    if (!c) return fail(SLM_ERR_ARG, who ": null context");              \
+    SLM_CUDA(cudaSetDevice(c->device));
+
+extern "C" int slm_deflect_phase(slm_ctx* c, int H, int W, double konst, double sy, double sx, double* out) {
+    SLM_EW_PROLOGUE("slm_deflect_phase");
+    if (!out || H < 1 || W < 1) return fail(SLM_ERR_ARG, "slm_deflect_phase: bad argument");
+    SLM_LAUNCH(deflect_kernel, dim3(ew_blocks((long long)H * W)), dim3(kEwThreads), 0, c->stream, out, H, W, konst, sy, sx);
+    c->launches++;
+    SLM_CUDA(cudaGetLastError());
+    return 0;
+}
+extern "C" int slm_lens_phase(slm_ctx* c, int H, int W, double px, double k, double f2, int trunc_u8, double* out) {
+    SLM_EW_PROLOGUE("slm_lens_phase");
+    if (!out || H < 1 || W < 1) return fail(SLM_ERR_ARG, "slm_lens_phase: bad argument");
+    SLM_LAUNCH(lens_kernel, dim3(ew_blocks((long long)H * W)), dim3(kEwThreads), 0, c->stream, out, H, W, px, k, f2, trunc_u8);
+    c->launches++;
+    SLM_CUDA(cudaGetLastError());
+    return 0;
+}
+extern "C" int slm_add_mod2pi(slm_ctx* c, const double* a, const double* b, double* out, long long n, long long plane) {
+    SLM_EW_PROLOGUE("slm_add_mod2pi");
+    if (!a || !b || !out || n < 1 || plane < 1) return fail(SLM_ERR_ARG, "slm_add_mod2pi: bad argument");
+    SLM_LAUNCH(add_mod2pi_kernel, dim3(ew_blocks(n)), dim3(kEwThreads), 0, c->stream, a, b, out, n, plane);
+    c->launches++;
+    SLM_CUDA(cudaGetLastError());
+    return 0;
+}
+extern "C" int slm_quantize(slm_ctx* c, const double* phase, const double* mask, double ct2pi, int mode, uint8_t* out,
+                            long long n, long long plane) {
+    SLM_EW_PROLOGUE("slm_quantize");
+    if (!phase || !out || n < 1 || plane < 1) return fail(SLM_ERR_ARG, "slm_quantize: bad argument");
+    if (mode != QUANT_Q1 && mode != QUANT_Q2 && mode != QUANT_Q3 && mode != QUANT_PREVIEW) return fail(SLM_ERR_ARG, "slm_quantize: unknown mode");
+    SLM_LAUNCH(quantize_kernel, dim3(ew_blocks(n)), dim3(kEwThreads), 0, c->stream, phase, mask, ct2pi, mode, out, n, plane);
+    c->launches++;
+    SLM_CUDA(cudaGetLastError());
+    return 0;
+}
+extern "C" int slm_quantize_grey(slm_ctx* c, const uint8_t* grey, const double* mask, double ct2pi, uint8_t* out,
+                                 long long n, long long plane) {
+    SLM_EW_PROLOGUE("slm_quantize_grey");
+    if (!grey || !mask || !out || n < 1 || plane < 1) return fail(SLM_ERR_ARG, "slm_quantize_grey: bad argument");
+    SLM_LAUNCH(quantize_grey_kernel, dim3(ew_blocks(n)), dim3(kEwThreads), 0, c->stream, grey, mask, ct2pi, out, n, plane);
+    c->launches++;
+    SLM_CUDA(cudaGetLastError());
+    return 0;
+}

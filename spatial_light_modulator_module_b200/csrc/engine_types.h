@@ -1,0 +1,121 @@
+// Types shared by the pass kernels (passes.cuh), their per-line-length instantiations
+// (gen/line_*.cu) and the engine (engine.cu).
+#pragma once
+#include "cuda_compat.h"
+
+namespace slm {
+
+enum Precision { PREC_F32 = 0, PREC_F64 = 1 };
+enum Algorithm { ALG_GS = 0, ALG_GD = 1 };
+
+// ---- per-plane loop state, device resident --------------------------------------------------
+// Written only by the last column tile of a plane to finish a Fourier-plane pass.
+struct PlaneStats {
+    double imax;     // max |C|^2 of the most recent Fourier-plane pass (algorithms.py:37,86)
+    double scale;    // norm / imax of that pass
+    double err;      // last error value (algorithms.py:38,92)
+    int iters;       // completed iterations == len(error_evolution)
+    int done;        // loop condition `error > tolerance` has failed (algorithms.py:29,83)
+};
+
+// Per-tile reduction record (deterministic two-stage reduce: tile -> plane).
+struct Partial { double mx, a, b, c; };
+
+// ---- SLM-plane (row) pass ----------------------------------------------------------------------
+enum RowSource {
+    ROW_FROM_Y = 0,      // rows of Y hold the column-inverse-transformed field: finish the ifft2
+    ROW_FROM_A32 = 1,    // complex64 field A (reference's first ifft2, algorithms.py:27): phasor in fp32
+    ROW_FROM_FIELD = 2,  // caller-supplied B of iteration 0 (GS) / x itself (GD first pass)
+    ROW_FROM_A = 3,      // complex<R> field A: phasor in R (targets whose first ifft2 is complex128)
+};
+
+struct RowArgs {
+    int B, H;
+    int source;              // RowSource
+    int final_pass;          // 1: emit the hologram (phase) and stop; no forward transform
+    const void* Y;           // complex<R> [B][H][W]
+    void* X;                 // complex<R> [B][H][W]
+    const void* field;       // complex<R> [B][H][W]   (ROW_FROM_FIELD, GS)
+    const void* A32;         // complex<float> [B][H][W] (ROW_FROM_A32)
+    void* x;                 // GD: complex<R> [B][H][W], updated in place
+    const void* inc;         // real<R> [H][W] illumination amplitude or null (uniform)
+    const double* lr;        // GD: learning rate of iteration k at lr[k]
+    double inv_hw;           // 1/(H*W): scipy's ifft2 normalisation (matters for GD only)
+    const PlaneStats* stats;
+    double* hologram;        // [B][H][W], final pass
+    const void* tw;          // complex<R> [W] row twiddles exp(-2 pi i q / W)
+};
+
+// ---- Fourier-plane (column) pass -----------------------------------------------------------------
+struct ColArgs {
+    int B, W;
+    const void* X;           // complex<R> [B][H][W]
+    void* Y;                 // complex<R> [B][H][W]
+    const uint8_t* T8;       // uint8 target [B][H][W] or null
+    const void* Treal;       // real<R> target (when T8 == null)
+    const void* plane2;      // real<R>: GS |sqrt(T)| plane, GD mask plane (when T8 == null)
+    const void* lut;         // R[256]: GS amplitude / GD mask by grey level (when T8 != null)
+    const double* norm;      // [B] amax(T)
+    PlaneStats* stats;       // [B]
+    Partial* partial;        // [B][W / TC]
+    unsigned* counter;       // [B] zero before first use; self-resetting
+    double* err_curve;       // [B][max_loops]
+    int max_loops;
+    double tolerance;
+    double inv_hw;
+    const void* tw;          // complex<R> [H] column twiddles
+};
+
+// ---- plain transforms / setup / preview ------------------------------------------------------
+enum PlainRowInput {
+    IN_COMPLEX = 0,          // complex<R> plane
+    IN_LUT_U8 = 1,           // real: lut[T8]   (GS setup: float16-rounded sqrt)
+    IN_REAL = 2,             // real<R> plane
+    IN_PHASE = 3,            // exp(i * phase), phase double plane (generate_hologram.py:25)
+};
+struct PlainRowArgs {
+    int B, H;
+    int input;               // PlainRowInput
+    int inverse;
+    const void* in;          // complex<R> / real<R> / double, by `input`
+    const uint8_t* T8;
+    const void* lut;         // R[256]
+    void* out;               // complex<R> [B][H][W]
+    const void* tw;
+};
+enum PlainColOutput {
+    OUT_COMPLEX = 0,         // write the transformed plane (scaled by `scale`)
+    OUT_STATS = 1,           // only max |C|^2 -> stats[b].imax / .scale
+    OUT_INTENSITY_GS = 2,    // |C|^2 * stats.scale                        (algorithms.py:36-37)
+    OUT_INTENSITY_GD = 3,    // (|C|^2 * norm) / imax                      (algorithms.py:85-86)
+    OUT_INTENSITY_PREVIEW = 4,  // (|C|^2 / imax) * norm                  (generate_hologram.py:26-29)
+};
+struct PlainColArgs {
+    int B, W;
+    int output;              // PlainColOutput
+    int inverse;
+    double scale;            // OUT_COMPLEX: multiply results (1/(HW) for ifft2)
+    const void* in;          // complex<R> [B][H][W]
+    void* out;               // complex<R> [B][H][W] or double [B][H][W]
+    const double* norm;      // [B]
+    PlaneStats* stats;
+    Partial* partial;
+    unsigned* counter;
+    const void* tw;
+};
+
+// ---- launch table: one entry per (line length, precision), see gen_lines.py ----------------------
+struct LineTable {
+    int L, prec;
+    int rows_per_cta, row_threads; size_t row_smem;     // when L is the row length W
+    int cols_per_cta, col_threads; size_t col_smem;     // when L is the column length H
+    void (*prepare)();                                   // per-device function attributes
+    int (*row_pass)(int alg, const RowArgs&, cudaStream_t);
+    int (*row_plain)(const PlainRowArgs&, cudaStream_t);
+    int (*col_pass)(int alg, const ColArgs&, cudaStream_t);
+    int (*col_plain)(const PlainColArgs&, cudaStream_t);
+};
+const LineTable* find_line_table(int L, int prec);
+int supported_lengths(int* out, int cap);
+
+}  // namespace slm
