@@ -48,6 +48,13 @@ size_t slm_ctx_workspace_bytes(const slm_ctx* ctx);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 long long slm_ctx_launch_count(const slm_ctx* ctx);
 
+/* Per-launch device timing for bench.py's roofline: while enabled every kernel launch is bracketed
+ * by CUDA events on the context's stream.  slm_ctx_profile_read synchronises, accumulates and
+ * clears them: ms[k] / count[k], k = 0 SLM-plane (row) pass, 1 Fourier-plane (column) pass,
+ * 2 column max pre-pass, 3 plain row transform, 4 plain column transform, 5 elementwise. */
+int slm_ctx_profile(slm_ctx* ctx, int enable);
+int slm_ctx_profile_read(slm_ctx* ctx, double* ms, long long* count);
+
 /* scipy.fft.fft2 / ifft2 (algorithms.py:2; forward unnormalised, inverse scaled 1/(H*W)).
  * in/out: device complex<R> [batch][H][W]; may alias. */
 int slm_fft2(slm_ctx* ctx, int batch, const void* in, void* out, int inverse);

@@ -27,6 +27,8 @@ SIGNATURES = {
     "slm_ctx_destroy": (None, [_vp]),
     "slm_ctx_workspace_bytes": (C.c_size_t, [_vp]),
     "slm_ctx_launch_count": (_ll, [_vp]),
+    "slm_ctx_profile": (_i, [_vp, _i]),
+    "slm_ctx_profile_read": (_i, [_vp, _dp, C.POINTER(_ll)]),
     "slm_fft2": (_i, [_vp, _i, _vp, _vp, _i]),
     "slm_gs_run": (_i, [_vp, _i, _vp, _vp, _vp, _dp, _dp, _vp, _vp, _i, _i, _d, _vp, _vp]),
     "slm_gd_run": (_i, [_vp, _i, _vp, _vp, _vp, _dp, _dp, _vp, _vp, _dp, _i, _d, _vp, _vp]),

@@ -16,6 +16,7 @@
 #define SLM_HD __host__ __device__ __forceinline__
 #define SLM_DEV __device__ __forceinline__
 #define SLM_GLOBAL __global__
+#define SLM_HOSTDEV __host__ __device__
 #define SLM_LAUNCH_BOUNDS(t, b) __launch_bounds__(t, b)
 // dynamic shared memory of the running CTA
 #define SLM_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]

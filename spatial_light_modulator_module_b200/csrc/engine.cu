@@ -50,7 +50,35 @@ struct slm_ctx {
     size_t bytes = 0;
     long long launches = 0;
     std::vector<void*> owned;
+    // optional per-launch device timing (slm_ctx_profile): event pairs on the context's stream
+    bool profiling = false;
+    struct Timed { int kind; cudaEvent_t a, b; };
+    std::vector<Timed> timed;
 };
+
+// launch kinds reported by slm_ctx_profile_read
+enum { K_ROW_PASS = 0, K_COL_PASS = 1, K_COL_STATS = 2, K_ROW_PLAIN = 3, K_COL_PLAIN = 4, K_ELEMENTWISE = 5, K_KINDS = 6 };
+
+#ifndef SLM_EMULATE
+struct LaunchTimer {
+    slm_ctx* c; int kind; cudaEvent_t a = nullptr, b = nullptr;
+    LaunchTimer(slm_ctx* c_, int k) : c(c_), kind(k) {
+        c->launches++;
+        if (!c->profiling) return;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, c->stream);
+    }
+    ~LaunchTimer() {
+        if (!a) return;
+        cudaEventRecord(b, c->stream);
+        c->timed.push_back({kind, a, b});
+    }
+};
+#else
+struct LaunchTimer { LaunchTimer(slm_ctx* c, int) { c->launches++; } };
+#endif
+#define SLM_TIMED(kind, expr) do { LaunchTimer t_(c, kind); SLM_TRY(expr); } while (0)
+
 
 static size_t real_size(int prec) { return prec == PREC_F64 ? 8 : 4; }
 
@@ -145,6 +173,29 @@ extern "C" int slm_ctx_create(slm_ctx** out, int device, int H, int W, int max_b
 }
 
 extern "C" size_t slm_ctx_workspace_bytes(const slm_ctx* c) { return c ? c->bytes : 0; }
+
+extern "C" int slm_ctx_profile(slm_ctx* c, int enable) {
+    if (!c) return fail(SLM_ERR_ARG, "slm_ctx_profile: null context");
+    c->profiling = enable != 0;
+    return 0;
+}
+// ms[k], count[k] for k < 6: row pass, column pass, column max pre-pass, plain row, plain column, elementwise
+extern "C" int slm_ctx_profile_read(slm_ctx* c, double* ms, long long* count) {
+    if (!c || !ms || !count) return fail(SLM_ERR_ARG, "slm_ctx_profile_read: null argument");
+    for (int k = 0; k < K_KINDS; ++k) { ms[k] = 0; count[k] = 0; }
+#ifndef SLM_EMULATE
+    SLM_CUDA(cudaSetDevice(c->device));
+    SLM_CUDA(cudaStreamSynchronize(c->stream));
+    for (auto& t : c->timed) {
+        float e = 0;
+        cudaEventElapsedTime(&e, t.a, t.b);
+        ms[t.kind] += e; count[t.kind]++;
+        cudaEventDestroy(t.a); cudaEventDestroy(t.b);
+    }
+    c->timed.clear();
+#endif
+    return 0;
+}
 extern "C" long long slm_ctx_launch_count(const slm_ctx* c) { return c ? c->launches : 0; }
 
 static int check_batch(slm_ctx* c, int batch, const char* who) {
@@ -189,17 +240,16 @@ static int setup_field(slm_ctx* c, int batch, const uint8_t* T8, const void* amp
         ra.input = IN_REAL; ra.in = amp_real;
         if (f32path && c->prec == PREC_F64) {   // narrow the float64 plane the way scipy's _asfarray does for float32 data
             const long long n = (long long)batch * c->H * c->W;
-            SLM_LAUNCH((convert_kernel<double, float>), dim3(ew_blocks(n)), dim3(kEwThreads), 0, c->stream,
-                       static_cast<const double*>(amp_real), static_cast<float*>(c->Y), n);
-            c->launches++;
+            { LaunchTimer t_(c, K_ELEMENTWISE); SLM_LAUNCH((convert_kernel<double, float>), dim3(ew_blocks(n)), dim3(kEwThreads), 0, c->stream,
+                       static_cast<const double*>(amp_real), static_cast<float*>(c->Y), n); }
             ra.in = c->Y;
         }
     }
-    SLM_TRY(row->row_plain(ra, c->stream)); c->launches++;
+    SLM_TIMED(K_ROW_PLAIN, row->row_plain(ra, c->stream));
     PlainColArgs ca{};
     ca.B = batch; ca.W = c->W; ca.output = OUT_COMPLEX; ca.inverse = 1; ca.scale = 1.0 / ((double)c->H * c->W);
     ca.in = c->X; ca.out = c->Y; ca.tw = f32path ? c->tw_col32 : c->tw_col;
-    SLM_TRY(col->col_plain(ca, c->stream)); c->launches++;
+    SLM_TIMED(K_COL_PLAIN, col->col_plain(ca, c->stream));
     *source = f32path ? ROW_FROM_A32 : ROW_FROM_A;
     return 0;
 }
@@ -217,12 +267,12 @@ extern "C" int slm_fft2(slm_ctx* c, int batch, const void* in, void* out, int in
     if (!in || !out) return fail(SLM_ERR_ARG, "slm_fft2: null plane");
     PlainRowArgs ra{};
     ra.B = batch; ra.H = c->H; ra.input = IN_COMPLEX; ra.inverse = inverse; ra.in = in; ra.out = c->X; ra.tw = c->tw_row;
-    SLM_TRY(c->row->row_plain(ra, c->stream)); c->launches++;
+    SLM_TIMED(K_ROW_PLAIN, c->row->row_plain(ra, c->stream));
     PlainColArgs ca{};
     ca.B = batch; ca.W = c->W; ca.output = OUT_COMPLEX; ca.inverse = inverse;
     ca.scale = inverse ? 1.0 / ((double)c->H * c->W) : 1.0;
     ca.in = c->X; ca.out = out; ca.tw = c->tw_col;
-    SLM_TRY(c->col->col_plain(ca, c->stream)); c->launches++;
+    SLM_TIMED(K_COL_PLAIN, c->col->col_plain(ca, c->stream));
     return 0;
 }
 
@@ -245,9 +295,9 @@ extern "C" int slm_gs_run(slm_ctx* c, int batch, const uint8_t* T8, const void* 
         SLM_TRY(setup_field(c, batch, T8, amp_real, setup_c64, &src));
         ra.source = src; ra.A32 = c->Y; ra.field = c->Y;
     }
-    SLM_TRY(c->row->row_pass(ALG_GS, ra, c->stream)); c->launches++;
+    SLM_TIMED(K_ROW_PASS, c->row->row_pass(ALG_GS, ra, c->stream));
     // exact scale of iteration 0 so the one-pass error of later iterations is well conditioned
-    SLM_TRY(c->col->col_plain(stats_args(c, batch, OUT_STATS, nullptr), c->stream)); c->launches++;
+    SLM_TIMED(K_COL_STATS, c->col->col_plain(stats_args(c, batch, OUT_STATS, nullptr), c->stream));
 
     ColArgs ca{};
     ca.B = batch; ca.W = c->W; ca.X = c->X; ca.Y = c->Y; ca.T8 = T8; ca.Treal = Treal; ca.plane2 = amp_real;
@@ -256,12 +306,12 @@ extern "C" int slm_gs_run(slm_ctx* c, int batch, const uint8_t* T8, const void* 
     ca.inv_hw = ra.inv_hw; ca.tw = c->tw_col;
     ra.source = ROW_FROM_Y;
     for (int k = 0; k < max_loops; ++k) {
-        SLM_TRY(c->col->col_pass(ALG_GS, ca, c->stream)); c->launches++;
-        if (k + 1 < max_loops) { SLM_TRY(c->row->row_pass(ALG_GS, ra, c->stream)); c->launches++; }
+        SLM_TIMED(K_COL_PASS, c->col->col_pass(ALG_GS, ca, c->stream));
+        if (k + 1 < max_loops) { SLM_TIMED(K_ROW_PASS, c->row->row_pass(ALG_GS, ra, c->stream)); }
     }
     ra.final_pass = 1;
-    SLM_TRY(c->row->row_pass(ALG_GS, ra, c->stream)); c->launches++;
-    if (expected_out) { SLM_TRY(c->col->col_plain(stats_args(c, batch, OUT_INTENSITY_GS, expected_out), c->stream)); c->launches++; }
+    SLM_TIMED(K_ROW_PASS, c->row->row_pass(ALG_GS, ra, c->stream));
+    if (expected_out) { SLM_TIMED(K_COL_PLAIN, c->col->col_plain(stats_args(c, batch, OUT_INTENSITY_GS, expected_out), c->stream)); }
     return 0;
 }
 
@@ -281,7 +331,7 @@ extern "C" int slm_gd_run(slm_ctx* c, int batch, const uint8_t* T8, const void* 
     ra.B = batch; ra.H = c->H; ra.Y = c->Y; ra.X = c->X; ra.x = x; ra.inc = inc_amp; ra.stats = c->stats; ra.lr = c->lr;
     ra.inv_hw = 1.0 / ((double)c->H * c->W); ra.hologram = hologram_out; ra.tw = c->tw_row;
     ra.source = ROW_FROM_FIELD;
-    SLM_TRY(c->row->row_pass(ALG_GD, ra, c->stream)); c->launches++;
+    SLM_TIMED(K_ROW_PASS, c->row->row_pass(ALG_GD, ra, c->stream));
 
     ColArgs ca{};
     ca.B = batch; ca.W = c->W; ca.X = c->X; ca.Y = c->Y; ca.T8 = T8; ca.Treal = Treal; ca.plane2 = mask_real;
@@ -291,13 +341,13 @@ extern "C" int slm_gd_run(slm_ctx* c, int batch, const uint8_t* T8, const void* 
     const PlainColArgs sa = stats_args(c, batch, OUT_STATS, nullptr);
     ra.source = ROW_FROM_Y;
     for (int k = 0; k < max_loops; ++k) {
-        SLM_TRY(c->col->col_plain(sa, c->stream)); c->launches++;            // amax(output_unnormed), algorithms.py:86
-        SLM_TRY(c->col->col_pass(ALG_GD, ca, c->stream)); c->launches++;
-        if (k + 1 < max_loops) { SLM_TRY(c->row->row_pass(ALG_GD, ra, c->stream)); c->launches++; }
+        SLM_TIMED(K_COL_STATS, c->col->col_plain(sa, c->stream));            // amax(output_unnormed), algorithms.py:86
+        SLM_TIMED(K_COL_PASS, c->col->col_pass(ALG_GD, ca, c->stream));
+        if (k + 1 < max_loops) { SLM_TIMED(K_ROW_PASS, c->row->row_pass(ALG_GD, ra, c->stream)); }
     }
     ra.final_pass = 1;
-    SLM_TRY(c->row->row_pass(ALG_GD, ra, c->stream)); c->launches++;
-    if (expected_out) { SLM_TRY(c->col->col_plain(stats_args(c, batch, OUT_INTENSITY_GD, expected_out), c->stream)); c->launches++; }
+    SLM_TIMED(K_ROW_PASS, c->row->row_pass(ALG_GD, ra, c->stream));
+    if (expected_out) { SLM_TIMED(K_COL_PLAIN, c->col->col_plain(stats_args(c, batch, OUT_INTENSITY_GD, expected_out), c->stream)); }
     return 0;
 }
 
@@ -310,16 +360,18 @@ extern "C" int slm_fourier_guess(slm_ctx* c, int batch, const uint8_t* T8, const
     SLM_TRY(setup_field(c, batch, T8, amp_real, setup_c64, &src));
     const long long plane = (long long)c->H * c->W, n = plane * batch;
     const dim3 grid(ew_blocks(n)), block(kEwThreads);
-    if (c->prec == PREC_F32)
-        SLM_LAUNCH((phasor_field_kernel<float, float>), grid, block, 0, c->stream, static_cast<const cpx<float>*>(c->Y),
-                   static_cast<const float*>(inc_amp), static_cast<cpx<float>*>(x_out), n, plane);
-    else if (src == ROW_FROM_A32)
-        SLM_LAUNCH((phasor_field_kernel<double, float>), grid, block, 0, c->stream, static_cast<const cpx<float>*>(c->Y),
-                   static_cast<const double*>(inc_amp), static_cast<cpx<double>*>(x_out), n, plane);
-    else
-        SLM_LAUNCH((phasor_field_kernel<double, double>), grid, block, 0, c->stream, static_cast<const cpx<double>*>(c->Y),
-                   static_cast<const double*>(inc_amp), static_cast<cpx<double>*>(x_out), n, plane);
-    c->launches++;
+    {
+        LaunchTimer t_(c, K_ELEMENTWISE);
+        if (c->prec == PREC_F32)
+            SLM_LAUNCH((phasor_field_kernel<float, float>), grid, block, 0, c->stream, static_cast<const cpx<float>*>(c->Y),
+                       static_cast<const float*>(inc_amp), static_cast<cpx<float>*>(x_out), n, plane);
+        else if (src == ROW_FROM_A32)
+            SLM_LAUNCH((phasor_field_kernel<double, float>), grid, block, 0, c->stream, static_cast<const cpx<float>*>(c->Y),
+                       static_cast<const double*>(inc_amp), static_cast<cpx<double>*>(x_out), n, plane);
+        else
+            SLM_LAUNCH((phasor_field_kernel<double, double>), grid, block, 0, c->stream, static_cast<const cpx<double>*>(c->Y),
+                       static_cast<const double*>(inc_amp), static_cast<cpx<double>*>(x_out), n, plane);
+    }
     SLM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -341,9 +393,9 @@ extern "C" int slm_expected_outcome(slm_ctx* c, int batch, const double* hologra
     SLM_TRY(begin_run(c, batch, norm, 1));
     PlainRowArgs ra{};
     ra.B = batch; ra.H = c->H; ra.input = IN_PHASE; ra.inverse = 0; ra.in = hologram; ra.out = c->X; ra.tw = c->tw_row;
-    SLM_TRY(c->row->row_plain(ra, c->stream)); c->launches++;
-    SLM_TRY(c->col->col_plain(stats_args(c, batch, OUT_STATS, nullptr), c->stream)); c->launches++;
-    SLM_TRY(c->col->col_plain(stats_args(c, batch, OUT_INTENSITY_PREVIEW, out), c->stream)); c->launches++;
+    SLM_TIMED(K_ROW_PLAIN, c->row->row_plain(ra, c->stream));
+    SLM_TIMED(K_COL_STATS, c->col->col_plain(stats_args(c, batch, OUT_STATS, nullptr), c->stream));
+    SLM_TIMED(K_COL_PLAIN, c->col->col_plain(stats_args(c, batch, OUT_INTENSITY_PREVIEW, out), c->stream));
     return 0;
 }
 
@@ -354,24 +406,21 @@ extern "C" int slm_expected_outcome(slm_ctx* c, int batch, const double* hologra
 extern "C" int slm_deflect_phase(slm_ctx* c, int H, int W, double konst, double sy, double sx, double* out) {
     SLM_EW_PROLOGUE("slm_deflect_phase");
     if (!out || H < 1 || W < 1) return fail(SLM_ERR_ARG, "slm_deflect_phase: bad argument");
-    SLM_LAUNCH(deflect_kernel, dim3(ew_blocks((long long)H * W)), dim3(kEwThreads), 0, c->stream, out, H, W, konst, sy, sx);
-    c->launches++;
+    { LaunchTimer t_(c, K_ELEMENTWISE); SLM_LAUNCH(deflect_kernel, dim3(ew_blocks((long long)H * W)), dim3(kEwThreads), 0, c->stream, out, H, W, konst, sy, sx); }
     SLM_CUDA(cudaGetLastError());
     return 0;
 }
 extern "C" int slm_lens_phase(slm_ctx* c, int H, int W, double px, double k, double f2, int trunc_u8, double* out) {
     SLM_EW_PROLOGUE("slm_lens_phase");
     if (!out || H < 1 || W < 1) return fail(SLM_ERR_ARG, "slm_lens_phase: bad argument");
-    SLM_LAUNCH(lens_kernel, dim3(ew_blocks((long long)H * W)), dim3(kEwThreads), 0, c->stream, out, H, W, px, k, f2, trunc_u8);
-    c->launches++;
+    { LaunchTimer t_(c, K_ELEMENTWISE); SLM_LAUNCH(lens_kernel, dim3(ew_blocks((long long)H * W)), dim3(kEwThreads), 0, c->stream, out, H, W, px, k, f2, trunc_u8); }
     SLM_CUDA(cudaGetLastError());
     return 0;
 }
 extern "C" int slm_add_mod2pi(slm_ctx* c, const double* a, const double* b, double* out, long long n, long long plane) {
     SLM_EW_PROLOGUE("slm_add_mod2pi");
     if (!a || !b || !out || n < 1 || plane < 1) return fail(SLM_ERR_ARG, "slm_add_mod2pi: bad argument");
-    SLM_LAUNCH(add_mod2pi_kernel, dim3(ew_blocks(n)), dim3(kEwThreads), 0, c->stream, a, b, out, n, plane);
-    c->launches++;
+    { LaunchTimer t_(c, K_ELEMENTWISE); SLM_LAUNCH(add_mod2pi_kernel, dim3(ew_blocks(n)), dim3(kEwThreads), 0, c->stream, a, b, out, n, plane); }
     SLM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -380,8 +429,7 @@ extern "C" int slm_quantize(slm_ctx* c, const double* phase, const double* mask,
     SLM_EW_PROLOGUE("slm_quantize");
     if (!phase || !out || n < 1 || plane < 1) return fail(SLM_ERR_ARG, "slm_quantize: bad argument");
     if (mode != QUANT_Q1 && mode != QUANT_Q2 && mode != QUANT_Q3 && mode != QUANT_PREVIEW) return fail(SLM_ERR_ARG, "slm_quantize: unknown mode");
-    SLM_LAUNCH(quantize_kernel, dim3(ew_blocks(n)), dim3(kEwThreads), 0, c->stream, phase, mask, ct2pi, mode, out, n, plane);
-    c->launches++;
+    { LaunchTimer t_(c, K_ELEMENTWISE); SLM_LAUNCH(quantize_kernel, dim3(ew_blocks(n)), dim3(kEwThreads), 0, c->stream, phase, mask, ct2pi, mode, out, n, plane); }
     SLM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -389,8 +437,7 @@ extern "C" int slm_quantize_grey(slm_ctx* c, const uint8_t* grey, const double* 
                                  long long n, long long plane) {
     SLM_EW_PROLOGUE("slm_quantize_grey");
     if (!grey || !mask || !out || n < 1 || plane < 1) return fail(SLM_ERR_ARG, "slm_quantize_grey: bad argument");
-    SLM_LAUNCH(quantize_grey_kernel, dim3(ew_blocks(n)), dim3(kEwThreads), 0, c->stream, grey, mask, ct2pi, out, n, plane);
-    c->launches++;
+    { LaunchTimer t_(c, K_ELEMENTWISE); SLM_LAUNCH(quantize_grey_kernel, dim3(ew_blocks(n)), dim3(kEwThreads), 0, c->stream, grey, mask, ct2pi, out, n, plane); }
     SLM_CUDA(cudaGetLastError());
     return 0;
 }

@@ -155,7 +155,7 @@ template <int N> struct FftPlan {
     static_assert(E * E * MID == N, "line length must be E*E*m");
     static_assert(MID == 1 || MID == 2 || MID == 3 || MID == 4 || MID == 8 || MID == 16, "unsupported line length");
     static_assert(MID <= E || MID == 3, "middle radix must fit the per-thread register tile");
-    static constexpr int pad(int i) { return i + i / E; }
+    SLM_HOSTDEV static constexpr int pad(int i) { return i + i / E; }
 };
 
 // Transform one line.  v[r] = x[j + r*M] on entry, X[j + r*M] on exit.  `line` points at the

@@ -1,0 +1,62 @@
+"""TEST INFRASTRUCTURE ONLY: drive the host emulation of the kernel sources (libslmholo_emu.so)
+through the package's own Engine class, with numpy arrays standing in for device buffers.
+
+Used by the CPU test-suite to check the kernels' logic against the oracle without a GPU.  The
+package never imports this module and never loads the emulation library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from spatial_light_modulator_module_b200 import _ffi
+from spatial_light_modulator_module_b200.engine import Engine
+
+from . import build_emu
+
+_LIB = None
+
+
+def emu_library():
+    global _LIB
+    if _LIB is None:
+        _LIB = _ffi.declare(C.CDLL(build_emu.build()))
+    return _LIB
+
+
+class HostBuf(np.ndarray):
+    """numpy array with the two tensor methods Engine uses on device buffers."""
+
+    def data_ptr(self):
+        return self.ctypes.data
+
+    def dim(self):
+        return self.ndim
+
+
+class EmuEngine(Engine):
+    def _load_library(self):
+        return emu_library()
+
+    def _mem_init(self, device):
+        return 0
+
+    def _mem_stream(self, stream):
+        return C.c_void_p(0)
+
+    def _mem_empty(self, shape, dtype):
+        return np.full(tuple(shape), 0xFF, dtype=np.uint8).repeat(np.dtype(dtype).itemsize).view(dtype).reshape(shape).view(HostBuf) \
+            if False else np.empty(tuple(shape), dtype=dtype).view(HostBuf)
+
+    def _mem_upload(self, array):
+        return np.array(array, copy=True, order="C").view(HostBuf)
+
+    def _mem_is_device(self, obj):
+        return isinstance(obj, HostBuf)
+
+    def _mem_download(self, buf):
+        return np.asarray(buf).copy()
+
+    def _mem_np_dtype(self, buf):
+        return buf.dtype

@@ -26,6 +26,7 @@ struct dim3 {
     dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
 typedef void* cudaStream_t;
+typedef void* cudaEvent_t;
 typedef int cudaError_t;
 enum { cudaSuccess = 0 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
@@ -176,6 +177,7 @@ inline Idx thread_idx() {
 #define SLM_HD inline
 #define SLM_DEV inline
 #define SLM_GLOBAL
+#define SLM_HOSTDEV
 #define SLM_LAUNCH_BOUNDS(t, b)
 #define SLM_DYN_SMEM(name) unsigned char* name = emu::S().smem
 #define SLM_STATIC_SMEM static

@@ -1,0 +1,70 @@
+"""CPU checks of the CUDA kernel SOURCES through their host emulation (tests/emu): the same
+.cu/.cuh files the product compiles with nvcc are compiled with g++ -DSLM_EMULATE and driven
+through the C ABI by the package's Engine class, then compared with the oracle and the golden
+fixtures.  This proves the kernels' logic (indexing, butterflies, fused pointwise steps,
+reductions, loop control) without a GPU; the `-m gpu` suite repeats the same checks on the B200.
+"""
+import pytest
+
+from tests import parity_checks as pc
+from tests.emu.emu_engine import EmuEngine
+
+
+def make_engine(shape, precision, max_batch):
+    return EmuEngine(shape, precision, max_batch)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+@pytest.mark.parametrize("shape", [(64, 64), (128, 192), (192, 256), (256, 512), (64, 768), (768, 64), (1024, 64),
+                                   (64, 2048), (64, 4096), (4096, 64)])
+def test_fft2_matches_scipy(shape, precision):
+    pc.check_fft2(make_engine, shape, precision)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+@pytest.mark.parametrize("kind", ["noise", "shapes"])
+@pytest.mark.parametrize("shape", [(128, 128), (192, 256)])
+def test_gs_teacher_forced(shape, kind, precision):
+    pc.check_gs_teacher_forced(make_engine, shape, precision, kind)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+@pytest.mark.parametrize("kind", ["noise", "shapes", "traps"])
+def test_gs_device_setup(kind, precision):
+    pc.check_gs_device_setup(make_engine, (128, 128), precision, kind)
+
+
+GD_CASES = ["gd_noise_random_128x128", "gd_shapes_fourier_192x256", "gd_traps_unsettle_128x128",
+            "gd_noise_wa2int_128x128", "gd_noise_wa05_128x128", "gd_shapes_old_128x128",
+            "gd_shapes_unnormed_128x128", "gd_shapes_zeros_128x128", "gd_shapes_ones_128x128",
+            "gd_traps_tol_128x128"]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+@pytest.mark.parametrize("name", GD_CASES)
+def test_gd_matches_reference_golden(golden, name, precision):
+    pc.check_gd_golden(make_engine, golden, name, precision)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_gs_tolerance_and_batch(precision):
+    pc.check_gs_tolerance_and_batch(make_engine, precision)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_gs_real_valued_targets(golden, precision):
+    pc.check_gs_real_targets(make_engine, golden, precision)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_illumination(precision):
+    pc.check_illumination(make_engine, precision)
+
+
+def test_analytic_and_quantisers_bit_exact(golden):
+    pc.check_analytic_and_quantisers(make_engine, golden)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_expected_outcome(golden, precision):
+    pc.check_expected_outcome(make_engine, golden, precision)

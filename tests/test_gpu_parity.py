@@ -1,0 +1,287 @@
+"""Parity tests proper: the CUDA library on a B200, called through the C ABI by the package's
+Engine / drop-in functions, against the CPU oracle and the reference-generated golden fixtures.
+Same checks as the emulation suite (tests/parity_checks.py) plus full-size and end-to-end cases.
+"""
+import argparse
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+from oracle import numpy_port as P
+from spatial_light_modulator_module_b200 import host_logic as hl, synthetic
+from tests import parity_checks as pc
+
+pytestmark = pytest.mark.gpu
+
+
+def make_engine(shape, precision, max_batch):
+    from spatial_light_modulator_module_b200.engine import Engine
+    return Engine(shape, precision, max_batch)
+
+
+def ns(**kw):
+    base = dict(incomming_intensity="uniform", tolerance=0, max_loops=10, gif=False, gif_skip=1, gif_type="i",
+                print_info=False, plot_error=False, initial_guess="random", random_seed=42, white_attention=1,
+                learning_rate=0.005, unsettle=0, correspond_to2pi=256)
+    base.update(kw)
+    return argparse.Namespace(**base)
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def test_native_library_is_the_compute_path():
+    import ctypes
+    from spatial_light_modulator_module_b200 import _ffi
+    lib = _ffi.load()
+    assert isinstance(lib, ctypes.CDLL) and lib.slm_version() >= 100
+    eng = make_engine((128, 128), "fp32", 1)
+    n0 = eng.launch_count()
+    eng.gs(synthetic.noise_target((128, 128)), 3)
+    assert eng.launch_count() - n0 == 3 + 2 + 2 * 3 - 1 + 1 + 1   # setup(2)+row+stats, 3 col, 2 row, final, intensity
+    eng.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+@pytest.mark.parametrize("shape", [(64, 64), (128, 192), (192, 256), (512, 512), (768, 1024), (1024, 1024),
+                                   (2048, 2048), (64, 4096), (4096, 64)])
+def test_fft2_matches_scipy(shape, precision):
+    pc.check_fft2(make_engine, shape, precision)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+@pytest.mark.parametrize("kind", ["noise", "shapes"])
+@pytest.mark.parametrize("shape", [(128, 128), (192, 256), (768, 1024)])
+def test_gs_teacher_forced(shape, kind, precision):
+    pc.check_gs_teacher_forced(make_engine, shape, precision, kind, steps=(0, 1, 4) if shape[0] < 768 else (0, 2))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+@pytest.mark.parametrize("kind", ["noise", "shapes", "traps"])
+def test_gs_device_setup(kind, precision):
+    pc.check_gs_device_setup(make_engine, (128, 128), precision, kind)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+@pytest.mark.parametrize("name", ["gd_noise_random_128x128", "gd_shapes_fourier_192x256", "gd_traps_unsettle_128x128",
+                                  "gd_noise_wa2int_128x128", "gd_noise_wa05_128x128", "gd_shapes_old_128x128",
+                                  "gd_shapes_unnormed_128x128", "gd_shapes_zeros_128x128", "gd_shapes_ones_128x128",
+                                  "gd_traps_tol_128x128"])
+def test_gd_matches_reference_golden(golden, name, precision):
+    pc.check_gd_golden(make_engine, golden, name, precision)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_gs_tolerance_and_batch(precision):
+    pc.check_gs_tolerance_and_batch(make_engine, precision)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_gs_real_valued_targets(golden, precision):
+    pc.check_gs_real_targets(make_engine, golden, precision)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_illumination(precision):
+    pc.check_illumination(make_engine, precision)
+
+
+def test_analytic_and_quantisers_bit_exact(golden):
+    pc.check_analytic_and_quantisers(make_engine, golden)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_expected_outcome(golden, precision):
+    pc.check_expected_outcome(make_engine, golden, precision)
+
+
+# ---- full-size cases against the reference's recorded curves (tests/golden/*_curves.npz) -------------
+def test_gd_full_size_curve_fp64(golden):
+    """Config 2 shape (768x1024, 100 iterations) free-running against the unmodified reference."""
+    g = golden("gd_noise_768x1024_curves")
+    t = synthetic.noise_target((768, 1024), seed=0)
+    holo, exp, errs = quiet(__import__("spatial_light_modulator_module_b200.algorithms", fromlist=["x"]).gradient_descent,
+                            t, ns(max_loops=100, precision="fp64"))
+    assert len(errs) == 100
+    assert np.max(np.abs(np.array(errs) - g["errors"]) / g["errors"]) < 1e-9
+    sub = (slice(None, None, 16), slice(None, None, 16))
+    assert pc.circ(holo[sub], g["hologram_sub"]).max() < 1e-8
+    assert np.abs(exp[sub] - g["expected_sub"]).max() < 1e-9 * g["expected_sub"].max()
+
+
+def test_gd_full_size_curve_fp32(golden):
+    g = golden("gd_noise_768x1024_curves")
+    t = synthetic.noise_target((768, 1024), seed=0)
+    from spatial_light_modulator_module_b200 import algorithms
+    holo, exp, errs = quiet(algorithms.gradient_descent, t, ns(max_loops=100, precision="fp32"))
+    assert np.max(np.abs(np.array(errs) - g["errors"]) / g["errors"]) < 1e-3
+    sub = (slice(None, None, 16), slice(None, None, 16))
+    d = pc.circ(holo[sub], g["hologram_sub"])
+    assert np.mean(d < 1e-3) >= 0.999                      # north star: 1e-3 rad
+    assert np.abs(exp[sub] - g["expected_sub"]).max() < 1e-3 * g["expected_sub"].max()   # north star: 1e-3
+
+
+def test_gs_traps_full_size_from_reference_phasor(golden):
+    """Trap movie frame (768x1024, 50 iterations): free-running from the reference's first phasor."""
+    g = golden("gs_traps_768x1024_curves")
+    pts = [tuple(p) for p in g["trap_points"]]
+    t = synthetic.traps_target((768, 1024), pts)
+    st = P.gs_setup(t)
+    B0 = P.gs_first_phasor(st)
+    for precision, tol in (("fp64", 1e-6), ("fp32", 1e-3)):
+        eng = make_engine((768, 1024), precision, 1)
+        res = eng.gs(t, 50, phasor0=B0)
+        e = res.errors[0]
+        assert len(e) == 50
+        assert np.max(np.abs(e - g["errors"]) / g["errors"]) < tol
+        eng.close()
+
+
+def test_gs_512_config1_statistics(golden):
+    """Config 1 (512x512, 20 iterations, dense noise): the trajectory is chaotic, so the
+    free-running device run is compared with the reference curve at the first iteration tightly
+    and at the end statistically."""
+    g = golden("gs_noise_512x512_curves")
+    from spatial_light_modulator_module_b200 import algorithms
+    t = synthetic.noise_target((512, 512), seed=0)
+    for precision in ("fp32", "fp64"):
+        holo, exp, errs = quiet(algorithms.gerchberg_saxton, t, ns(max_loops=20, precision=precision))
+        assert len(errs) == 20 and holo.shape == (512, 512) and holo.dtype == np.float64
+        assert abs(errs[0] - g["errors"][0]) < 1e-5 * g["errors"][0]
+        assert abs(errs[-1] - g["errors"][-1]) < 0.05 * g["errors"][-1]
+        assert all(isinstance(e, np.float64) for e in errs)
+
+
+# ---- size-independent properties at the bench sizes -------------------------------------------------
+@pytest.mark.parametrize("shape", [(1024, 1024), (2048, 2048)])
+def test_fft_roundtrip_and_parseval(shape):
+    eng = make_engine(shape, "fp32", 1)
+    rng = np.random.default_rng(1)
+    x = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(np.complex64)
+    X = eng.fft2(x)
+    xr = eng.to_host(eng.fft2(X, inverse=True))
+    assert np.abs(xr - x).max() < 5e-6 * np.abs(x).max()
+    Xh = eng.to_host(X).astype(np.complex128)
+    assert abs((np.abs(Xh) ** 2).sum() / (shape[0] * shape[1]) - (np.abs(x.astype(np.complex128)) ** 2).sum()) \
+        < 1e-5 * (np.abs(x) ** 2).sum()
+    eng.close()
+
+
+def test_gs_invariants_1024():
+    """At 1024^2: |hologram| <= pi, max(expected) == max(target), the returned error equals
+    error_f(expected, target) recomputed on the host, and the error decreases on a trap target."""
+    from spatial_light_modulator_module_b200 import algorithms
+    t = synthetic.traps_target((1024, 1024), [(300, 200), (700, 500), (512, 900)])
+    holo, exp, errs = quiet(algorithms.gerchberg_saxton, t, ns(max_loops=15, precision="fp32"))
+    assert np.all(np.abs(holo) <= np.pi)
+    assert abs(exp.max() - 255.0) < 1e-9
+    assert abs(algorithms.error_f(exp, t, t.size) - errs[-1]) < 1e-6 * errs[-1] + 1e-12
+    assert errs[-1] <= errs[0]
+    # the hologram really produces the expected outcome: |fft2(exp(i*h))|^2 peaks at the traps
+    from spatial_light_modulator_module_b200 import generate_hologram as gh
+    prev = gh.expected_outcome(holo, 255, precision="fp32")
+    top = np.argsort(prev.ravel())[-3:]
+    assert set(map(tuple, np.argwhere(t == 255))) == set(zip(*np.unravel_index(top, t.shape)))
+
+
+def test_batched_equals_single_1024():
+    eng = make_engine((768, 1024), "fp32", 4)
+    frames = synthetic.movie_frames(4)
+    res = eng.gs(frames, 8)
+    hb = eng.to_host(res.hologram)
+    for k in (0, 3):
+        r1 = eng.gs(frames[k], 8)
+        np.testing.assert_array_equal(eng.to_host(r1.hologram)[0], hb[k])
+        np.testing.assert_array_equal(r1.errors[0], res.errors[k])
+    eng.close()
+
+
+# ---- drop-in surface ----------------------------------------------------------------------------------
+def test_dropin_error_behaviour():
+    from spatial_light_modulator_module_b200 import algorithms
+    t = synthetic.traps_target((128, 128))
+    with pytest.raises(UnboundLocalError):
+        quiet(algorithms.gerchberg_saxton, t, ns(max_loops=0))
+    with pytest.raises(UnboundLocalError):
+        quiet(algorithms.gradient_descent, t, ns(max_loops=0))
+    with pytest.raises(ValueError, match="unknown type of initial guess"):
+        quiet(algorithms.gradient_descent, t, ns(initial_guess="nope"))
+    with pytest.raises(AttributeError):
+        a = ns()
+        del a.random_seed
+        quiet(algorithms.gradient_descent, t, a)
+    with pytest.raises(ZeroDivisionError):
+        quiet(algorithms.gradient_descent, t, ns(max_loops=1, unsettle=5))
+    with pytest.raises(ValueError):
+        quiet(algorithms.gerchberg_saxton, np.zeros((100, 100), np.uint8), ns())   # unsupported plane shape
+    # all-zero target: one iteration, error 0.0, zero hologram (algorithms.py:29 stops on `0 > 0`)
+    holo, exp, errs = quiet(algorithms.gerchberg_saxton, np.zeros((128, 128), np.uint8), ns(max_loops=7))
+    assert errs == [0.0] and not holo.any() and not exp.any()
+
+
+def test_dropin_unsettle_mutates_args(golden):
+    from spatial_light_modulator_module_b200 import algorithms
+    g = golden("gd_traps_unsettle_128x128")
+    a = ns(max_loops=12, unsettle=2, learning_rate=0.01, precision="fp64")
+    holo, exp, errs = quiet(algorithms.gradient_descent, g["target"], a)
+    assert a.learning_rate == float(g["final_learning_rate"])
+    assert np.max(np.abs(np.array(errs) - g["errors"]) / g["errors"]) < 1e-9
+
+
+def test_dropin_progress_output(capsys):
+    from spatial_light_modulator_module_b200 import algorithms
+    algorithms.gerchberg_saxton(synthetic.traps_target((128, 128)), ns(max_loops=4, print_info=True))
+    out = capsys.readouterr().out
+    assert "\rloop 4/4" in out and "number of loops: 4" in out and "error: " in out
+
+
+def test_dropin_analytic_and_display(golden, tmp_path):
+    from spatial_light_modulator_module_b200 import display_holograms as dh, generate_hologram as gh, wavefront_correction as wfc
+    g = golden("analytic")
+    sub = (slice(None, None, 16), slice(None, None, 16))
+    np.testing.assert_array_equal(wfc.deflect_2pi((1.0, 2.0))[sub], g["deflect_sub"])
+    ln = gh.lens(0.5, (768, 1024))
+    assert ln.dtype == np.uint8
+    np.testing.assert_array_equal(ln[sub], g["lens_sub"])
+    h0 = np.random.default_rng(int(g["h0_seed"])).uniform(-np.pi, np.pi, size=(768, 1024))
+    np.testing.assert_array_equal(gh.deflect_hologram(h0, (1.0, 2.0)), P.deflect_hologram(h0, (1.0, 2.0)))
+    np.testing.assert_array_equal(gh.add_lens(h0, 0.5), P.add_lens(h0, 0.5))
+    with pytest.raises(ValueError):
+        gh.deflect_hologram(np.zeros((128, 128)), (1.0, 2.0))
+    q = golden("quantize_96x128")
+    p = tmp_path / "h.npy"
+    np.save(p, q["hologram"])
+    np.testing.assert_array_equal(np.array(dh.mask_hologram(str(p), q["mask"], 256)), q["q2_rand_256"])
+    np.testing.assert_array_equal(wfc.convert_2pi_hologram_to_int_hologram(q["hologram_edge"], 255), q["q1_edge_255"])
+    np.testing.assert_array_equal(dh.hologram_to_grey(q["hologram"], q["mask"], 200), q["q3_rand_200"])
+    from PIL import Image as im
+    pp = tmp_path / "g.png"
+    im.fromarray(q["png"]).save(pp)
+    np.testing.assert_array_equal(np.array(dh.mask_hologram(str(pp), q["mask"], 200)), q["q2png_200"])
+
+
+def test_sequence_driver_files(tmp_path, monkeypatch):
+    """generate_hologram_sequence: PNG frames in, .npy holograms + preview PNGs out
+    (generate_hologram_sequence.py:10-32)."""
+    from PIL import Image as im
+    from spatial_light_modulator_module_b200 import generate_hologram_sequence as ghs
+    monkeypatch.chdir(tmp_path)
+    src = tmp_path / "images" / "moving_traps" / "seq"
+    src.mkdir(parents=True)
+    frames = synthetic.movie_frames(5, rescale_parameter=9.0)
+    for i, f in enumerate(frames):
+        im.fromarray(f).save(src / f"{i}.png")
+    a = ns(source_dir="seq", version="v1", max_loops=6, preview=True, precision="fp64", batch=2)
+    errors = quiet(ghs.generate_hologram_sequence, a)
+    assert len(errors) == 5 and all(len(e) == 6 for e in errors)
+    eng = make_engine((768, 1024), "fp64", 1)
+    for i in (0, 4):
+        h = np.load(tmp_path / "holograms" / "seq_v1_holograms" / f"{i}.npy")
+        r = eng.gs(frames[i], 6)
+        np.testing.assert_array_equal(h, eng.to_host(r.hologram)[0])
+        assert (tmp_path / "images" / "moving_traps" / "seq_v1_preview" / f"{i}.png").exists()
+    eng.close()

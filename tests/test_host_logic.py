@@ -1,0 +1,91 @@
+"""Host-side logic of the drop-in shims against numpy / the oracle / the reference goldens."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import numpy_port as P
+from spatial_light_modulator_module_b200 import host_logic as hl
+
+
+def test_amplitude_lut_is_numpys_float16_sqrt():
+    lut = hl.amplitude_lut()
+    t = np.arange(256, dtype=np.uint8)
+    assert np.sqrt(t).dtype == np.float16
+    np.testing.assert_array_equal(lut, np.abs(np.sqrt(t)).astype(np.float64))
+    assert lut[255] != np.sqrt(255.0)       # rounded to float16
+
+
+@pytest.mark.parametrize("wa", [1, 2, 0.5, np.float64(3.0)])
+def test_gd_mask_lut_follows_numpy_promotion(wa):
+    t = np.arange(256, dtype=np.uint8).reshape(16, 16)
+    np.testing.assert_array_equal(hl.gd_mask_lut(wa)[t], 1 + wa * t / 255)
+
+
+def test_classify_target():
+    rng = np.random.default_rng(0)
+    t8 = (rng.random((8, 8)) * 255).astype(np.uint8)
+    assert hl.classify_target(t8)[0] == "u8"
+    for dt, c64 in ((np.float64, False), (np.float32, True), (np.uint16, True), (np.int32, False)):
+        kind, treal, amp, flag = hl.classify_target(t8.astype(dt))
+        st = P.gs_setup(t8.astype(dt))
+        assert kind == "real" and flag == c64 == (st.A.dtype == np.complex64)
+        np.testing.assert_array_equal(amp, np.abs(st.target_amp).astype(np.float64))
+
+
+@pytest.mark.parametrize("lr,unsettle,loops", [(0.005, 0, 10), (0.01, 2, 12), (0.01, 3, 10), (0.5, 1, 5), (0.1, 4, 30)])
+def test_learning_rate_schedule_matches_oracle(lr, unsettle, loops):
+    during, after = hl.learning_rate_schedule(lr, unsettle, loops)
+    st = P.gd_setup(np.ones((4, 4), np.uint8), learning_rate=lr, unsettle=unsettle, max_loops=loops, x0=np.ones((4, 4)))
+    for k in range(loops):
+        assert during[k] == st.learning_rate
+        st.i += 1
+        if st.unsettle and st.i % int(round(st.max_loops / (st.unsettle + 1))) == 0:
+            st.learning_rate *= 2
+        assert after[k + 1] == st.learning_rate
+
+
+def test_learning_rate_schedule_zero_period():
+    with pytest.raises(ZeroDivisionError):
+        hl.learning_rate_schedule(0.1, 5, 1)
+
+
+def test_initial_guesses_match_reference(golden):
+    g = golden("initial_guess_24x40")
+    shape = g["target"].shape
+    for kind in ("random", "old", "unnormed", "zeros", "ones"):
+        np.testing.assert_array_equal(hl.host_initial_guess(kind, shape, 42), g[kind])
+    np.testing.assert_array_equal(hl.host_initial_guess("random", shape, 7), g["random_seed7"])
+    np.testing.assert_array_equal(hl.host_initial_guess("random", shape, 42.0), g["random_seed_float"])
+    np.testing.assert_array_equal(hl.host_initial_guess("random", shape, 2**40 + 12345), g["random_seed_big"])
+    assert hl.host_initial_guess("fourier", shape, 1) is None
+    with pytest.raises(ValueError, match="unknown type of initial guess"):
+        hl.host_initial_guess("nope", shape, 1)
+
+
+def test_random_stream_leaves_module_state_like_the_reference_loop():
+    u = hl.python_random_stream(123, 1000)
+    after = random.random()
+    random.seed(123)
+    ref = [random.random() for _ in range(1000)]
+    np.testing.assert_array_equal(u, ref)
+    assert after == random.random()
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 8, 1024, 1025):
+        for world in (1, 2, 3, 8):
+            blocks = [hl.shard_range(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = [h - l for l, h in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_scalars():
+    from spatial_light_modulator_module_b200 import constants as c
+    const, sy, sx = hl.deflect_scalars((1.0, 2.0), c.px_distance, c.wavelength, c.u)
+    assert const == 2 * np.pi * c.px_distance / c.wavelength
+    assert sy == np.sin(2.0 * c.u) and sx == np.sin(1.0 * c.u)
+    k, f2 = hl.lens_scalars(0.5, c.wavelength)
+    assert k == 2 * np.pi * 0.5 / c.wavelength and f2 == 0.25
