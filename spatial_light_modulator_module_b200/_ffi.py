@@ -63,6 +63,10 @@ def load() -> C.CDLL:
     """The CUDA library, loaded once.  Raises if it has not been built."""
     global _lib
     if _lib is None:
+        path = os.environ.get("SLM_HOLO_LIB", LIB_PATH)      # another BUILD of the same CUDA library (tuning variants)
+        if path != LIB_PATH:
+            _lib = declare(C.CDLL(path))
+            return _lib
         if not os.path.exists(LIB_PATH):
             raise EngineError(
                 f"{LIB_PATH} is missing: build it with `python -m spatial_light_modulator_module_b200.build` "

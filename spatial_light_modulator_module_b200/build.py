@@ -44,17 +44,24 @@ def up_to_date() -> bool:
     return all(os.path.getmtime(s) <= t for s in _sources())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if up_to_date() and not force:
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = None, lengths=None) -> str:
+    """``defines``/``out``/``lengths`` build a tuning variant (e.g. -DSLM_TCMAX_F32=4) beside the product library."""
+    global OBJ, LIB
+    if out is None and up_to_date() and not force:
         return LIB
+    obj_dir, lib = (OBJ, LIB) if out is None else (os.path.join(HERE, "lib", "obj_" + os.path.basename(out)), out)
+    return _build(force, verbose, list(defines), obj_dir, lib, lengths)
+
+
+def _build(force, verbose, defines, OBJ, LIB, lengths):
     os.makedirs(OBJ, exist_ok=True)
     cc = nvcc()
-    base = [cc, "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-I", CSRC] + ARCH
+    base = [cc, "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-I", CSRC] + ARCH + defines
     if verbose:
         base += ["-Xptxas", "-v"]
     jobs = [(os.path.join(CSRC, "engine.cu"), os.path.join(OBJ, "engine.o"), []),
             (os.path.join(CSRC, "registry.cu"), os.path.join(OBJ, "registry.o"), [])]
-    for n in line_lengths():
+    for n in (lengths or line_lengths()):
         for p in (0, 1):
             jobs.append((os.path.join(CSRC, "line_inst.cu"), os.path.join(OBJ, f"line_{n}_{p}.o"),
                          [f"-DSLM_LINE_L={n}", f"-DSLM_LINE_PREC={p}"]))

@@ -19,7 +19,7 @@
 #define SLM_HOSTDEV __host__ __device__
 #define SLM_LAUNCH_BOUNDS(t, b) __launch_bounds__(t, b)
 // dynamic shared memory of the running CTA
-#define SLM_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define SLM_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
 #define SLM_STATIC_SMEM __shared__
 #define SLM_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #define SLM_RESTRICT __restrict__
@@ -32,6 +32,7 @@ SLM_DEV void fence_device() { __threadfence(); }
 SLM_DEV unsigned atomic_inc_wrap(unsigned* p, unsigned limit) { return atomicInc(p, limit); }
 SLM_DEV float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 SLM_DEV double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+SLM_DEV unsigned shfl_idx(unsigned v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 SLM_DEV void sync_cta() { __syncthreads(); }
 // IEEE operations that must not be contracted into FMAs (bit parity with numpy)
 SLM_DEV double mul_rn(double a, double b) { return __dmul_rn(a, b); }

@@ -9,6 +9,7 @@
 // needs no host round trip per iteration.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -50,6 +51,10 @@ struct slm_ctx {
     size_t bytes = 0;
     long long launches = 0;
     std::vector<void*> owned;
+    // TMA tile map over X for the persistent column kernels (context precision), and their grid
+    TileMap tile_map;
+    bool use_tma = false;
+    int persist_ctas = 1;
     // optional per-launch device timing (slm_ctx_profile): event pairs on the context's stream
     bool profiling = false;
     struct Timed { int kind; cudaEvent_t a, b; };
@@ -104,6 +109,46 @@ static int make_twiddles(slm_ctx* c, int N, int prec, void** out) {
     SLM_TRY(dev_alloc(c, out, bytes));
     SLM_CUDA(cudaMemcpy(*out, prec == PREC_F64 ? (const void*)td.data() : (const void*)tf.data(), bytes, cudaMemcpyHostToDevice));
     return 0;
+}
+
+// Describe X ([max_batch*H rows][W complex columns]) to the TMA unit: 2-D tensor of real elements,
+// box = TC complex columns x up to 256 rows, dense (unswizzled) shared-memory image.
+static int make_tile_map(slm_ctx* c) {
+    const size_t cs = 2 * real_size(c->prec);
+    const int tc = c->col->cols_per_cta;
+#ifdef SLM_EMULATE
+    c->tile_map.base = static_cast<const unsigned char*>(c->X);
+    c->tile_map.pitch_bytes = (size_t)c->W * cs;
+    c->tile_map.col_bytes = (int)cs;
+    c->tile_map.box_rows = c->H < 256 ? c->H : 256;
+    c->persist_ctas = 3;
+    c->use_tma = getenv("SLM_NO_TMA") == nullptr;
+    return 0;
+#else
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    SLM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) return fail(SLM_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    const int box_rows = c->H < 256 ? c->H : 256;
+    const cuuint64_t dims[2] = {(cuuint64_t)2 * c->W, (cuuint64_t)c->max_batch * c->H};
+    const cuuint64_t strides[1] = {(cuuint64_t)c->W * cs};
+    const cuuint32_t box[2] = {(cuuint32_t)(2 * tc), (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = reinterpret_cast<EncodeFn>(fn)(
+        &c->tile_map.map, c->prec == PREC_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c->X,
+        dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SLM_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    c->tile_map.box_rows = box_rows;
+    int sms = 0;
+    SLM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    c->persist_ctas = sms > 0 ? sms : 1;
+    c->use_tma = getenv("SLM_NO_TMA") == nullptr;
+    return 0;
+#endif
 }
 
 static int ensure_loops(slm_ctx* c, int max_loops) {
@@ -165,6 +210,7 @@ extern "C" int slm_ctx_create(slm_ctx** out, int device, int H, int W, int max_b
     if (!rc && precision == PREC_F64) { rc = make_twiddles(c, W, PREC_F32, &c->tw_row32); if (!rc) rc = make_twiddles(c, H, PREC_F32, &c->tw_col32); }
     if (!rc && precision == PREC_F32) { c->tw_row32 = c->tw_row; c->tw_col32 = c->tw_col; }
     if (!rc) rc = ensure_loops(c, 256);
+    if (!rc) rc = make_tile_map(c);
     if (!rc && cudaMemset(c->counter, 0, (size_t)max_batch * sizeof(unsigned)) != cudaSuccess) rc = fail(SLM_ERR_CUDA, "cudaMemset(counter)");
     if (!rc && cudaMemset(c->stats, 0, (size_t)max_batch * sizeof(PlaneStats)) != cudaSuccess) rc = fail(SLM_ERR_CUDA, "cudaMemset(stats)");
     if (rc) { std::string keep = g_err; slm_ctx_destroy(c); g_err = keep; return rc; }
@@ -249,6 +295,7 @@ static int setup_field(slm_ctx* c, int batch, const uint8_t* T8, const void* amp
     PlainColArgs ca{};
     ca.B = batch; ca.W = c->W; ca.output = OUT_COMPLEX; ca.inverse = 1; ca.scale = 1.0 / ((double)c->H * c->W);
     ca.in = c->X; ca.out = c->Y; ca.tw = f32path ? c->tw_col32 : c->tw_col;
+    if (c->use_tma && col == c->col) { ca.tile_map = &c->tile_map; ca.persist_ctas = c->persist_ctas; }
     SLM_TIMED(K_COL_PLAIN, col->col_plain(ca, c->stream));
     *source = f32path ? ROW_FROM_A32 : ROW_FROM_A;
     return 0;
@@ -259,6 +306,7 @@ static PlainColArgs stats_args(slm_ctx* c, int batch, int output, void* out) {
     a.B = batch; a.W = c->W; a.output = output; a.inverse = 0; a.scale = 1.0;
     a.in = c->X; a.out = out; a.norm = c->norm; a.stats = c->stats; a.partial = c->partial; a.counter = c->counter;
     a.tw = c->tw_col;
+    if (c->use_tma) { a.tile_map = &c->tile_map; a.persist_ctas = c->persist_ctas; }
     return a;
 }
 
@@ -272,6 +320,7 @@ extern "C" int slm_fft2(slm_ctx* c, int batch, const void* in, void* out, int in
     ca.B = batch; ca.W = c->W; ca.output = OUT_COMPLEX; ca.inverse = inverse;
     ca.scale = inverse ? 1.0 / ((double)c->H * c->W) : 1.0;
     ca.in = c->X; ca.out = out; ca.tw = c->tw_col;
+    if (c->use_tma) { ca.tile_map = &c->tile_map; ca.persist_ctas = c->persist_ctas; }
     SLM_TIMED(K_COL_PLAIN, c->col->col_plain(ca, c->stream));
     return 0;
 }
@@ -304,6 +353,7 @@ extern "C" int slm_gs_run(slm_ctx* c, int batch, const uint8_t* T8, const void* 
     ca.lut = c->lut; ca.norm = c->norm; ca.stats = c->stats; ca.partial = c->partial; ca.counter = c->counter;
     ca.err_curve = c->err_curve; ca.max_loops = max_loops; ca.tolerance = tolerance;
     ca.inv_hw = ra.inv_hw; ca.tw = c->tw_col;
+    if (c->use_tma) { ca.tile_map = &c->tile_map; ca.persist_ctas = c->persist_ctas; }
     ra.source = ROW_FROM_Y;
     for (int k = 0; k < max_loops; ++k) {
         SLM_TIMED(K_COL_PASS, c->col->col_pass(ALG_GS, ca, c->stream));
@@ -338,6 +388,7 @@ extern "C" int slm_gd_run(slm_ctx* c, int batch, const uint8_t* T8, const void* 
     ca.lut = c->lut; ca.norm = c->norm; ca.stats = c->stats; ca.partial = c->partial; ca.counter = c->counter;
     ca.err_curve = c->err_curve; ca.max_loops = max_loops; ca.tolerance = tolerance;
     ca.inv_hw = ra.inv_hw; ca.tw = c->tw_col;
+    if (c->use_tma) { ca.tile_map = &c->tile_map; ca.persist_ctas = c->persist_ctas; }
     const PlainColArgs sa = stats_args(c, batch, OUT_STATS, nullptr);
     ra.source = ROW_FROM_Y;
     for (int k = 0; k < max_loops; ++k) {

@@ -64,6 +64,8 @@ struct ColArgs {
     double tolerance;
     double inv_hw;
     const void* tw;          // complex<R> [H] column twiddles
+    const void* tile_map;    // host TileMap* over X (tma.cuh) -> persistent TMA kernel; null -> one CTA per tile
+    int persist_ctas;        // resident CTAs of the persistent kernel
 };
 
 // ---- plain transforms / setup / preview ------------------------------------------------------
@@ -102,6 +104,8 @@ struct PlainColArgs {
     Partial* partial;
     unsigned* counter;
     const void* tw;
+    const void* tile_map;    // host TileMap* over `in` or null (see ColArgs)
+    int persist_ctas;
 };
 
 // ---- launch table: one entry per (line length, precision), see gen_lines.py ----------------------

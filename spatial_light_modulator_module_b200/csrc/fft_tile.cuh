@@ -10,6 +10,12 @@
 // inverse-FFT -> pointwise -> forward-FFT chain therefore never leaves registers between the
 // two transforms, and global loads/stores are always unit-stride across threads.)
 //
+// Arithmetic: a complex number is one 64-bit register pair.  In fp32 every complex add, real
+// scaling and complex multiply is issued as Blackwell's packed FADD2 / FMUL2 / FFMA2
+// (PTX add/mul/fma.rn.f32x2): ptxas folds the half swaps, broadcasts and per-half negations of
+// the formulas below into operand modifiers, so a complex multiply is 2 instructions and a
+// radix-4 butterfly 8.  All shared-memory addresses are (per-thread base) + (compile-time offset).
+//
 // Replaces scipy.fft.fft2/ifft2 (pocketfft/DUCC) at the reference call sites
 // algorithms.py:27,31,34,84,88,155 and generate_hologram.py:25.  Convention follows scipy:
 // forward unnormalised; the 1/(H*W) of the inverse is applied by the caller where it matters.
@@ -40,38 +46,73 @@ template <typename R> SLM_DEV cpx<R> ld_const(const cpx<R>* p) {
     cpx<R> r; r.x = v.x; r.y = v.y; return r;
 }
 
-template <typename R> SLM_DEV cpx<R> cadd(cpx<R> a, cpx<R> b) { cpx<R> r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
-template <typename R> SLM_DEV cpx<R> csub(cpx<R> a, cpx<R> b) { cpx<R> r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
-template <typename R> SLM_DEV cpx<R> cmul(cpx<R> a, cpx<R> b) {
-    cpx<R> r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
+// ---- packed pair arithmetic: (x, y) lanes ---------------------------------------------------
+template <typename R> SLM_DEV cpx<R> mk(R x, R y) { cpx<R> r; r.x = x; r.y = y; return r; }
+template <typename R> SLM_DEV cpx<R> pk_add(cpx<R> a, cpx<R> b) { return mk<R>(a.x + b.x, a.y + b.y); }
+template <typename R> SLM_DEV cpx<R> pk_mul(cpx<R> a, cpx<R> b) { return mk<R>(a.x * b.x, a.y * b.y); }
+template <typename R> SLM_DEV cpx<R> pk_fma(cpx<R> a, cpx<R> b, cpx<R> c) { return mk<R>(a.x * b.x + c.x, a.y * b.y + c.y); }
+#if defined(__CUDA_ARCH__) && !defined(SLM_EMULATE)
+SLM_DEV unsigned long long pk_bits(cpx<float> a) {
+    unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y)); return r;
+}
+SLM_DEV cpx<float> pk_val(unsigned long long v) {
+    cpx<float> r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r;
+}
+SLM_DEV cpx<float> pk_add(cpx<float> a, cpx<float> b) {
+    unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk_bits(a)), "l"(pk_bits(b))); return pk_val(r);
+}
+SLM_DEV cpx<float> pk_mul(cpx<float> a, cpx<float> b) {
+    unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk_bits(a)), "l"(pk_bits(b))); return pk_val(r);
+}
+SLM_DEV cpx<float> pk_fma(cpx<float> a, cpx<float> b, cpx<float> c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk_bits(a)), "l"(pk_bits(b)), "l"(pk_bits(c)));
+    return pk_val(r);
+}
+#endif
+
+template <typename R> SLM_DEV cpx<R> cadd(cpx<R> a, cpx<R> b) { return pk_add(a, b); }
+template <typename R> SLM_DEV cpx<R> csub(cpx<R> a, cpx<R> b) { return pk_add(a, mk<R>(-b.x, -b.y)); }
+// a * w = a.x*(w.x, w.y) + a.y*(-w.y, w.x)
+template <typename R> SLM_DEV cpx<R> cmul(cpx<R> a, cpx<R> w) {
+    const cpx<R> t = pk_mul(mk<R>(a.y, a.y), mk<R>(w.y, w.x));
+    return pk_fma(mk<R>(a.x, a.x), w, mk<R>(-t.x, t.y));
 }
 template <typename R> SLM_DEV cpx<R> cconj(cpx<R> a) { a.y = -a.y; return a; }
-template <typename R> SLM_DEV cpx<R> cscale(cpx<R> a, R s) { a.x *= s; a.y *= s; return a; }
+template <typename R> SLM_DEV cpx<R> cscale(cpx<R> a, R s) { return pk_mul(a, mk<R>(s, s)); }
+// squared modulus and its two halves
+template <typename R> SLM_DEV R cnorm2(cpx<R> a) { const cpx<R> q = pk_mul(a, a); return q.x + q.y; }
 
 // multiply by exp(DIR * i * pi/2): DIR=-1 (forward) -> -i ; DIR=+1 (inverse) -> +i
 template <int DIR, typename R> SLM_DEV cpx<R> rot90(cpx<R> a) {
-    cpx<R> r;
-    if (DIR < 0) { r.x = a.y; r.y = -a.x; } else { r.x = -a.y; r.y = a.x; }
-    return r;
+    return DIR < 0 ? mk<R>(a.y, -a.x) : mk<R>(-a.y, a.x);
 }
 // multiply by exp(DIR * 2*pi*i * P/16)
 template <int DIR, int P, typename R> SLM_DEV cpx<R> mul_w16(cpx<R> a) {
     constexpr int p = ((P % 16) + 16) % 16;
     if constexpr (p == 0) return a;
     else if constexpr (p == 4) return rot90<DIR>(a);
-    else if constexpr (p == 8) { a.x = -a.x; a.y = -a.y; return a; }
+    else if constexpr (p == 8) return mk<R>(-a.x, -a.y);
     else if constexpr (p == 12) return rot90<-DIR>(a);
-    else {
-        constexpr double C[16] = {1.0, 0.92387953251128673848, 0.70710678118654752440, 0.38268343236508977173,
-                                  0.0, -0.38268343236508977173, -0.70710678118654752440, -0.92387953251128673848,
-                                  -1.0, -0.92387953251128673848, -0.70710678118654752440, -0.38268343236508977173,
-                                  0.0, 0.38268343236508977173, 0.70710678118654752440, 0.92387953251128673848};
-        constexpr double S[16] = {0.0, 0.38268343236508977173, 0.70710678118654752440, 0.92387953251128673848,
-                                  1.0, 0.92387953251128673848, 0.70710678118654752440, 0.38268343236508977173,
-                                  0.0, -0.38268343236508977173, -0.70710678118654752440, -0.92387953251128673848,
-                                  -1.0, -0.92387953251128673848, -0.70710678118654752440, -0.38268343236508977173};
-        const R c = (R)C[p], s = (R)(DIR < 0 ? -S[p] : S[p]);
-        cpx<R> r; r.x = a.x * c - a.y * s; r.y = a.x * s + a.y * c; return r;
+    else if constexpr (p % 2 == 0) {
+        // odd multiples of pi/4: (cos, sin) = (+-h, +-h):  a*(c + i s) = (c*a.x - s*a.y, s*a.x + c*a.y)
+        constexpr double h = 0.70710678118654752440;
+        constexpr double C = (p == 2 || p == 14) ? h : -h;
+        constexpr double S0 = (p == 2 || p == 6) ? h : -h;
+        constexpr double S = DIR < 0 ? -S0 : S0;
+        // = h * ( sc*a.x - ss*a.y, ss*a.x + sc*a.y ) with signs sc, ss
+        const cpx<R> u = (C > 0) == (S > 0) ? pk_add(a, mk<R>(-a.y, a.x)) : pk_add(a, mk<R>(a.y, -a.x));
+        return pk_mul(u, mk<R>((R)C, (R)C));
+    } else {
+        constexpr double CS[16] = {1.0, 0.92387953251128673848, 0.70710678118654752440, 0.38268343236508977173,
+                                   0.0, -0.38268343236508977173, -0.70710678118654752440, -0.92387953251128673848,
+                                   -1.0, -0.92387953251128673848, -0.70710678118654752440, -0.38268343236508977173,
+                                   0.0, 0.38268343236508977173, 0.70710678118654752440, 0.92387953251128673848};
+        constexpr double SN[16] = {0.0, 0.38268343236508977173, 0.70710678118654752440, 0.92387953251128673848,
+                                   1.0, 0.92387953251128673848, 0.70710678118654752440, 0.38268343236508977173,
+                                   0.0, -0.38268343236508977173, -0.70710678118654752440, -0.92387953251128673848,
+                                   -1.0, -0.92387953251128673848, -0.70710678118654752440, -0.38268343236508977173};
+        return cmul(a, mk<R>((R)CS[p], (R)(DIR < 0 ? -SN[p] : SN[p])));
     }
 }
 
@@ -81,15 +122,15 @@ template <int DIR, typename R> SLM_DEV void dft2(cpx<R>& a, cpx<R>& b) {
 }
 template <int DIR, typename R> SLM_DEV void dft3(cpx<R>& a, cpx<R>& b, cpx<R>& c) {
     const R h = (R)0.86602540378443864676;          // sin(2*pi/3)
-    cpx<R> s = cadd(b, c), d = csub(b, c);
-    cpx<R> m; m.x = a.x - (R)0.5 * s.x; m.y = a.y - (R)0.5 * s.y;
-    cpx<R> q = rot90<DIR>(d); q.x *= h; q.y *= h;    // DIR * i * sin(2pi/3) * (b - c)
+    const cpx<R> s = cadd(b, c), d = csub(b, c);
+    const cpx<R> m = pk_fma(mk<R>((R)-0.5, (R)-0.5), s, a);
+    const cpx<R> q = pk_mul(rot90<DIR>(d), mk<R>(h, h));   // DIR * i * sin(2pi/3) * (b - c)
     a = cadd(a, s);
     b = cadd(m, q);
     c = csub(m, q);
 }
 template <int DIR, typename R> SLM_DEV void dft4(cpx<R>& a0, cpx<R>& a1, cpx<R>& a2, cpx<R>& a3) {
-    cpx<R> t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = rot90<DIR>(csub(a1, a3));
+    const cpx<R> t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = rot90<DIR>(csub(a1, a3));
     a0 = cadd(t0, t2); a1 = cadd(t1, t3); a2 = csub(t0, t2); a3 = csub(t1, t3);
 }
 template <int DIR, typename R> SLM_DEV void dft8(cpx<R>* v) {
@@ -136,14 +177,11 @@ template <int DIR, typename R> SLM_DEV cpx<R> tw_load(const cpx<R>* tw, int q) {
     if (DIR > 0) w.y = -w.y;
     return w;
 }
-// v[r] *= w^r for r = 1..RAD-1, with w^r built by a depth-log2 product tree (error ~ log2(RAD) ulp)
-template <int RAD, typename R> SLM_DEV void apply_twiddle_powers(cpx<R>* v, cpx<R> w1) {
-    cpx<R> w[RAD > 1 ? RAD : 2];
+// w[r] = w1^r for r = 1..RAD-1 by a depth-log2 product tree (error ~ log2(RAD) ulp)
+template <int RAD, typename R> SLM_DEV void twiddle_powers(cpx<R>* w, cpx<R> w1) {
     w[1] = w1;
 #pragma unroll
     for (int r = 2; r < RAD; ++r) w[r] = cmul(w[r / 2], w[r - r / 2]);
-#pragma unroll
-    for (int r = 1; r < RAD; ++r) v[r] = cmul(v[r], w[r]);
 }
 
 // ---- line FFT ----------------------------------------------------------------------------
@@ -159,61 +197,69 @@ template <int N> struct FftPlan {
 };
 
 // Transform one line.  v[r] = x[j + r*M] on entry, X[j + r*M] on exit.  `line` points at the
-// line's element 0 in shared memory; element i lives at line[pad(i) * STRIDE].  Every thread of
-// the CTA must call this together (it contains __syncthreads()).
+// line's element 0 in shared memory; element i lives at line[pad(i) * STRIDE], pad(i) = i + i/E.
+// Every thread of the CTA must call this together (it contains CTA barriers).
+//
+// Address algebra (M = MID*E, so every index below splits into a per-thread base and a
+// compile-time offset):
+//   stage-1 store   j*E + r                    -> pad = j*(E+1) + r
+//   loads           j + e*M                    -> pad = (j + j/E) + e*(M + MID)
+//   middle store    (j/E + q*MID)*E*MID + j%E + r*E
+//                                              -> pad = (j/E)*(E*MID+MID) + j%E + q*MID*(E*MID+MID) + r*(E+1)
 template <typename R, int N, int DIR, int STRIDE>
-SLM_DEV void line_fft(cpx<R>* v, cpx<R>* line, int j, const cpx<R>* __restrict__ tw) {
+SLM_DEV void line_fft(cpx<R>* v, cpx<R>* line, int j, const cpx<R>* SLM_RESTRICT tw) {
     using P = FftPlan<N>;
     constexpr int E = P::E, M = P::M, MID = P::MID;
+    constexpr int EP = E + 1, MP = M + MID, BLK = E * MID + MID;
+    cpx<R>* const st1 = line + (j * EP) * STRIDE;
+    cpx<R>* const ldp = line + (j + j / E) * STRIDE;
 
     // stage 1 (Ns = 1): no twiddles; butterfly output r goes to position j*E + r
     dft_small<E, DIR>(v);
 #pragma unroll
-    for (int r = 0; r < E; ++r) line[P::pad(j * E + r) * STRIDE] = v[r];
+    for (int r = 0; r < E; ++r) st1[r * STRIDE] = v[r];
     sync_cta();
 
-    if constexpr (MID > 1 && MID != 3) {
-        constexpr int Q = E / MID;          // butterflies per thread
-        constexpr int Ns = E;
+    if constexpr (MID > 1) {
+        const int jh = j / E, jl = j % E;
+        cpx<R>* const stm = line + (jh * BLK + jl) * STRIDE;
+        cpx<R> w[MID];
+        twiddle_powers<MID>(w, tw_load<DIR>(tw, jl * E));      // exp(-+2 pi i jl / (E*MID)), same for every q
+        if constexpr (MID != 3) {
+            constexpr int Q = E / MID;                           // butterflies per thread
 #pragma unroll
-        for (int e = 0; e < E; ++e) v[e] = line[P::pad(j + e * M) * STRIDE];
-        sync_cta();
+            for (int e = 0; e < E; ++e) v[e] = ldp[e * MP * STRIDE];
+            sync_cta();
 #pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            const int b = j + q * M;
-            const int k = b % Ns;
-            cpx<R> a[MID];
+            for (int q = 0; q < Q; ++q) {
+                cpx<R> a[MID];
+                a[0] = v[q];
 #pragma unroll
-            for (int r = 0; r < MID; ++r) a[r] = v[q + r * Q];
-            apply_twiddle_powers<MID>(a, tw_load<DIR>(tw, k * (N / (Ns * MID))));
-            dft_small<MID, DIR>(a);
-            const int o = (b / Ns) * (Ns * MID) + k;
+                for (int r = 1; r < MID; ++r) a[r] = cmul(v[q + r * Q], w[r]);
+                dft_small<MID, DIR>(a);
 #pragma unroll
-            for (int r = 0; r < MID; ++r) line[P::pad(o + r * Ns) * STRIDE] = a[r];
-        }
-        sync_cta();
-    } else if constexpr (MID == 3) {
-        constexpr int NB = N / 3, QMAX = (NB + M - 1) / M, Ns = E;
-        cpx<R> a[QMAX][3];
-#pragma unroll
-        for (int q = 0; q < QMAX; ++q) {
-            const int b = j + q * M;
-            if (b < NB) {
-#pragma unroll
-                for (int r = 0; r < 3; ++r) a[q][r] = line[P::pad(b + r * NB) * STRIDE];
+                for (int r = 0; r < MID; ++r) stm[(q * MID * BLK + r * EP) * STRIDE] = a[r];
             }
-        }
-        sync_cta();
+        } else {
+            constexpr int NB = N / 3, NBP = NB + NB / E, QMAX = (NB + M - 1) / M;
+            cpx<R> a[QMAX][3];
 #pragma unroll
-        for (int q = 0; q < QMAX; ++q) {
-            const int b = j + q * M;
-            if (b < NB) {
-                const int k = b % Ns;
-                apply_twiddle_powers<3>(a[q], tw_load<DIR>(tw, k * (N / (Ns * 3))));
-                dft3<DIR>(a[q][0], a[q][1], a[q][2]);
-                const int o = (b / Ns) * (Ns * 3) + k;
+            for (int q = 0; q < QMAX; ++q) {
+                if (j + q * M < NB) {
 #pragma unroll
-                for (int r = 0; r < 3; ++r) line[P::pad(o + r * Ns) * STRIDE] = a[q][r];
+                    for (int r = 0; r < 3; ++r) a[q][r] = ldp[(q * MP + r * NBP) * STRIDE];
+                }
+            }
+            sync_cta();
+#pragma unroll
+            for (int q = 0; q < QMAX; ++q) {
+                if (j + q * M < NB) {
+                    a[q][1] = cmul(a[q][1], w[1]);
+                    a[q][2] = cmul(a[q][2], w[2]);
+                    dft3<DIR>(a[q][0], a[q][1], a[q][2]);
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) stm[(q * MID * BLK + r * EP) * STRIDE] = a[q][r];
+                }
             }
         }
         sync_cta();
@@ -221,9 +267,14 @@ SLM_DEV void line_fft(cpx<R>* v, cpx<R>* line, int j, const cpx<R>* __restrict__
 
     // last stage (Ns = M): twiddle W_N^(r*j), butterfly, result r is X[j + r*M]
 #pragma unroll
-    for (int r = 0; r < E; ++r) v[r] = line[P::pad(j + r * M) * STRIDE];
+    for (int r = 0; r < E; ++r) v[r] = ldp[r * MP * STRIDE];
     sync_cta();                      // the tile may be overwritten by the next transform
-    apply_twiddle_powers<E>(v, tw_load<DIR>(tw, j));
+    {
+        cpx<R> w[E];
+        twiddle_powers<E>(w, tw_load<DIR>(tw, j));
+#pragma unroll
+        for (int r = 1; r < E; ++r) v[r] = cmul(v[r], w[r]);
+    }
     dft_small<E, DIR>(v);
 }
 

@@ -15,66 +15,91 @@
 #pragma once
 #include "engine_types.h"
 #include "fft_tile.cuh"
+#include "tma.cuh"
 
 namespace slm {
 
 // ---- pointwise pieces ---------------------------------------------------------------------------
 // exp(1j*angle(z)) as written at algorithms.py:30,33: z/|z|, with angle(+0)=0 -> 1, angle(-0)=pi -> -1
 template <typename R> SLM_DEV cpx<R> unit_phasor(cpx<R> z) {
-    const R m2 = z.x * z.x + z.y * z.y;
-    cpx<R> r;
-    if (m2 == (R)0) { r.x = copysign((R)1, z.x); r.y = (R)0; return r; }
-    const R inv = rsqrt_fast(m2);
-    r.x = z.x * inv; r.y = z.y * inv;
-    return r;
+    const R m2 = cnorm2(z);
+    if (m2 == (R)0) return mk<R>(copysign((R)1, z.x), (R)0);
+    return cscale(z, rsqrt_fast(m2));
 }
 
 // dEdX_complex (algorithms.py:179-185) == (g - xh <xh, g>) / |x| with xh = x/|x|; returns the
 // updated x (algorithms.py:91).
 template <typename R> SLM_DEV cpx<R> tangent_step(cpx<R> x, cpx<R> g, R lr) {
-    const R inv = rsqrt_fast(x.x * x.x + x.y * x.y);
-    cpx<R> xh; xh.x = x.x * inv; xh.y = x.y * inv;
-    const R dot = xh.x * g.x + xh.y * g.y;
-    const R step = lr * inv;
-    x.x -= step * (g.x - xh.x * dot);
-    x.y -= step * (g.y - xh.y * dot);
-    return x;
+    const R inv = rsqrt_fast(cnorm2(x));
+    const cpx<R> xh = cscale(x, inv);
+    const cpx<R> pr = pk_mul(xh, g);
+    const R dot = pr.x + pr.y;
+    const R step = -(lr * inv);
+    const cpx<R> tang = pk_fma(mk<R>(-dot, -dot), xh, g);          // g - xh <xh, g>
+    return pk_fma(mk<R>(step, step), tang, x);                     // x - lr * tang / |x|
 }
 
 // ---- deterministic reductions ---------------------------------------------------------------------
-SLM_DEV Partial combine(Partial p, Partial q) {
-    p.mx = fmax(p.mx, q.mx); p.a += q.a; p.b += q.b; p.c += q.c; return p;
+// FIELDS selects which members of Partial a kernel actually uses (bit 0 mx, 1 a, 2 b, 3 c) so the
+// shuffle trees only move those.
+enum { F_MX = 1, F_A = 2, F_B = 4, F_C = 8, F_ALL = 15 };
+template <int FIELDS> SLM_DEV Partial combine(Partial p, Partial q) {
+    if (FIELDS & F_MX) p.mx = fmax(p.mx, q.mx);
+    if (FIELDS & F_A) p.a += q.a;
+    if (FIELDS & F_B) p.b += q.b;
+    if (FIELDS & F_C) p.c += q.c;
+    return p;
 }
-SLM_DEV Partial warp_reduce(Partial p) {
+template <int FIELDS> SLM_DEV Partial warp_reduce(Partial p) {
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) {
-        Partial q;
-        q.mx = shfl_xor(p.mx, m); q.a = shfl_xor(p.a, m); q.b = shfl_xor(p.b, m); q.c = shfl_xor(p.c, m);
-        p = combine(p, q);
+        Partial q = p;
+        if (FIELDS & F_MX) q.mx = shfl_xor(p.mx, m);
+        if (FIELDS & F_A) q.a = shfl_xor(p.a, m);
+        if (FIELDS & F_B) q.b = shfl_xor(p.b, m);
+        if (FIELDS & F_C) q.c = shfl_xor(p.c, m);
+        p = combine<FIELDS>(p, q);
     }
     return p;
 }
 // Result valid in thread 0.  NT = threads per CTA (multiple of 32).
-template <int NT> SLM_DEV Partial block_reduce(Partial p, int t) {
+template <int NT, int FIELDS> SLM_DEV Partial block_reduce(Partial p, int t) {
     static_assert(NT % 32 == 0 && NT <= 1024, "CTA size");
     SLM_STATIC_SMEM Partial red[32];
-    p = warp_reduce(p);
+    p = warp_reduce<FIELDS>(p);
     if (t % 32 == 0) red[t / 32] = p;
     sync_cta();
     if (t < 32) {
         Partial q; q.mx = 0; q.a = 0; q.b = 0; q.c = 0;
         if (t < NT / 32) q = red[t];
-        p = warp_reduce(q);
+        p = warp_reduce<FIELDS>(q);
     }
     return p;
 }
 SLM_DEV Partial ld_partial(const Partial* p) {
     Partial q; q.mx = ld_cg(&p->mx); q.a = ld_cg(&p->a); q.b = ld_cg(&p->b); q.c = ld_cg(&p->c); return q;
 }
+// Split form used by the loop's column pass: thread 0 publishes right after the block reduce (the
+// atomic's round trip overlaps the inverse transform) and warp 0 alone looks at the ticket afterwards.
+SLM_DEV unsigned publish_partial(Partial mine, Partial* plane_partials, int tile, int tiles, unsigned* counter) {
+    plane_partials[tile] = mine;
+    fence_device();
+    return atomic_inc_wrap(counter, (unsigned)tiles - 1);                        // wraps to 0: reusable
+}
+// warp 0, all 32 lanes: `ticket` is valid in lane 0.  True (with the plane total in every lane) for the last tile.
+template <int FIELDS> SLM_DEV bool collect_if_last(unsigned ticket, int t, const Partial* plane_partials, int tiles, Partial& total) {
+    ticket = shfl_idx(ticket, 0);
+    if (ticket != (unsigned)tiles - 1) return false;
+    fence_device();
+    Partial q; q.mx = 0; q.a = 0; q.b = 0; q.c = 0;
+    for (int i = t; i < tiles; i += 32) q = combine<FIELDS>(q, ld_partial(plane_partials + i));
+    total = warp_reduce<FIELDS>(q);
+    return true;
+}
 // Publish this tile's partial; returns (to every thread) whether this CTA is the last of its plane,
 // in which case thread 0 of it receives the plane total in `total`.
-template <int NT> SLM_DEV bool publish_and_collect(Partial mine, int t, Partial* plane_partials, int tile, int tiles,
-                                                   unsigned* counter, Partial& total) {
+template <int NT, int FIELDS> SLM_DEV bool publish_and_collect(Partial mine, int t, Partial* plane_partials, int tile, int tiles,
+                                                               unsigned* counter, Partial& total) {
     SLM_STATIC_SMEM int is_last;
     if (t == 0) {
         plane_partials[tile] = mine;
@@ -88,8 +113,8 @@ template <int NT> SLM_DEV bool publish_and_collect(Partial mine, int t, Partial*
     fence_device();
     if (t < 32) {
         Partial q; q.mx = 0; q.a = 0; q.b = 0; q.c = 0;
-        for (int i = t; i < tiles; i += 32) q = combine(q, ld_partial(plane_partials + i));
-        total = warp_reduce(q);
+        for (int i = t; i < tiles; i += 32) q = combine<FIELDS>(q, ld_partial(plane_partials + i));
+        total = warp_reduce<FIELDS>(q);
     }
     return true;
 }
@@ -102,12 +127,19 @@ template <typename R, int L> struct RowGeom {
     static constexpr int NR = floor_pow2(256 / M);           // rows per CTA (power of two)
     static constexpr int THREADS = NR * M;
     static constexpr size_t SMEM = (size_t)NR * P::NP * sizeof(cpx<R>);
+    static constexpr int MIN_CTAS = sizeof(R) == 4 ? (512 / THREADS > 0 ? 512 / THREADS : 1) : 1;   // fp32: <= 128 registers
 };
 template <typename R, int L> struct ColGeom {
     using P = FftPlan<L>;
     static constexpr int M = P::M;
+#ifndef SLM_TCMAX_F32
+#define SLM_TCMAX_F32 8
+#endif
+#ifndef SLM_TCMAX_F64
+#define SLM_TCMAX_F64 4
+#endif
     static constexpr int TMAX = sizeof(R) == 4 ? 512 : 256;
-    static constexpr int TCMAX = sizeof(R) == 4 ? 8 : 4;
+    static constexpr int TCMAX = sizeof(R) == 4 ? SLM_TCMAX_F32 : SLM_TCMAX_F64;
     static constexpr int TCRAW = (TMAX / M) < TCMAX ? (TMAX / M) : TCMAX;
     static constexpr int TC = TCRAW >= 8 ? 8 : TCRAW >= 4 ? 4 : TCRAW >= 2 ? 2 : 1;            // columns per CTA
     static constexpr int THREADS = TC * M;
@@ -116,8 +148,10 @@ template <typename R, int L> struct ColGeom {
 };
 
 // ---- SLM-plane pass ------------------------------------------------------------------------------
-template <typename R, int W, int ALG>
-SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), 1) row_pass_kernel(RowArgs a) {
+// FINAL = 1 is the pass after the loop: it emits the hologram (angle) instead of starting the next
+// forward transform; a separate instantiation keeps the atan2 code out of the loop kernel.
+template <typename R, int W, int ALG, int FINAL>
+SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), (RowGeom<R, W>::MIN_CTAS)) row_pass_kernel(RowArgs a) {
     using G = RowGeom<R, W>;
     using P = FftPlan<W>;
     constexpr int E = P::E, M = P::M;
@@ -127,7 +161,7 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), 1) row_pass_kernel(R
     const int b = (int)(grow / a.H), y = (int)(grow % a.H);
     const PlaneStats* st = a.stats + b;
     const int done = ld_cg(&st->done);
-    if (!a.final_pass && done) return;                       // uniform: a CTA never straddles planes
+    if (!FINAL && done) return;                       // uniform: a CTA never straddles planes
     cpx<R>* line = reinterpret_cast<cpx<R>*>(raw) + (size_t)rr * P::NP;
     const cpx<R>* tw = static_cast<const cpx<R>*>(a.tw);
     const size_t base = ((size_t)b * a.H + y) * W + j;
@@ -142,14 +176,14 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), 1) row_pass_kernel(R
             for (int r = 0; r < E; ++r) v[r] = ld_plane(Y + r * M);
             line_fft<R, W, +1, 1>(v, line, j, tw);           // A = ifft2(D) up to a positive scale
 #pragma unroll
-            for (int r = 0; r < E; ++r) if (!a.final_pass) v[r] = unit_phasor(v[r]);
+            for (int r = 0; r < E; ++r) if (!FINAL) v[r] = unit_phasor(v[r]);
         } else if (a.source == ROW_FROM_A32) {
             // first phasor in complex64, as the reference computes it (algorithms.py:27,30)
             const cpx<float>* A = static_cast<const cpx<float>*>(a.A32) + base;
 #pragma unroll
             for (int r = 0; r < E; ++r) {
                 cpx<float> z = ld_plane(A + r * M);
-                if (!a.final_pass) z = unit_phasor(z);
+                if (!FINAL) z = unit_phasor(z);
                 v[r].x = (R)z.x; v[r].y = (R)z.y;
             }
         } else {
@@ -157,10 +191,10 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), 1) row_pass_kernel(R
 #pragma unroll
             for (int r = 0; r < E; ++r) {
                 v[r] = ld_plane(F + r * M);
-                if (a.source == ROW_FROM_A && !a.final_pass) v[r] = unit_phasor(v[r]);
+                if (a.source == ROW_FROM_A && !FINAL) v[r] = unit_phasor(v[r]);
             }
         }
-        if (a.final_pass) {                                   // hologram = angle(A), algorithms.py:48
+        if (FINAL) {                                   // hologram = angle(A), algorithms.py:48
             double* h = a.hologram + base;
 #pragma unroll
             for (int r = 0; r < E; ++r) h[r * M] = atan2((double)v[r].y, (double)v[r].x);
@@ -168,7 +202,7 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), 1) row_pass_kernel(R
         }
         if (inc && a.source != ROW_FROM_FIELD) {
 #pragma unroll
-            for (int r = 0; r < E; ++r) { const R s = ld_ro(inc + ibase + r * M); v[r].x *= s; v[r].y *= s; }
+            for (int r = 0; r < E; ++r) v[r] = cscale(v[r], ld_ro(inc + ibase + r * M));
         }
     } else {
         cpx<R>* xp = static_cast<cpx<R>*>(a.x) + base;
@@ -185,14 +219,13 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), 1) row_pass_kernel(R
             const R nrm = (R)a.inv_hw;
 #pragma unroll
             for (int r = 0; r < E; ++r) {
-                cpx<R> g;                                       // dEdF = ifft2(...) * inc_amp, algorithms.py:87-89
-                g.x = v[r].x * nrm; g.y = v[r].y * nrm;
-                if (inc) { const R s = ld_ro(inc + ibase + r * M); g.x *= s; g.y *= s; }
-                xx[r] = tangent_step(xx[r], g, lr);             // algorithms.py:90-91
+                R gs = nrm;                                     // dEdF = ifft2(...) * inc_amp, algorithms.py:87-89
+                if (inc) gs *= ld_ro(inc + ibase + r * M);
+                xx[r] = tangent_step(xx[r], cscale(v[r], gs), lr);   // algorithms.py:90-91
                 st_plane(xp + r * M, xx[r]);
             }
         }
-        if (a.final_pass) {                                   // hologram = angle(input), algorithms.py:111
+        if (FINAL) {                                   // hologram = angle(input), algorithms.py:111
             double* h = a.hologram + base;
 #pragma unroll
             for (int r = 0; r < E; ++r) h[r * M] = atan2((double)xx[r].y, (double)xx[r].x);
@@ -200,9 +233,9 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), 1) row_pass_kernel(R
         }
 #pragma unroll
         for (int r = 0; r < E; ++r) {                            // input / abs(input) * inc_amp, algorithms.py:84
-            const R inv = rsqrt_fast(xx[r].x * xx[r].x + xx[r].y * xx[r].y);
-            v[r].x = xx[r].x * inv; v[r].y = xx[r].y * inv;
-            if (inc) { const R s = ld_ro(inc + ibase + r * M); v[r].x *= s; v[r].y *= s; }
+            R inv = rsqrt_fast(cnorm2(xx[r]));
+            if (inc) inv *= ld_ro(inc + ibase + r * M);
+            v[r] = cscale(xx[r], inv);
         }
     }
     line_fft<R, W, -1, 1>(v, line, j, tw);
@@ -212,34 +245,39 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), 1) row_pass_kernel(R
 }
 
 // ---- Fourier-plane pass ---------------------------------------------------------------------------
+// Two launch shapes share one tile body:
+//   PERSIST = 0 : one CTA per column tile, points loaded straight from global memory;
+//   PERSIST = 1 : gridDim.x resident CTAs walk the tiles round-robin; the NEXT tile is fetched by
+//                 TMA (cp.async.bulk.tensor, tma.cuh) into a second dense shared-memory buffer while
+//                 the current one is transformed, so global-load latency is off the critical path.
+template <typename R, int H> struct ColSmem {
+    using G = ColGeom<R, H>;
+    static constexpr size_t DENSE = (size_t)H * G::TC * sizeof(cpx<R>);     // one TMA tile buffer
+    static constexpr size_t PERSIST_BYTES = 2 * DENSE + G::SMEM + 64;       // 2 tile buffers, exchange, barriers
+};
+
+// One column tile of the loop's Fourier-plane step.  v = the tile's points (thread (j,c) holds rows
+// j + r*M of column c); lut_s = the 256-entry amplitude (GS) / weight (GD) table in shared memory.
+// Ordering is chosen so no warp waits on a dependent global access: the grey levels are requested
+// before the forward transform and only looked up (in shared memory) after it; the tile's partial
+// sums are published before the inverse transform, whose work covers the atomic's round trip.
 template <typename R, int H, int ALG>
-SLM_GLOBAL void SLM_LAUNCH_BOUNDS((ColGeom<R, H>::THREADS), 1) col_pass_kernel(ColArgs a) {
+SLM_DEV void col_pass_tile(const ColArgs& a, int b, int tile, int tiles, cpx<R>* v, cpx<R>* line, const R* lut_s,
+                           int t, int c, int j) {
     using G = ColGeom<R, H>;
     using P = FftPlan<H>;
     constexpr int E = P::E, M = P::M, TC = G::TC;
-    SLM_DYN_SMEM(raw);
-    const int tiles = a.W / TC;
-    const int b = blockIdx.x / tiles, tile = blockIdx.x % tiles;
     PlaneStats* st = a.stats + b;
-    if (ld_cg(&st->done)) return;
-    const int t = threadIdx.x, c = t % TC, j = t / TC;
     const size_t W = a.W;
     const size_t off = (size_t)b * H * W + (size_t)j * W + tile * TC + c;
     const cpx<R>* tw = static_cast<const cpx<R>*>(a.tw);
-    cpx<R>* line = reinterpret_cast<cpx<R>*>(raw) + c;
     const double s0 = ld_cg(&st->scale), imax = ld_cg(&st->imax), norm = ld_ro(a.norm + b);
-
-    cpx<R> v[E];
-    const cpx<R>* X = static_cast<const cpx<R>*>(a.X) + off;
-#pragma unroll
-    for (int r = 0; r < E; ++r) v[r] = ld_plane(X + (size_t)r * M * W);
-    // target grey level and its amplitude (GS) / weight (GD), fetched while the transform runs
+    int grey[E];
     R tv[E], aux[E];
     if (a.T8) {
         const uint8_t* T = a.T8 + off;
-        const R* lut = static_cast<const R*>(a.lut);
 #pragma unroll
-        for (int r = 0; r < E; ++r) { const int g = ld_ro(T + (size_t)r * M * W); tv[r] = (R)g; aux[r] = ld_ro(lut + g); }
+        for (int r = 0; r < E; ++r) grey[r] = ld_ro(T + (size_t)r * M * W);
     } else {
         const R* T = static_cast<const R*>(a.Treal) + off;
         const R* Q = static_cast<const R*>(a.plane2) + off;
@@ -247,40 +285,56 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((ColGeom<R, H>::THREADS), 1) col_pass_kernel(C
         for (int r = 0; r < E; ++r) { tv[r] = ld_ro(T + (size_t)r * M * W); aux[r] = ld_ro(Q + (size_t)r * M * W); }
     }
     line_fft<R, H, -1, TC>(v, line, j, tw);                   // C = fft2(B)  /  med_output
+    if (a.T8) {
+#pragma unroll
+        for (int r = 0; r < E; ++r) { tv[r] = (R)grey[r]; aux[r] = lut_s[grey[r]]; }
+    }
 
-    Partial p; p.mx = 0; p.a = 0; p.b = 0; p.c = 0;
+    // per-thread sums in R (E terms), widened to double before they meet other threads
+    R mx = 0, sa = 0, sb = 0, sc = 0;
+    const R s0r = (R)s0;                                        // GS: scale of the previous iteration
+    const R gdk = sizeof(R) == 8 ? (R)0 : (R)(norm / imax);    // GD fp32: output = |F|^2 * (norm/max)
 #pragma unroll
     for (int r = 0; r < E; ++r) {
-        const R m2 = v[r].x * v[r].x + v[r].y * v[r].y;       // |C|^2, algorithms.py:36 / :85
+        const R m2 = cnorm2(v[r]);                              // |C|^2, algorithms.py:36 / :85
         if (ALG == ALG_GS) {
             // error of this iteration against the scale s0 of the previous one; the exact scale
             // s = norm/max is folded in by the last tile (see finish below).
-            const double u = s0 * (double)m2, d = u - (double)tv[r];
-            p.mx = fmax(p.mx, (double)m2); p.a += d * d; p.b += d * u; p.c += u * u;
-            const cpx<R> ph = unit_phasor(v[r]);                // D = |amp| * exp(1j*angle(C)), :33
-            v[r].x = aux[r] * ph.x; v[r].y = aux[r] * ph.y;
+            const R u = s0r * m2, d = u - tv[r];
+            mx = fmax(mx, m2); sa += d * d; sb += d * u; sc += u * u;
+            // D = |amp| * exp(1j*angle(C)), algorithms.py:33
+            v[r] = (m2 == (R)0) ? mk<R>(copysign(aux[r], v[r].x), (R)0) : cscale(v[r], aux[r] * rsqrt_fast(m2));
         } else {
-            const double I = ((double)m2 * norm) / imax;        // output, algorithms.py:86
-            const double d = I - (double)tv[r];
-            p.a += d * d;
-            const R dr = (R)d;                                   // mask * med_output * (output - T), :88
-            v[r].x = (aux[r] * v[r].x) * dr; v[r].y = (aux[r] * v[r].y) * dr;
+            R I;                                                 // output, algorithms.py:86
+            if (sizeof(R) == 8) I = (R)(((double)m2 * norm) / imax);
+            else I = m2 * gdk;
+            const R d = I - tv[r];
+            sa += d * d;
+            v[r] = cscale(cscale(v[r], aux[r]), d);              // mask * med_output * (output - T), :88
         }
     }
+    constexpr int FIELDS = ALG == ALG_GS ? F_ALL : F_A;
+    Partial p; p.mx = (double)mx; p.a = (double)sa; p.b = (double)sb; p.c = (double)sc;
+    p = block_reduce<G::THREADS, FIELDS>(p, t);
+    Partial* plane_partials = a.partial + (size_t)b * tiles;
+    unsigned ticket = 0;
+    if (t == 0) ticket = publish_partial(p, plane_partials, tile, tiles, a.counter + b);
+
     line_fft<R, H, +1, TC>(v, line, j, tw);
     cpx<R>* Y = static_cast<cpx<R>*>(a.Y) + off;
 #pragma unroll
     for (int r = 0; r < E; ++r) st_plane(Y + (size_t)r * M * W, v[r]);
 
-    p = block_reduce<G::THREADS>(p, t);
+    if (t >= 32) return;
     Partial tot;
-    if (!publish_and_collect<G::THREADS>(p, t, a.partial + (size_t)b * tiles, tile, tiles, a.counter + b, tot)) return;
+    if (!collect_if_last<FIELDS>(ticket, t, plane_partials, tiles, tot)) return;
     if (t == 0) {
         const double hw = (double)H * (double)W;
         double err;
         if (ALG == ALG_GS) {
             const double s = norm / tot.mx;                      // algorithms.py:37
-            const double dl = (s0 != 0.0) ? s / s0 - 1.0 : 0.0;
+            const double s0u = (double)s0r;                      // the scale the tiles actually used
+            const double dl = (s0u != 0.0) ? s / s0u - 1.0 : 0.0;
             err = (tot.a + 2.0 * dl * tot.b + dl * dl * tot.c) / hw;   // == sum((s*I - T)^2)/HW, :38,:162
             st->imax = tot.mx; st->scale = s;
         } else {
@@ -291,6 +345,126 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((ColGeom<R, H>::THREADS), 1) col_pass_kernel(C
         st->err = err; st->iters = k + 1;
         st->done = !(err > a.tolerance);                         // loop condition, algorithms.py:29,83
     }
+}
+
+// One column tile of a plain transform: complex out, max-only, or normalised intensity out.
+template <typename R, int H>
+SLM_DEV void col_plain_tile(const PlainColArgs& a, int b, int tile, int tiles, cpx<R>* v, cpx<R>* line, int t, int c, int j) {
+    using G = ColGeom<R, H>;
+    using P = FftPlan<H>;
+    constexpr int E = P::E, M = P::M, TC = G::TC;
+    PlaneStats* st = a.stats ? a.stats + b : nullptr;
+    const size_t W = a.W;
+    const size_t off = (size_t)b * H * W + (size_t)j * W + tile * TC + c;
+    const cpx<R>* tw = static_cast<const cpx<R>*>(a.tw);
+    if (a.inverse) line_fft<R, H, +1, TC>(v, line, j, tw);
+    else line_fft<R, H, -1, TC>(v, line, j, tw);
+
+    if (a.output == OUT_COMPLEX) {
+        cpx<R>* out = static_cast<cpx<R>*>(a.out) + off;
+        const R s = (R)a.scale;
+#pragma unroll
+        for (int r = 0; r < E; ++r) st_plane(out + (size_t)r * M * W, cscale(v[r], s));
+    } else if (a.output == OUT_STATS) {
+        Partial p; p.mx = 0; p.a = 0; p.b = 0; p.c = 0;
+        R mx = 0;
+#pragma unroll
+        for (int r = 0; r < E; ++r) mx = fmax(mx, cnorm2(v[r]));
+        p.mx = (double)mx;
+        p = block_reduce<G::THREADS, F_MX>(p, t);
+        if (t >= 32) return;
+        Partial* plane_partials = a.partial + (size_t)b * tiles;
+        unsigned ticket = 0;
+        if (t == 0) ticket = publish_partial(p, plane_partials, tile, tiles, a.counter + b);
+        Partial tot;
+        if (!collect_if_last<F_MX>(ticket, t, plane_partials, tiles, tot)) return;
+        if (t == 0) { st->imax = tot.mx; st->scale = ld_ro(a.norm + b) / tot.mx; }
+    } else {
+        double* out = static_cast<double*>(a.out) + off;
+        const double imax = ld_cg(&st->imax), scale = ld_cg(&st->scale), norm = ld_ro(a.norm + b);
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+            const double m2 = (double)cnorm2(v[r]);
+            double I;
+            if (a.output == OUT_INTENSITY_GS) I = m2 * scale;
+            else if (a.output == OUT_INTENSITY_GD) I = (m2 * norm) / imax;
+            else I = (m2 / imax) * norm;
+            out[(size_t)r * M * W] = I;
+        }
+    }
+}
+
+// Shared driver of both column kernels.  BODY(b, tile, v) processes one tile; SKIP(b) says whether plane b rests.
+template <typename R, int H, int PERSIST, class Skip, class Body>
+SLM_DEV void col_tiles(const void* in, int B, int W, const TileMap& tm, unsigned char* raw, Skip skip, Body body) {
+    using G = ColGeom<R, H>;
+    using P = FftPlan<H>;
+    constexpr int E = P::E, M = P::M, TC = G::TC;
+    const int tiles = W / TC;
+    const int t = threadIdx.x, c = t % TC, j = t / TC;
+    cpx<R> v[E];
+    if (!PERSIST) {
+        const int b = blockIdx.x / tiles, tile = blockIdx.x % tiles;
+        if (skip(b)) return;
+        const cpx<R>* X = static_cast<const cpx<R>*>(in) + (size_t)b * H * W + (size_t)j * W + tile * TC + c;
+#pragma unroll
+        for (int r = 0; r < E; ++r) v[r] = ld_plane(X + (size_t)r * M * W);
+        body(b, tile, tiles, v, reinterpret_cast<cpx<R>*>(raw) + c, t, c, j);
+        return;
+    }
+    // persistent: [dense buffer 0][dense buffer 1][exchange][2 barriers]; the dynamic shared memory
+    // window is declared 128-byte aligned (TMA destination requirement)
+    unsigned char* base = raw;
+    constexpr size_t DENSE = ColSmem<R, H>::DENSE;
+    cpx<R>* const dense0 = reinterpret_cast<cpx<R>*>(base);
+    cpx<R>* const dense1 = reinterpret_cast<cpx<R>*>(base + DENSE);
+    cpx<R>* const line = reinterpret_cast<cpx<R>*>(base + 2 * DENSE) + c;
+    TileBarrier* const bar = reinterpret_cast<TileBarrier*>(base + 2 * DENSE + G::SMEM);
+    const long long total = (long long)B * tiles;
+    if (t == 0) { tile_barrier_init(bar); tile_barrier_init(bar + 1); tile_barrier_fence(); }
+    sync_cta();
+    unsigned uses0 = 0, uses1 = 0;      // completed uses of each buffer's barrier (uniform across the CTA)
+    int cur = 0;
+    long long g = blockIdx.x;
+    auto fetch = [&](long long gt, int buf) {       // thread 0 only
+        const int fb = (int)(gt / tiles), ft = (int)(gt % tiles);
+        tile_prefetch(tm, buf ? dense1 : dense0, bar + buf, (long long)fb * H, H, ft * TC, TC, (int)sizeof(cpx<R>));
+    };
+    // The next tile is always requested (a finished plane's tile is fetched and dropped: rare, and it
+    // keeps one wait per fetch); whether a plane rests is looked up while its tile is in flight.
+    if (g < total && t == 0) fetch(g, 0);
+    while (g < total) {
+        const long long gn = g + gridDim.x;
+        if (gn < total && t == 0) fetch(gn, cur ^ 1);   // buffer cur^1 was drained before the barriers of the previous tile
+        const int b = (int)(g / tiles), tile = (int)(g % tiles);
+        const bool rest = skip(b);
+        tile_wait(bar + cur, cur ? uses1 : uses0);
+        if (cur) uses1++; else uses0++;
+        if (!rest) {
+            const cpx<R>* src = (cur ? dense1 : dense0) + (size_t)j * TC + c;
+#pragma unroll
+            for (int r = 0; r < E; ++r) v[r] = src[(size_t)r * M * TC];
+            body(b, tile, tiles, v, line, t, c, j);
+        }
+        sync_cta();                      // everyone is out of this tile (static smem of the reductions, buffer cur)
+        g = gn;
+        cur ^= 1;
+    }
+}
+
+template <typename R, int H, int ALG, int PERSIST>
+SLM_GLOBAL void SLM_LAUNCH_BOUNDS((ColGeom<R, H>::THREADS), 1) col_pass_kernel(ColArgs a, const SLM_GRID_CONSTANT TileMap tm) {
+    SLM_DYN_SMEM(raw);
+    SLM_STATIC_SMEM R lut_s[256];
+    if (a.T8) {                                                 // visible after the first barrier of the transform
+        const R* lut = static_cast<const R*>(a.lut);
+        for (int i = threadIdx.x; i < 256; i += ColGeom<R, H>::THREADS) lut_s[i] = ld_ro(lut + i);
+    }
+    col_tiles<R, H, PERSIST>(a.X, a.B, a.W, tm, raw,
+        [&](int b) { return ld_cg(&a.stats[b].done) != 0; },
+        [&](int b, int tile, int tiles, cpx<R>* v, cpx<R>* line, int t, int c, int j) {
+            col_pass_tile<R, H, ALG>(a, b, tile, tiles, v, line, lut_s, t, c, j);
+        });
 }
 
 // ---- plain row transform (setup, preview, slm_fft2) --------------------------------------------------
@@ -330,74 +504,45 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), 1) row_plain_kernel(
     for (int r = 0; r < E; ++r) st_plane(out + r * M, v[r]);
 }
 
-// ---- plain column transform: complex out, max-only, or normalised intensity out -------------------------
-template <typename R, int H>
-SLM_GLOBAL void SLM_LAUNCH_BOUNDS((ColGeom<R, H>::THREADS), 1) col_plain_kernel(PlainColArgs a) {
-    using G = ColGeom<R, H>;
-    using P = FftPlan<H>;
-    constexpr int E = P::E, M = P::M, TC = G::TC;
+// ---- plain column transform kernel -------------------------------------------------------------------
+template <typename R, int H, int PERSIST>
+SLM_GLOBAL void SLM_LAUNCH_BOUNDS((ColGeom<R, H>::THREADS), 1) col_plain_kernel(PlainColArgs a, const SLM_GRID_CONSTANT TileMap tm) {
     SLM_DYN_SMEM(raw);
-    const int tiles = a.W / TC;
-    const int b = blockIdx.x / tiles, tile = blockIdx.x % tiles;
-    PlaneStats* st = a.stats ? a.stats + b : nullptr;
-    if (a.output == OUT_STATS && ld_cg(&st->done)) return;    // in-loop use (GD): finished planes rest
-    const int t = threadIdx.x, c = t % TC, j = t / TC;
-    const size_t W = a.W;
-    const size_t off = (size_t)b * H * W + (size_t)j * W + tile * TC + c;
-    const cpx<R>* tw = static_cast<const cpx<R>*>(a.tw);
-    cpx<R>* line = reinterpret_cast<cpx<R>*>(raw) + c;
-    cpx<R> v[E];
-    const cpx<R>* in = static_cast<const cpx<R>*>(a.in) + off;
-#pragma unroll
-    for (int r = 0; r < E; ++r) v[r] = ld_plane(in + (size_t)r * M * W);
-    if (a.inverse) line_fft<R, H, +1, TC>(v, line, j, tw);
-    else line_fft<R, H, -1, TC>(v, line, j, tw);
-
-    if (a.output == OUT_COMPLEX) {
-        cpx<R>* out = static_cast<cpx<R>*>(a.out) + off;
-        const R s = (R)a.scale;
-#pragma unroll
-        for (int r = 0; r < E; ++r) { v[r].x *= s; v[r].y *= s; st_plane(out + (size_t)r * M * W, v[r]); }
-    } else if (a.output == OUT_STATS) {
-        Partial p; p.mx = 0; p.a = 0; p.b = 0; p.c = 0;
-#pragma unroll
-        for (int r = 0; r < E; ++r) p.mx = fmax(p.mx, (double)(v[r].x * v[r].x + v[r].y * v[r].y));
-        p = block_reduce<G::THREADS>(p, t);
-        Partial tot;
-        if (!publish_and_collect<G::THREADS>(p, t, a.partial + (size_t)b * tiles, tile, tiles, a.counter + b, tot)) return;
-        if (t == 0) { st->imax = tot.mx; st->scale = ld_ro(a.norm + b) / tot.mx; }
-    } else {
-        double* out = static_cast<double*>(a.out) + off;
-        const double imax = ld_cg(&st->imax), scale = ld_cg(&st->scale), norm = ld_ro(a.norm + b);
-#pragma unroll
-        for (int r = 0; r < E; ++r) {
-            const double m2 = (double)(v[r].x * v[r].x + v[r].y * v[r].y);
-            double I;
-            if (a.output == OUT_INTENSITY_GS) I = m2 * scale;
-            else if (a.output == OUT_INTENSITY_GD) I = (m2 * norm) / imax;
-            else I = (m2 / imax) * norm;
-            out[(size_t)r * M * W] = I;
-        }
-    }
+    col_tiles<R, H, PERSIST>(a.in, a.B, a.W, tm, raw,
+        [&](int b) { return a.output == OUT_STATS && ld_cg(&a.stats[b].done) != 0; },   // in-loop use (GD): finished planes rest
+        [&](int b, int tile, int tiles, cpx<R>* v, cpx<R>* line, int t, int c, int j) {
+            col_plain_tile<R, H>(a, b, tile, tiles, v, line, t, c, j);
+        });
 }
 
 // ---- host-side launchers ----------------------------------------------------------------------------
 template <typename R, int L> struct LineOps {
     using RG = RowGeom<R, L>;
     using CG = ColGeom<R, L>;
+    static constexpr size_t PSMEM = ColSmem<R, L>::PERSIST_BYTES;
     static int check() { cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? 0 : -(int)e - 1000; }
     static void prepare() {
-        cudaFuncSetAttribute(row_pass_kernel<R, L, ALG_GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
-        cudaFuncSetAttribute(row_pass_kernel<R, L, ALG_GD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
+        cudaFuncSetAttribute(row_pass_kernel<R, L, ALG_GS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
+        cudaFuncSetAttribute(row_pass_kernel<R, L, ALG_GS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
+        cudaFuncSetAttribute(row_pass_kernel<R, L, ALG_GD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
+        cudaFuncSetAttribute(row_pass_kernel<R, L, ALG_GD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
         cudaFuncSetAttribute(row_plain_kernel<R, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
-        cudaFuncSetAttribute(col_pass_kernel<R, L, ALG_GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG::SMEM);
-        cudaFuncSetAttribute(col_pass_kernel<R, L, ALG_GD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG::SMEM);
-        cudaFuncSetAttribute(col_plain_kernel<R, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG::SMEM);
+        cudaFuncSetAttribute(col_pass_kernel<R, L, ALG_GS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG::SMEM);
+        cudaFuncSetAttribute(col_pass_kernel<R, L, ALG_GD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG::SMEM);
+        cudaFuncSetAttribute(col_plain_kernel<R, L, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG::SMEM);
+        cudaFuncSetAttribute(col_pass_kernel<R, L, ALG_GS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PSMEM);
+        cudaFuncSetAttribute(col_pass_kernel<R, L, ALG_GD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PSMEM);
+        cudaFuncSetAttribute(col_plain_kernel<R, L, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PSMEM);
     }
     static int row_pass(int alg, const RowArgs& a, cudaStream_t s) {
         const dim3 grid((unsigned)((long long)a.B * a.H / RG::NR)), block(RG::THREADS);
-        if (alg == ALG_GS) SLM_LAUNCH((row_pass_kernel<R, L, ALG_GS>), grid, block, RG::SMEM, s, a);
-        else SLM_LAUNCH((row_pass_kernel<R, L, ALG_GD>), grid, block, RG::SMEM, s, a);
+        if (alg == ALG_GS) {
+            if (a.final_pass) SLM_LAUNCH((row_pass_kernel<R, L, ALG_GS, 1>), grid, block, RG::SMEM, s, a);
+            else SLM_LAUNCH((row_pass_kernel<R, L, ALG_GS, 0>), grid, block, RG::SMEM, s, a);
+        } else {
+            if (a.final_pass) SLM_LAUNCH((row_pass_kernel<R, L, ALG_GD, 1>), grid, block, RG::SMEM, s, a);
+            else SLM_LAUNCH((row_pass_kernel<R, L, ALG_GD, 0>), grid, block, RG::SMEM, s, a);
+        }
         return check();
     }
     static int row_plain(const PlainRowArgs& a, cudaStream_t s) {
@@ -405,15 +550,35 @@ template <typename R, int L> struct LineOps {
         SLM_LAUNCH((row_plain_kernel<R, L>), grid, block, RG::SMEM, s, a);
         return check();
     }
+    // a.tile_map != null selects the persistent TMA kernel on min(tiles, a.persist_ctas) resident CTAs
     static int col_pass(int alg, const ColArgs& a, cudaStream_t s) {
-        const dim3 grid((unsigned)((long long)a.B * (a.W / CG::TC))), block(CG::THREADS);
-        if (alg == ALG_GS) SLM_LAUNCH((col_pass_kernel<R, L, ALG_GS>), grid, block, CG::SMEM, s, a);
-        else SLM_LAUNCH((col_pass_kernel<R, L, ALG_GD>), grid, block, CG::SMEM, s, a);
+        const long long tiles = (long long)a.B * (a.W / CG::TC);
+        const dim3 block(CG::THREADS);
+        if (a.tile_map) {
+            const TileMap& tm = *static_cast<const TileMap*>(a.tile_map);
+            const dim3 grid((unsigned)(tiles < a.persist_ctas ? tiles : a.persist_ctas));
+            if (alg == ALG_GS) SLM_LAUNCH((col_pass_kernel<R, L, ALG_GS, 1>), grid, block, PSMEM, s, a, tm);
+            else SLM_LAUNCH((col_pass_kernel<R, L, ALG_GD, 1>), grid, block, PSMEM, s, a, tm);
+        } else {
+            const TileMap tm{};
+            const dim3 grid((unsigned)tiles);
+            if (alg == ALG_GS) SLM_LAUNCH((col_pass_kernel<R, L, ALG_GS, 0>), grid, block, CG::SMEM, s, a, tm);
+            else SLM_LAUNCH((col_pass_kernel<R, L, ALG_GD, 0>), grid, block, CG::SMEM, s, a, tm);
+        }
         return check();
     }
     static int col_plain(const PlainColArgs& a, cudaStream_t s) {
-        const dim3 grid((unsigned)((long long)a.B * (a.W / CG::TC))), block(CG::THREADS);
-        SLM_LAUNCH((col_plain_kernel<R, L>), grid, block, CG::SMEM, s, a);
+        const long long tiles = (long long)a.B * (a.W / CG::TC);
+        const dim3 block(CG::THREADS);
+        if (a.tile_map) {
+            const TileMap& tm = *static_cast<const TileMap*>(a.tile_map);
+            const dim3 grid((unsigned)(tiles < a.persist_ctas ? tiles : a.persist_ctas));
+            SLM_LAUNCH((col_plain_kernel<R, L, 1>), grid, block, PSMEM, s, a, tm);
+        } else {
+            const TileMap tm{};
+            const dim3 grid((unsigned)tiles);
+            SLM_LAUNCH((col_plain_kernel<R, L, 0>), grid, block, CG::SMEM, s, a, tm);
+        }
         return check();
     }
 };

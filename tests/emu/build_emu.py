@@ -40,7 +40,7 @@ def build(force=False) -> str:
         return LIB
     os.makedirs(OUT, exist_ok=True)
     base = ["g++", "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-DSLM_EMULATE", "-x", "c++",
-            "-I", HERE, "-I", CSRC, "-Wno-unused-function"]
+            "-I", HERE, "-I", CSRC, "-Wno-unused-function", "-Wno-psabi"]
     jobs = [(os.path.join(CSRC, "engine.cu"), os.path.join(OUT, "engine.o"), []),
             (os.path.join(CSRC, "registry.cu"), os.path.join(OUT, "registry.o"), [])]
     for n in line_lengths():

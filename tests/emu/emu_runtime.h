@@ -117,6 +117,19 @@ template <class T> inline T shfl_xor(T v, int m) {
     return r;
 }
 
+template <class T> inline T shfl_idx(T v, int src) {
+    State& s = S();
+    unsigned lane = s.cur->tid % 32;
+    WarpSlot& ws = s.warps[s.cur->tid / 32];
+    int p = s.cur->shfl_parity;
+    s.cur->shfl_parity ^= 1;
+    memcpy(&ws.buf[p][lane], &v, sizeof(T));
+    sync_warp();
+    T r;
+    memcpy(&r, &ws.buf[p][src % 32], sizeof(T));
+    return r;
+}
+
 template <class F> void run_cta(dim3 bidx, dim3 grid, dim3 block, size_t smem_bytes, F& f) {
     State& s = S();
     const unsigned n = block.x * block.y * block.z;
@@ -130,8 +143,8 @@ template <class F> void run_cta(dim3 bidx, dim3 grid, dim3 block, size_t smem_by
     s.n = s.alive = n;
     s.bar_count = 0;
     s.block_idx = bidx; s.block_dim = block; s.grid_dim = grid;
-    std::vector<unsigned char> smem(smem_bytes + 64, 0xFF);
-    s.smem = (unsigned char*)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
+    std::vector<unsigned char> smem(smem_bytes + 256, 0xFF);
+    s.smem = (unsigned char*)(((uintptr_t)smem.data() + 127) & ~(uintptr_t)127);
     s.body = [](void* a) { (*static_cast<F*>(a))(); };
     s.body_arg = &f;
     for (unsigned i = 0; i < n; ++i) {
@@ -193,6 +206,7 @@ inline void fence_device() {}
 inline unsigned atomic_inc_wrap(unsigned* p, unsigned limit) { unsigned o = *p; *p = (o >= limit) ? 0 : o + 1; return o; }
 inline float shfl_xor(float v, int m) { return emu::shfl_xor(v, m); }
 inline double shfl_xor(double v, int m) { return emu::shfl_xor(v, m); }
+inline unsigned shfl_idx(unsigned v, int src) { return emu::shfl_idx(v, src); }
 inline void sync_cta() { emu::sync_cta(); }
 // compiled with -ffp-contract=off, so plain operators are single IEEE operations
 inline double mul_rn(double a, double b) { return a * b; }

@@ -91,7 +91,7 @@ def check_gs_device_setup(make_engine, shape, precision, kind, loops=6):
     holo = eng.to_host(res.hologram)[0]
     assert np.all(np.abs(holo) <= np.pi + 1e-12)
     if kind != "traps":
-        assert abs(e[-1] - errs[-1]) < 0.2 * errs[-1]        # same basin statistically
+        assert e[-1] < e[0] and 0.5 * errs[-1] < e[-1] < 1.5 * errs[-1]     # same basin statistically
     eng.close()
 
 
