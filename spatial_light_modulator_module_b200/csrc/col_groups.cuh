@@ -1,0 +1,267 @@
+// Warp-specialised persistent column kernels (sm_100a).
+//
+// One resident CTA per SM walks the column tiles ([H rows][TC columns]) round-robin:
+//   * a PRODUCER warp streams tiles in and out with TMA (tma.cuh): the next tile's field data is
+//     loaded (32B/64B-swizzled) while the current one is transformed, the tile's 8-bit target rows
+//     are staged beside it, and finished tiles are written back with a TMA store;
+//   * the COMPUTE warps own whole columns: the M = H/E threads of a column are consecutive, so a
+//     column's transform synchronises on a named barrier over its own warps only.  Column groups
+//     run out of phase with each other, which hides barrier, shared-memory and reduction latency
+//     that a CTA-wide lock-step exposes (ncu: profiles/).
+// Hand-over is by mbarriers: full[s] (tile s landed), done[s] (every compute thread has written its
+// results into tile s and fenced them for the async proxy).  A tile's buffer is reused for its own
+// output, so two tile buffers suffice.
+#pragma once
+#include "passes.cuh"
+
+namespace slm {
+
+constexpr int lines_per_group(int m) { return m % 32 == 0 ? 1 : (m % 16 == 0 ? 2 : (m % 8 == 0 ? 4 : 8)); }
+
+template <typename R, int H> struct ColGroupGeom {
+    using P = FftPlan<H>;
+    using CG = ColGeom<R, H>;
+    static constexpr int E = P::E, M = P::M, TC = CG::TC;
+    static constexpr int COMPUTE = TC * M;                        // compute threads
+    static constexpr int NW = COMPUTE / 32;                       // compute warps
+    static constexpr int THREADS = COMPUTE + 32;                  // + producer warp
+    static constexpr int ROWB = TC * (int)sizeof(cpx<R>);         // bytes of one tile row
+    static constexpr int LPG = lines_per_group(M);
+    static constexpr int GROUPS = TC / LPG;
+    static constexpr int GROUP_THREADS = LPG * M;
+    static constexpr bool OK = (ROWB == 64 || ROWB == 32) && COMPUTE % 32 == 0 && TC % LPG == 0 && GROUPS <= 14 &&
+                               H % 32 == 0 && NW <= 32;
+    static constexpr size_t TILE = (size_t)H * ROWB;
+    static constexpr size_t XCH = (size_t)TC * P::NP * sizeof(cpx<R>);
+    static constexpr size_t GREY = (size_t)H * TC;
+    // [tile0][tile1][exchange][grey0][grey1][lut][red 2 x NW][counters][barriers]
+    static constexpr size_t OFF_XCH = 2 * TILE;
+    static constexpr size_t OFF_GREY = OFF_XCH + XCH;
+    static constexpr size_t OFF_LUT = OFF_GREY + 2 * GREY;
+    static constexpr size_t OFF_RED = OFF_LUT + 256 * sizeof(R);
+    static constexpr size_t OFF_CNT = OFF_RED + 2 * 32 * sizeof(Partial);
+    static constexpr size_t OFF_BAR = OFF_CNT + 16;
+    static constexpr size_t SMEM = OFF_BAR + 4 * 16;
+    using Sync = GroupSync<GROUP_THREADS>;
+};
+
+// copy TC bytes (one tile row of the 8-bit target)
+template <int TC> SLM_DEV void copy_grey_row(const uint8_t* src, uint8_t* dst) {
+    if (TC == 8) *reinterpret_cast<uint2*>(dst) = ld_ro(reinterpret_cast<const uint2*>(src));
+    else if (TC == 4) *reinterpret_cast<unsigned*>(dst) = ld_ro(reinterpret_cast<const unsigned*>(src));
+    else if (TC == 2) *reinterpret_cast<unsigned short*>(dst) = ld_ro(reinterpret_cast<const unsigned short*>(src));
+    else *dst = ld_ro(src);
+}
+
+template <typename R, int H, int MODE>
+SLM_GLOBAL void SLM_LAUNCH_BOUNDS((ColGroupGeom<R, H>::THREADS), 1)
+col_group_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SLM_GRID_CONSTANT TileMap tm_out) {
+    using G = ColGroupGeom<R, H>;
+    using P = FftPlan<H>;
+    constexpr int E = G::E, M = G::M, TC = G::TC, ROWB = G::ROWB, CS = (int)sizeof(cpx<R>);
+    constexpr bool HAS_T = MODE == CGM_GS || MODE == CGM_GD || MODE == CGM_GD_POST;
+    constexpr bool HAS_OUT = MODE != CGM_STATS;
+    constexpr bool IS_GD = MODE == CGM_GD || MODE == CGM_GD_POST;
+    constexpr bool IS_STATS = MODE == CGM_STATS || MODE == CGM_STATS_KEEP;
+    const ColArgs& a = ga.c;
+    SLM_DYN_SMEM(raw);
+    unsigned char* const tile0 = raw;
+    unsigned char* const tile1 = raw + G::TILE;
+    uint8_t* const grey0 = raw + G::OFF_GREY;
+    uint8_t* const grey1 = grey0 + G::GREY;
+    R* const lut_s = reinterpret_cast<R*>(raw + G::OFF_LUT);
+    Partial* const red = reinterpret_cast<Partial*>(raw + G::OFF_RED);
+    unsigned* const cnt = reinterpret_cast<unsigned*>(raw + G::OFF_CNT);
+    TileBarrier* const full = reinterpret_cast<TileBarrier*>(raw + G::OFF_BAR);       // [2]
+    TileBarrier* const done = full + 2;                                                // [2]
+
+    const int t = threadIdx.x;
+    const int tiles = a.W / TC;
+    const long long total = (long long)a.B * tiles;
+    const bool use_t8 = HAS_T && a.T8 != nullptr;
+    if (t == 0) {
+        mbar_init(full + 0, use_t8 ? 33u : 1u); mbar_init(full + 1, use_t8 ? 33u : 1u);
+        mbar_init(done + 0, (unsigned)G::COMPUTE); mbar_init(done + 1, (unsigned)G::COMPUTE);
+        cnt[0] = 0; cnt[1] = 0;
+        mbar_fence_init();
+    }
+    if (use_t8) {
+        const R* lut = static_cast<const R*>(a.lut);
+        for (int i = t; i < 256; i += G::THREADS) lut_s[i] = ld_ro(lut + i);
+    }
+    sync_cta();
+    auto rests = [&](int b) { return MODE != CGM_COMPLEX && ld_cg(&a.stats[b].done) != 0; };
+
+    if (t >= G::COMPUTE) {
+        // ================= producer warp =================
+        const int lane = t - G::COMPUTE;
+        auto issue = [&](long long g, int s) {
+            const int b = (int)(g / tiles), tile = (int)(g % tiles);
+            if (lane == 0) {
+                tile_store_wait_read();          // the store that last read this buffer has drained it
+                tile_load(tm_in, s ? tile1 : tile0, full + s, (long long)b * H, H, (long long)tile * ROWB, ROWB, (int)sizeof(R));
+            }
+            if (use_t8) {
+                shfl_idx(0u, 0);                 // warp convergence point: lane 0's wait covers the grey buffer too
+                const uint8_t* src = a.T8 + (size_t)b * H * a.W + (size_t)tile * TC;
+                uint8_t* dst = s ? grey1 : grey0;
+#pragma unroll 8
+                for (int row = lane; row < H; row += 32) copy_grey_row<TC>(src + (size_t)row * a.W, dst + (size_t)row * TC);
+                mbar_arrive(full + s);
+            }
+        };
+        long long g = blockIdx.x;
+        while (g < total && rests((int)(g / tiles))) g += gridDim.x;
+        if (g < total) issue(g, 0);
+        unsigned k = 0;
+        while (g < total) {
+            long long gn = g + gridDim.x;
+            while (gn < total && rests((int)(gn / tiles))) gn += gridDim.x;
+            const int s = (int)(k & 1u);
+            if (gn < total) issue(gn, s ^ 1);
+            mbar_wait(done + s, (k >> 1) & 1u);
+            if (HAS_OUT && lane == 0) {
+                const int b = (int)(g / tiles), tile = (int)(g % tiles);
+                tile_store(tm_out, s ? tile1 : tile0, (long long)b * H, H, (long long)tile * ROWB, ROWB, (int)sizeof(R));
+                tile_store_commit();
+            }
+            g = gn;
+            ++k;
+        }
+        if (lane == 0) tile_store_wait_all();
+        return;
+    }
+
+    // ================= compute warps =================
+    const int c = t / M, j = t % M, lane = t % 32, warp = t / 32;
+    const typename G::Sync sync{1 + c / G::LPG};
+    cpx<R>* const line = reinterpret_cast<cpx<R>*>(raw + G::OFF_XCH) + (size_t)c * P::NP;
+    const cpx<R>* tw = static_cast<const cpx<R>*>(a.tw);
+    const double hw = (double)H * (double)a.W;
+    cpx<R> v[E];
+    unsigned k = 0;
+    // the "plane rests" flag of a tile is requested one tile ahead, so its L2 round trip is never waited for
+    bool rest_next = blockIdx.x < total ? rests((int)(blockIdx.x / tiles)) : true;
+    for (long long g = blockIdx.x; g < total; g += gridDim.x) {
+        const int b = (int)(g / tiles), tile = (int)(g % tiles);
+        const bool rest_cur = rest_next;
+        rest_next = (g + gridDim.x < total) ? rests((int)((g + gridDim.x) / tiles)) : true;
+        if (rest_cur) continue;
+        const int s = (int)(k & 1u);
+        unsigned char* const buf = s ? tile1 : tile0;
+        PlaneStats* st = a.stats ? a.stats + b : nullptr;
+        double s0 = 0, imax = 0, norm = 0;
+        if (MODE == CGM_GS || IS_GD) { s0 = ld_cg(&st->scale); imax = ld_cg(&st->imax); norm = ld_ro(a.norm + b); }
+        mbar_wait(full + s, (k >> 1) & 1u);
+#pragma unroll
+        for (int r = 0; r < E; ++r)
+            v[r] = *reinterpret_cast<const cpx<R>*>(buf + tile_swizzle<ROWB>((unsigned)((j + r * M) * ROWB + c * CS)));
+        R tv[E], aux[E];
+        if (HAS_T && !use_t8) {                                   // real-valued targets: planes in global memory
+            const size_t off = (size_t)b * H * a.W + (size_t)j * a.W + tile * TC + c;
+            const R* T = static_cast<const R*>(a.Treal) + off;
+            const R* Q = static_cast<const R*>(a.plane2) + off;
+#pragma unroll
+            for (int r = 0; r < E; ++r) { tv[r] = ld_ro(T + (size_t)r * M * a.W); aux[r] = ld_ro(Q + (size_t)r * M * a.W); }
+        }
+        if (MODE == CGM_COMPLEX && ga.mode_inverse) line_fft<R, H, +1, 1>(v, line, j, tw, sync);
+        else if (MODE != CGM_GD_POST) line_fft<R, H, -1, 1>(v, line, j, tw, sync);
+
+        // ---- pointwise step and per-thread sums ----
+        R mx = 0, sa = 0, sb = 0, sc = 0;
+        const R s0r = (R)s0;
+        if (MODE == CGM_GS || IS_GD) {
+            if (use_t8) {                                          // grey level and its table entry, both from shared memory
+                const uint8_t* gsrc = (s ? grey1 : grey0) + (size_t)j * TC + c;
+#pragma unroll
+                for (int r = 0; r < E; ++r) { const int gl = gsrc[(size_t)r * M * TC]; tv[r] = (R)gl; aux[r] = lut_s[gl]; }
+            }
+            const R gdk = sizeof(R) == 8 ? (R)0 : (R)(norm / imax);
+#pragma unroll
+            for (int r = 0; r < E; ++r) {
+                const R m2 = cnorm2(v[r]);
+                if (MODE == CGM_GS) {                                 // algorithms.py:33,36-38 (see col_pass_tile)
+                    const R u = s0r * m2, d = u - tv[r];
+                    mx = fmax(mx, m2); sa += d * d; sb += d * u; sc += u * u;
+                    v[r] = (m2 == (R)0) ? mk<R>(copysign(aux[r], v[r].x), (R)0) : cscale(v[r], aux[r] * rsqrt_fast(m2));
+                } else {                                              // algorithms.py:85-88,92
+                    R I;
+                    if (sizeof(R) == 8) I = (R)(((double)m2 * norm) / imax);
+                    else I = m2 * gdk;
+                    const R d = I - tv[r];
+                    sa += d * d;
+                    v[r] = cscale(cscale(v[r], aux[r]), d);
+                }
+            }
+        } else if (IS_STATS) {
+#pragma unroll
+            for (int r = 0; r < E; ++r) mx = fmax(mx, cnorm2(v[r]));
+        } else {
+            const R sc_out = (R)ga.scale;
+#pragma unroll
+            for (int r = 0; r < E; ++r) v[r] = cscale(v[r], sc_out);
+        }
+
+        // ---- tile reduction without a CTA barrier: the last warp to arrive sums the warps' partials ----
+        constexpr int FIELDS = MODE == CGM_GS ? F_ALL : (IS_GD ? F_A : F_MX);
+        bool tail_warp = false;
+        unsigned ticket = 0;
+        Partial* plane_partials = nullptr;
+        if (MODE != CGM_COMPLEX) {
+            Partial p; p.mx = (double)mx; p.a = (double)sa; p.b = (double)sb; p.c = (double)sc;
+            p = warp_reduce<FIELDS>(p);
+            unsigned arrived = 0;
+            if (lane == 0) {
+                red[s * 32 + warp] = p;
+                fence_block();
+                arrived = atomic_add_shared(cnt + s, 1u);
+            }
+            arrived = shfl_idx(arrived, 0);
+            tail_warp = arrived == (unsigned)G::NW - 1;
+            if (tail_warp) {
+                fence_block();
+                Partial q; q.mx = 0; q.a = 0; q.b = 0; q.c = 0;
+                if (lane < G::NW) q = red[s * 32 + lane];
+                q = warp_reduce<FIELDS>(q);
+                plane_partials = a.partial + (size_t)b * tiles;
+                if (lane == 0) { cnt[s] = 0; ticket = publish_partial(q, plane_partials, tile, tiles, a.counter + b); }
+            }
+        }
+
+        if (MODE == CGM_GS || IS_GD) line_fft<R, H, +1, 1>(v, line, j, tw, sync);
+        if (HAS_OUT) {
+#pragma unroll
+            for (int r = 0; r < E; ++r)
+                *reinterpret_cast<cpx<R>*>(buf + tile_swizzle<ROWB>((unsigned)((j + r * M) * ROWB + c * CS))) = v[r];
+            fence_async_smem();
+        }
+        mbar_arrive(done + s);
+        ++k;
+
+        if (tail_warp) {
+            Partial tot;
+            if (collect_if_last<FIELDS>(ticket, lane, plane_partials, tiles, tot) && lane == 0) {
+                if (IS_STATS) {
+                    st->imax = tot.mx; st->scale = ld_ro(a.norm + b) / tot.mx;
+                } else {
+                    double err;
+                    if (MODE == CGM_GS) {
+                        const double sN = norm / tot.mx;
+                        const double s0u = (double)s0r;
+                        const double dl = (s0u != 0.0) ? sN / s0u - 1.0 : 0.0;
+                        err = (tot.a + 2.0 * dl * tot.b + dl * dl * tot.c) / hw;
+                        st->imax = tot.mx; st->scale = sN;
+                    } else {
+                        err = tot.a / hw;
+                    }
+                    const int it = st->iters;
+                    a.err_curve[(size_t)b * a.max_loops + it] = err;
+                    st->err = err; st->iters = it + 1;
+                    st->done = !(err > a.tolerance);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace slm

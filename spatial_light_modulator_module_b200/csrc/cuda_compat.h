@@ -29,11 +29,15 @@ template <typename T> SLM_DEV T ld_ro(const T* p) { return __ldg(p); }     // im
 template <typename T> SLM_DEV T ld_cg(const T* p) { return __ldcg(p); }    // streamed plane data (L2 only)
 template <typename T> SLM_DEV void st_cg(T* p, T v) { __stcg(p, v); }
 SLM_DEV void fence_device() { __threadfence(); }
+SLM_DEV void fence_block() { __threadfence_block(); }
+SLM_DEV unsigned atomic_add_shared(unsigned* p, unsigned v) { return atomicAdd(p, v); }
 SLM_DEV unsigned atomic_inc_wrap(unsigned* p, unsigned limit) { return atomicInc(p, limit); }
 SLM_DEV float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 SLM_DEV double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 SLM_DEV unsigned shfl_idx(unsigned v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 SLM_DEV void sync_cta() { __syncthreads(); }
+// named barrier `id` (1..15) over `nthreads` threads (whole warps) of the CTA
+SLM_DEV void sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 // IEEE operations that must not be contracted into FMAs (bit parity with numpy)
 SLM_DEV double mul_rn(double a, double b) { return __dmul_rn(a, b); }
 SLM_DEV double add_rn(double a, double b) { return __dadd_rn(a, b); }

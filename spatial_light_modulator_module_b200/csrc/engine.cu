@@ -51,9 +51,9 @@ struct slm_ctx {
     size_t bytes = 0;
     long long launches = 0;
     std::vector<void*> owned;
-    // TMA tile map over X for the persistent column kernels (context precision), and their grid
-    TileMap tile_map;
-    bool use_tma = false;
+    // TMA tile maps over X and Y for the warp-specialised column kernel (context precision), its grid
+    TileMap map_x, map_y;
+    bool use_groups = false;
     int persist_ctas = 1;
     // optional per-launch device timing (slm_ctx_profile): event pairs on the context's stream
     bool profiling = false;
@@ -111,44 +111,72 @@ static int make_twiddles(slm_ctx* c, int N, int prec, void** out) {
     return 0;
 }
 
-// Describe X ([max_batch*H rows][W complex columns]) to the TMA unit: 2-D tensor of real elements,
-// box = TC complex columns x up to 256 rows, dense (unswizzled) shared-memory image.
-static int make_tile_map(slm_ctx* c) {
+// Describe a field plane stack ([rows][W complex columns]) to the TMA unit: 2-D tensor of real
+// elements, box = TC complex columns x up to 256 rows, 32B/64B-swizzled shared-memory image.
+static int make_tile_map(slm_ctx* c, void* base, long long rows, TileMap* out) {
     const size_t cs = 2 * real_size(c->prec);
-    const int tc = c->col->cols_per_cta;
+    const int row_bytes = c->col->group_row_bytes;
+    const int box_rows = c->H < 256 ? c->H : 256;
 #ifdef SLM_EMULATE
-    c->tile_map.base = static_cast<const unsigned char*>(c->X);
-    c->tile_map.pitch_bytes = (size_t)c->W * cs;
-    c->tile_map.col_bytes = (int)cs;
-    c->tile_map.box_rows = c->H < 256 ? c->H : 256;
-    c->persist_ctas = 3;
-    c->use_tma = getenv("SLM_NO_TMA") == nullptr;
+    (void)rows;
+    out->base = static_cast<unsigned char*>(base);
+    out->pitch_bytes = (size_t)c->W * cs;
+    out->box_rows = box_rows;
+    out->row_bytes = row_bytes;
     return 0;
 #else
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    SLM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
-    if (!fn || q != cudaDriverEntryPointSuccess) return fail(SLM_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
-    const int box_rows = c->H < 256 ? c->H : 256;
-    const cuuint64_t dims[2] = {(cuuint64_t)2 * c->W, (cuuint64_t)c->max_batch * c->H};
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        SLM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) return fail(SLM_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)2 * c->W, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)c->W * cs};
-    const cuuint32_t box[2] = {(cuuint32_t)(2 * tc), (cuuint32_t)box_rows};
+    const cuuint32_t box[2] = {(cuuint32_t)(row_bytes / real_size(c->prec)), (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = reinterpret_cast<EncodeFn>(fn)(
-        &c->tile_map.map, c->prec == PREC_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c->X,
-        dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult r = encode(&out->map, c->prec == PREC_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                              base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(SLM_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
-    c->tile_map.box_rows = box_rows;
+    out->box_rows = box_rows;
+    out->row_bytes = row_bytes;
+    return 0;
+#endif
+}
+
+static int setup_groups(slm_ctx* c) {
+    c->use_groups = false;
+    if (!c->col->group_ok || getenv("SLM_NO_GROUPS")) return 0;
+    SLM_TRY(make_tile_map(c, c->X, (long long)c->max_batch * c->H, &c->map_x));
+    SLM_TRY(make_tile_map(c, c->Y, (long long)c->max_batch * c->H, &c->map_y));
+#ifdef SLM_EMULATE
+    c->persist_ctas = 3;
+#else
     int sms = 0;
     SLM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
     c->persist_ctas = sms > 0 ? sms : 1;
-    c->use_tma = getenv("SLM_NO_TMA") == nullptr;
-    return 0;
 #endif
+    c->use_groups = true;
+    return 0;
+}
+
+// Launch one mode of the warp-specialised column kernel over X (in) -> map_out.
+static int launch_group(slm_ctx* c, int mode, int batch, const ColArgs* loop, const TileMap* map_out, int inverse, double scale) {
+    ColGroupArgs ga{};
+    if (loop) ga.c = *loop;
+    ga.mode_inverse = inverse; ga.scale = scale;
+    ga.c.B = batch; ga.c.W = c->W; ga.c.stats = c->stats; ga.c.partial = c->partial; ga.c.counter = c->counter;
+    ga.c.norm = c->norm; ga.c.tw = c->tw_col;
+    const int kind = (mode == CGM_STATS || mode == CGM_STATS_KEEP) ? K_COL_STATS : (mode == CGM_COMPLEX ? K_COL_PLAIN : K_COL_PASS);
+    SLM_TIMED(kind, c->col->col_group(mode, ga, &c->map_x, map_out ? map_out : &c->map_x, c->persist_ctas, c->stream));
+    return 0;
 }
 
 static int ensure_loops(slm_ctx* c, int max_loops) {
@@ -210,7 +238,7 @@ extern "C" int slm_ctx_create(slm_ctx** out, int device, int H, int W, int max_b
     if (!rc && precision == PREC_F64) { rc = make_twiddles(c, W, PREC_F32, &c->tw_row32); if (!rc) rc = make_twiddles(c, H, PREC_F32, &c->tw_col32); }
     if (!rc && precision == PREC_F32) { c->tw_row32 = c->tw_row; c->tw_col32 = c->tw_col; }
     if (!rc) rc = ensure_loops(c, 256);
-    if (!rc) rc = make_tile_map(c);
+    if (!rc) rc = setup_groups(c);
     if (!rc && cudaMemset(c->counter, 0, (size_t)max_batch * sizeof(unsigned)) != cudaSuccess) rc = fail(SLM_ERR_CUDA, "cudaMemset(counter)");
     if (!rc && cudaMemset(c->stats, 0, (size_t)max_batch * sizeof(PlaneStats)) != cudaSuccess) rc = fail(SLM_ERR_CUDA, "cudaMemset(stats)");
     if (rc) { std::string keep = g_err; slm_ctx_destroy(c); g_err = keep; return rc; }
@@ -295,8 +323,8 @@ static int setup_field(slm_ctx* c, int batch, const uint8_t* T8, const void* amp
     PlainColArgs ca{};
     ca.B = batch; ca.W = c->W; ca.output = OUT_COMPLEX; ca.inverse = 1; ca.scale = 1.0 / ((double)c->H * c->W);
     ca.in = c->X; ca.out = c->Y; ca.tw = f32path ? c->tw_col32 : c->tw_col;
-    if (c->use_tma && col == c->col) { ca.tile_map = &c->tile_map; ca.persist_ctas = c->persist_ctas; }
-    SLM_TIMED(K_COL_PLAIN, col->col_plain(ca, c->stream));
+    if (c->use_groups && col == c->col) SLM_TRY(launch_group(c, CGM_COMPLEX, batch, nullptr, &c->map_y, 1, ca.scale));
+    else SLM_TIMED(K_COL_PLAIN, col->col_plain(ca, c->stream));
     *source = f32path ? ROW_FROM_A32 : ROW_FROM_A;
     return 0;
 }
@@ -306,8 +334,14 @@ static PlainColArgs stats_args(slm_ctx* c, int batch, int output, void* out) {
     a.B = batch; a.W = c->W; a.output = output; a.inverse = 0; a.scale = 1.0;
     a.in = c->X; a.out = out; a.norm = c->norm; a.stats = c->stats; a.partial = c->partial; a.counter = c->counter;
     a.tw = c->tw_col;
-    if (c->use_tma) { a.tile_map = &c->tile_map; a.persist_ctas = c->persist_ctas; }
     return a;
+}
+
+// max |C|^2 of the column transform of X -> stats (GS iteration 0 / every GD iteration / preview)
+static int run_stats(slm_ctx* c, int batch) {
+    if (c->use_groups) return launch_group(c, CGM_STATS, batch, nullptr, nullptr, 0, 1.0);
+    SLM_TIMED(K_COL_STATS, c->col->col_plain(stats_args(c, batch, OUT_STATS, nullptr), c->stream));
+    return 0;
 }
 
 extern "C" int slm_fft2(slm_ctx* c, int batch, const void* in, void* out, int inverse) {
@@ -320,8 +354,13 @@ extern "C" int slm_fft2(slm_ctx* c, int batch, const void* in, void* out, int in
     ca.B = batch; ca.W = c->W; ca.output = OUT_COMPLEX; ca.inverse = inverse;
     ca.scale = inverse ? 1.0 / ((double)c->H * c->W) : 1.0;
     ca.in = c->X; ca.out = out; ca.tw = c->tw_col;
-    if (c->use_tma) { ca.tile_map = &c->tile_map; ca.persist_ctas = c->persist_ctas; }
-    SLM_TIMED(K_COL_PLAIN, c->col->col_plain(ca, c->stream));
+    if (c->use_groups) {
+        TileMap map_out;
+        SLM_TRY(make_tile_map(c, out, (long long)batch * c->H, &map_out));
+        SLM_TRY(launch_group(c, CGM_COMPLEX, batch, nullptr, &map_out, inverse, ca.scale));
+    } else {
+        SLM_TIMED(K_COL_PLAIN, c->col->col_plain(ca, c->stream));
+    }
     return 0;
 }
 
@@ -346,17 +385,17 @@ extern "C" int slm_gs_run(slm_ctx* c, int batch, const uint8_t* T8, const void* 
     }
     SLM_TIMED(K_ROW_PASS, c->row->row_pass(ALG_GS, ra, c->stream));
     // exact scale of iteration 0 so the one-pass error of later iterations is well conditioned
-    SLM_TIMED(K_COL_STATS, c->col->col_plain(stats_args(c, batch, OUT_STATS, nullptr), c->stream));
+    SLM_TRY(run_stats(c, batch));
 
     ColArgs ca{};
     ca.B = batch; ca.W = c->W; ca.X = c->X; ca.Y = c->Y; ca.T8 = T8; ca.Treal = Treal; ca.plane2 = amp_real;
     ca.lut = c->lut; ca.norm = c->norm; ca.stats = c->stats; ca.partial = c->partial; ca.counter = c->counter;
     ca.err_curve = c->err_curve; ca.max_loops = max_loops; ca.tolerance = tolerance;
     ca.inv_hw = ra.inv_hw; ca.tw = c->tw_col;
-    if (c->use_tma) { ca.tile_map = &c->tile_map; ca.persist_ctas = c->persist_ctas; }
     ra.source = ROW_FROM_Y;
     for (int k = 0; k < max_loops; ++k) {
-        SLM_TIMED(K_COL_PASS, c->col->col_pass(ALG_GS, ca, c->stream));
+        if (c->use_groups) SLM_TRY(launch_group(c, CGM_GS, batch, &ca, &c->map_y, 0, 1.0));
+        else SLM_TIMED(K_COL_PASS, c->col->col_pass(ALG_GS, ca, c->stream));
         if (k + 1 < max_loops) { SLM_TIMED(K_ROW_PASS, c->row->row_pass(ALG_GS, ra, c->stream)); }
     }
     ra.final_pass = 1;
@@ -388,17 +427,26 @@ extern "C" int slm_gd_run(slm_ctx* c, int batch, const uint8_t* T8, const void* 
     ca.lut = c->lut; ca.norm = c->norm; ca.stats = c->stats; ca.partial = c->partial; ca.counter = c->counter;
     ca.err_curve = c->err_curve; ca.max_loops = max_loops; ca.tolerance = tolerance;
     ca.inv_hw = ra.inv_hw; ca.tw = c->tw_col;
-    if (c->use_tma) { ca.tile_map = &c->tile_map; ca.persist_ctas = c->persist_ctas; }
-    const PlainColArgs sa = stats_args(c, batch, OUT_STATS, nullptr);
     ra.source = ROW_FROM_Y;
     for (int k = 0; k < max_loops; ++k) {
-        SLM_TIMED(K_COL_STATS, c->col->col_plain(sa, c->stream));            // amax(output_unnormed), algorithms.py:86
-        SLM_TIMED(K_COL_PASS, c->col->col_pass(ALG_GD, ca, c->stream));
+        if (c->use_groups) {
+            // med_output = fft2(...) is finished in place in X while its max is taken (algorithms.py:84-86),
+            // so the gradient pass starts from the transformed field
+            SLM_TRY(launch_group(c, CGM_STATS_KEEP, batch, nullptr, &c->map_x, 0, 1.0));
+            SLM_TRY(launch_group(c, CGM_GD_POST, batch, &ca, &c->map_y, 0, 1.0));
+        } else {
+            SLM_TRY(run_stats(c, batch));                                     // amax(output_unnormed), algorithms.py:86
+            SLM_TIMED(K_COL_PASS, c->col->col_pass(ALG_GD, ca, c->stream));
+        }
         if (k + 1 < max_loops) { SLM_TIMED(K_ROW_PASS, c->row->row_pass(ALG_GD, ra, c->stream)); }
     }
     ra.final_pass = 1;
     SLM_TIMED(K_ROW_PASS, c->row->row_pass(ALG_GD, ra, c->stream));
-    if (expected_out) { SLM_TIMED(K_COL_PLAIN, c->col->col_plain(stats_args(c, batch, OUT_INTENSITY_GD, expected_out), c->stream)); }
+    if (expected_out) {
+        PlainColArgs ia = stats_args(c, batch, OUT_INTENSITY_GD, expected_out);
+        ia.skip_fft = c->use_groups ? 1 : 0;       // X already holds med_output
+        SLM_TIMED(K_COL_PLAIN, c->col->col_plain(ia, c->stream));
+    }
     return 0;
 }
 
@@ -445,7 +493,7 @@ extern "C" int slm_expected_outcome(slm_ctx* c, int batch, const double* hologra
     PlainRowArgs ra{};
     ra.B = batch; ra.H = c->H; ra.input = IN_PHASE; ra.inverse = 0; ra.in = hologram; ra.out = c->X; ra.tw = c->tw_row;
     SLM_TIMED(K_ROW_PLAIN, c->row->row_plain(ra, c->stream));
-    SLM_TIMED(K_COL_STATS, c->col->col_plain(stats_args(c, batch, OUT_STATS, nullptr), c->stream));
+    SLM_TRY(run_stats(c, batch));
     SLM_TIMED(K_COL_PLAIN, c->col->col_plain(stats_args(c, batch, OUT_INTENSITY_PREVIEW, out), c->stream));
     return 0;
 }

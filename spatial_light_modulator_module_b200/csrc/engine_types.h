@@ -64,8 +64,21 @@ struct ColArgs {
     double tolerance;
     double inv_hw;
     const void* tw;          // complex<R> [H] column twiddles
-    const void* tile_map;    // host TileMap* over X (tma.cuh) -> persistent TMA kernel; null -> one CTA per tile
-    int persist_ctas;        // resident CTAs of the persistent kernel
+};
+
+// ---- warp-specialised persistent column kernel (col_groups.cuh) ---------------------------------------
+enum ColGroupMode {
+    CGM_GS = 0,       // Fourier-plane step of GS      (== col_pass_kernel<GS>)
+    CGM_GD = 1,       // Fourier-plane step of GD      (== col_pass_kernel<GD>)
+    CGM_STATS = 2,    // forward transform, max |C|^2  (== col_plain_kernel OUT_STATS)
+    CGM_COMPLEX = 3,  // plain transform, complex out  (== col_plain_kernel OUT_COMPLEX)
+    CGM_STATS_KEEP = 4,  // CGM_STATS that also writes the transformed field back (GD: F = fft2(b) kept in X)
+    CGM_GD_POST = 5,     // CGM_GD on an already transformed field: no forward transform
+};
+struct ColGroupArgs {
+    int mode_inverse;        // CGM_COMPLEX: transform direction
+    double scale;            // CGM_COMPLEX: output scale
+    ColArgs c;               // loop arguments; B, W, stats, partial, counter, norm, tw are used by every mode
 };
 
 // ---- plain transforms / setup / preview ------------------------------------------------------
@@ -96,6 +109,7 @@ struct PlainColArgs {
     int B, W;
     int output;              // PlainColOutput
     int inverse;
+    int skip_fft;            // intensity outputs: `in` already holds the column-transformed field
     double scale;            // OUT_COMPLEX: multiply results (1/(HW) for ifft2)
     const void* in;          // complex<R> [B][H][W]
     void* out;               // complex<R> [B][H][W] or double [B][H][W]
@@ -104,8 +118,6 @@ struct PlainColArgs {
     Partial* partial;
     unsigned* counter;
     const void* tw;
-    const void* tile_map;    // host TileMap* over `in` or null (see ColArgs)
-    int persist_ctas;
 };
 
 // ---- launch table: one entry per (line length, precision), see gen_lines.py ----------------------
@@ -118,6 +130,9 @@ struct LineTable {
     int (*row_plain)(const PlainRowArgs&, cudaStream_t);
     int (*col_pass)(int alg, const ColArgs&, cudaStream_t);
     int (*col_plain)(const PlainColArgs&, cudaStream_t);
+    // warp-specialised persistent column kernel (col_groups.cuh); group_ok == 0: not built for this length
+    int group_ok, group_row_bytes;
+    int (*col_group)(int mode, const ColGroupArgs&, const void* map_in, const void* map_out, int ctas, cudaStream_t);
 };
 const LineTable* find_line_table(int L, int prec);
 int supported_lengths(int* out, int cap);

@@ -198,7 +198,9 @@ template <int N> struct FftPlan {
 
 // Transform one line.  v[r] = x[j + r*M] on entry, X[j + r*M] on exit.  `line` points at the
 // line's element 0 in shared memory; element i lives at line[pad(i) * STRIDE], pad(i) = i + i/E.
-// Every thread of the CTA must call this together (it contains CTA barriers).
+// `sync` is the barrier over the threads that share the shared-memory lines being transformed
+// together (the whole CTA, or a named barrier over the warps of one line group); every thread of
+// that group must call line_fft together.
 //
 // Address algebra (M = MID*E, so every index below splits into a per-thread base and a
 // compile-time offset):
@@ -206,8 +208,15 @@ template <int N> struct FftPlan {
 //   loads           j + e*M                    -> pad = (j + j/E) + e*(M + MID)
 //   middle store    (j/E + q*MID)*E*MID + j%E + r*E
 //                                              -> pad = (j/E)*(E*MID+MID) + j%E + q*MID*(E*MID+MID) + r*(E+1)
-template <typename R, int N, int DIR, int STRIDE>
-SLM_DEV void line_fft(cpx<R>* v, cpx<R>* line, int j, const cpx<R>* SLM_RESTRICT tw) {
+// Barrier policies for line_fft.
+struct CtaSync { SLM_DEV void operator()() const { sync_cta(); } };
+template <int THREADS> struct GroupSync {          // THREADS == 0: whole CTA
+    int id;
+    SLM_DEV void operator()() const { if (THREADS == 0) sync_cta(); else sync_named(id, THREADS); }
+};
+
+template <typename R, int N, int DIR, int STRIDE, class Sync = CtaSync>
+SLM_DEV void line_fft(cpx<R>* v, cpx<R>* line, int j, const cpx<R>* SLM_RESTRICT tw, Sync sync = Sync()) {
     using P = FftPlan<N>;
     constexpr int E = P::E, M = P::M, MID = P::MID;
     constexpr int EP = E + 1, MP = M + MID, BLK = E * MID + MID;
@@ -218,7 +227,7 @@ SLM_DEV void line_fft(cpx<R>* v, cpx<R>* line, int j, const cpx<R>* SLM_RESTRICT
     dft_small<E, DIR>(v);
 #pragma unroll
     for (int r = 0; r < E; ++r) st1[r * STRIDE] = v[r];
-    sync_cta();
+    sync();
 
     if constexpr (MID > 1) {
         const int jh = j / E, jl = j % E;
@@ -229,7 +238,7 @@ SLM_DEV void line_fft(cpx<R>* v, cpx<R>* line, int j, const cpx<R>* SLM_RESTRICT
             constexpr int Q = E / MID;                           // butterflies per thread
 #pragma unroll
             for (int e = 0; e < E; ++e) v[e] = ldp[e * MP * STRIDE];
-            sync_cta();
+            sync();
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
                 cpx<R> a[MID];
@@ -250,7 +259,7 @@ SLM_DEV void line_fft(cpx<R>* v, cpx<R>* line, int j, const cpx<R>* SLM_RESTRICT
                     for (int r = 0; r < 3; ++r) a[q][r] = ldp[(q * MP + r * NBP) * STRIDE];
                 }
             }
-            sync_cta();
+            sync();
 #pragma unroll
             for (int q = 0; q < QMAX; ++q) {
                 if (j + q * M < NB) {
@@ -262,13 +271,13 @@ SLM_DEV void line_fft(cpx<R>* v, cpx<R>* line, int j, const cpx<R>* SLM_RESTRICT
                 }
             }
         }
-        sync_cta();
+        sync();
     }
 
     // last stage (Ns = M): twiddle W_N^(r*j), butterfly, result r is X[j + r*M]
 #pragma unroll
     for (int r = 0; r < E; ++r) v[r] = ldp[r * MP * STRIDE];
-    sync_cta();                      // the tile may be overwritten by the next transform
+    sync();                      // the tile may be overwritten by the next transform
     {
         cpx<R> w[E];
         twiddle_powers<E>(w, tw_load<DIR>(tw, j));

@@ -1,5 +1,5 @@
 // One translation unit per (line length, precision): compiled with -DSLM_LINE_L=<L> -DSLM_LINE_PREC=<0|1>.
-#include "passes.cuh"
+#include "line_ops.cuh"
 
 namespace slm {
 #if SLM_LINE_PREC == 0
@@ -17,6 +17,9 @@ static int row_plain_(const PlainRowArgs& a, cudaStream_t s) { return Ops::row_p
 static int col_pass_(int alg, const ColArgs& a, cudaStream_t s) { return Ops::col_pass(alg, a, s); }
 static int col_plain_(const PlainColArgs& a, cudaStream_t s) { return Ops::col_plain(a, s); }
 static void prepare_() { Ops::prepare(); }
+static int col_group_(int mode, const ColGroupArgs& ga, const void* in, const void* out, int ctas, cudaStream_t s) {
+    return Ops::col_group(mode, ga, in, out, ctas, s);
+}
 
 extern const LineTable SLM_TABLE_NAME(SLM_LINE_L, SLM_LINE_PREC);
 const LineTable SLM_TABLE_NAME(SLM_LINE_L, SLM_LINE_PREC) = {
@@ -24,5 +27,6 @@ const LineTable SLM_TABLE_NAME(SLM_LINE_L, SLM_LINE_PREC) = {
     Ops::RG::NR, Ops::RG::THREADS, Ops::RG::SMEM,
     Ops::CG::TC, Ops::CG::THREADS, Ops::CG::SMEM,
     &prepare_, &row_pass_, &row_plain_, &col_pass_, &col_plain_,
+    Ops::GG::OK ? 1 : 0, Ops::GG::ROWB, &col_group_,
 };
 }  // namespace slm

@@ -1,0 +1,86 @@
+// Host-side launchers of the pass kernels for one (line length, precision).
+#pragma once
+#include "col_groups.cuh"
+#include "passes.cuh"
+
+namespace slm {
+
+template <typename R, int L, bool OK = ColGroupGeom<R, L>::OK> struct GroupLaunch {
+    static void prepare() {}
+    static int launch(int, const ColGroupArgs&, const TileMap&, const TileMap&, int, cudaStream_t) { return -1; }
+};
+template <typename R, int L> struct GroupLaunch<R, L, true> {
+    using GG = ColGroupGeom<R, L>;
+    static void prepare() {
+        cudaFuncSetAttribute(col_group_kernel<R, L, CGM_GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GG::SMEM);
+        cudaFuncSetAttribute(col_group_kernel<R, L, CGM_GD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GG::SMEM);
+        cudaFuncSetAttribute(col_group_kernel<R, L, CGM_STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GG::SMEM);
+        cudaFuncSetAttribute(col_group_kernel<R, L, CGM_COMPLEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GG::SMEM);
+        cudaFuncSetAttribute(col_group_kernel<R, L, CGM_STATS_KEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GG::SMEM);
+        cudaFuncSetAttribute(col_group_kernel<R, L, CGM_GD_POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GG::SMEM);
+    }
+    static int launch(int mode, const ColGroupArgs& ga, const TileMap& in, const TileMap& out, int ctas, cudaStream_t s) {
+        const long long tiles = (long long)ga.c.B * (ga.c.W / GG::TC);
+        const dim3 grid((unsigned)(tiles < ctas ? tiles : ctas)), block(GG::THREADS);
+        if (mode == CGM_GS) SLM_LAUNCH((col_group_kernel<R, L, CGM_GS>), grid, block, GG::SMEM, s, ga, in, out);
+        else if (mode == CGM_GD) SLM_LAUNCH((col_group_kernel<R, L, CGM_GD>), grid, block, GG::SMEM, s, ga, in, out);
+        else if (mode == CGM_STATS) SLM_LAUNCH((col_group_kernel<R, L, CGM_STATS>), grid, block, GG::SMEM, s, ga, in, out);
+        else if (mode == CGM_STATS_KEEP) SLM_LAUNCH((col_group_kernel<R, L, CGM_STATS_KEEP>), grid, block, GG::SMEM, s, ga, in, out);
+        else if (mode == CGM_GD_POST) SLM_LAUNCH((col_group_kernel<R, L, CGM_GD_POST>), grid, block, GG::SMEM, s, ga, in, out);
+        else SLM_LAUNCH((col_group_kernel<R, L, CGM_COMPLEX>), grid, block, GG::SMEM, s, ga, in, out);
+        return 0;
+    }
+};
+
+template <typename R, int L> struct LineOps {
+    using RG = RowGeom<R, L>;
+    using CG = ColGeom<R, L>;
+    using GG = ColGroupGeom<R, L>;
+    static int check() { cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? 0 : -(int)e - 1000; }
+    static void prepare() {
+        cudaFuncSetAttribute(row_pass_kernel<R, L, ALG_GS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
+        cudaFuncSetAttribute(row_pass_kernel<R, L, ALG_GS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
+        cudaFuncSetAttribute(row_pass_kernel<R, L, ALG_GD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
+        cudaFuncSetAttribute(row_pass_kernel<R, L, ALG_GD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
+        cudaFuncSetAttribute(row_plain_kernel<R, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
+        cudaFuncSetAttribute(col_pass_kernel<R, L, ALG_GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG::SMEM);
+        cudaFuncSetAttribute(col_pass_kernel<R, L, ALG_GD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG::SMEM);
+        cudaFuncSetAttribute(col_plain_kernel<R, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG::SMEM);
+        GroupLaunch<R, L>::prepare();
+    }
+    static int row_pass(int alg, const RowArgs& a, cudaStream_t s) {
+        const dim3 grid((unsigned)((long long)a.B * a.H / RG::NR)), block(RG::THREADS);
+        if (alg == ALG_GS) {
+            if (a.final_pass) SLM_LAUNCH((row_pass_kernel<R, L, ALG_GS, 1>), grid, block, RG::SMEM, s, a);
+            else SLM_LAUNCH((row_pass_kernel<R, L, ALG_GS, 0>), grid, block, RG::SMEM, s, a);
+        } else {
+            if (a.final_pass) SLM_LAUNCH((row_pass_kernel<R, L, ALG_GD, 1>), grid, block, RG::SMEM, s, a);
+            else SLM_LAUNCH((row_pass_kernel<R, L, ALG_GD, 0>), grid, block, RG::SMEM, s, a);
+        }
+        return check();
+    }
+    static int row_plain(const PlainRowArgs& a, cudaStream_t s) {
+        const dim3 grid((unsigned)((long long)a.B * a.H / RG::NR)), block(RG::THREADS);
+        SLM_LAUNCH((row_plain_kernel<R, L>), grid, block, RG::SMEM, s, a);
+        return check();
+    }
+    static int col_pass(int alg, const ColArgs& a, cudaStream_t s) {
+        const dim3 grid((unsigned)((long long)a.B * (a.W / CG::TC))), block(CG::THREADS);
+        if (alg == ALG_GS) SLM_LAUNCH((col_pass_kernel<R, L, ALG_GS>), grid, block, CG::SMEM, s, a);
+        else SLM_LAUNCH((col_pass_kernel<R, L, ALG_GD>), grid, block, CG::SMEM, s, a);
+        return check();
+    }
+    static int col_plain(const PlainColArgs& a, cudaStream_t s) {
+        const dim3 grid((unsigned)((long long)a.B * (a.W / CG::TC))), block(CG::THREADS);
+        SLM_LAUNCH((col_plain_kernel<R, L>), grid, block, CG::SMEM, s, a);
+        return check();
+    }
+    // warp-specialised persistent column kernel; mode = ColGroupMode.  -1: not available for this line length
+    static int col_group(int mode, const ColGroupArgs& ga, const void* map_in, const void* map_out, int ctas, cudaStream_t s) {
+        if (!GG::OK) return -1;
+        const int r = GroupLaunch<R, L>::launch(mode, ga, *static_cast<const TileMap*>(map_in), *static_cast<const TileMap*>(map_out), ctas, s);
+        return r ? r : check();
+    }
+};
+
+}  // namespace slm

@@ -128,6 +128,11 @@ template <typename R, int L> struct RowGeom {
     static constexpr int THREADS = NR * M;
     static constexpr size_t SMEM = (size_t)NR * P::NP * sizeof(cpx<R>);
     static constexpr int MIN_CTAS = sizeof(R) == 4 ? (512 / THREADS > 0 ? 512 / THREADS : 1) : 1;   // fp32: <= 128 registers
+    // rows are transformed independently: the threads of LPG rows (whole warps) share a named barrier
+    static constexpr int LPG = M % 32 == 0 ? 1 : (M % 16 == 0 ? 2 : (M % 8 == 0 ? 4 : 8));
+    static constexpr int GROUPS = NR / LPG;
+    static constexpr int GROUP_THREADS = (NR % LPG == 0 && GROUPS > 1 && GROUPS <= 15) ? LPG * M : 0;   // 0: CTA barrier
+    using Sync = GroupSync<GROUP_THREADS>;
 };
 template <typename R, int L> struct ColGeom {
     using P = FftPlan<L>;
@@ -163,6 +168,7 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), (RowGeom<R, W>::MIN_
     const int done = ld_cg(&st->done);
     if (!FINAL && done) return;                       // uniform: a CTA never straddles planes
     cpx<R>* line = reinterpret_cast<cpx<R>*>(raw) + (size_t)rr * P::NP;
+    const typename G::Sync sync{1 + rr / G::LPG};
     const cpx<R>* tw = static_cast<const cpx<R>*>(a.tw);
     const size_t base = ((size_t)b * a.H + y) * W + j;
     const size_t ibase = (size_t)y * W + j;
@@ -174,7 +180,7 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), (RowGeom<R, W>::MIN_
             const cpx<R>* Y = static_cast<const cpx<R>*>(a.Y) + base;
 #pragma unroll
             for (int r = 0; r < E; ++r) v[r] = ld_plane(Y + r * M);
-            line_fft<R, W, +1, 1>(v, line, j, tw);           // A = ifft2(D) up to a positive scale
+            line_fft<R, W, +1, 1>(v, line, j, tw, sync);           // A = ifft2(D) up to a positive scale
 #pragma unroll
             for (int r = 0; r < E; ++r) if (!FINAL) v[r] = unit_phasor(v[r]);
         } else if (a.source == ROW_FROM_A32) {
@@ -213,7 +219,7 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), (RowGeom<R, W>::MIN_
             const cpx<R>* Y = static_cast<const cpx<R>*>(a.Y) + base;
 #pragma unroll
             for (int r = 0; r < E; ++r) v[r] = ld_plane(Y + r * M);
-            line_fft<R, W, +1, 1>(v, line, j, tw);
+            line_fft<R, W, +1, 1>(v, line, j, tw, sync);
             // the update of the iteration whose Fourier-plane pass produced Y: lr of THAT iteration
             const R lr = (R)ld_ro(a.lr + (ld_cg(&st->iters) - 1));
             const R nrm = (R)a.inv_hw;
@@ -238,24 +244,13 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), (RowGeom<R, W>::MIN_
             v[r] = cscale(xx[r], inv);
         }
     }
-    line_fft<R, W, -1, 1>(v, line, j, tw);
+    line_fft<R, W, -1, 1>(v, line, j, tw, sync);
     cpx<R>* X = static_cast<cpx<R>*>(a.X) + base;
 #pragma unroll
     for (int r = 0; r < E; ++r) st_plane(X + r * M, v[r]);
 }
 
 // ---- Fourier-plane pass ---------------------------------------------------------------------------
-// Two launch shapes share one tile body:
-//   PERSIST = 0 : one CTA per column tile, points loaded straight from global memory;
-//   PERSIST = 1 : gridDim.x resident CTAs walk the tiles round-robin; the NEXT tile is fetched by
-//                 TMA (cp.async.bulk.tensor, tma.cuh) into a second dense shared-memory buffer while
-//                 the current one is transformed, so global-load latency is off the critical path.
-template <typename R, int H> struct ColSmem {
-    using G = ColGeom<R, H>;
-    static constexpr size_t DENSE = (size_t)H * G::TC * sizeof(cpx<R>);     // one TMA tile buffer
-    static constexpr size_t PERSIST_BYTES = 2 * DENSE + G::SMEM + 64;       // 2 tile buffers, exchange, barriers
-};
-
 // One column tile of the loop's Fourier-plane step.  v = the tile's points (thread (j,c) holds rows
 // j + r*M of column c); lut_s = the 256-entry amplitude (GS) / weight (GD) table in shared memory.
 // Ordering is chosen so no warp waits on a dependent global access: the grey levels are requested
@@ -357,8 +352,10 @@ SLM_DEV void col_plain_tile(const PlainColArgs& a, int b, int tile, int tiles, c
     const size_t W = a.W;
     const size_t off = (size_t)b * H * W + (size_t)j * W + tile * TC + c;
     const cpx<R>* tw = static_cast<const cpx<R>*>(a.tw);
-    if (a.inverse) line_fft<R, H, +1, TC>(v, line, j, tw);
-    else line_fft<R, H, -1, TC>(v, line, j, tw);
+    if (!a.skip_fft) {
+        if (a.inverse) line_fft<R, H, +1, TC>(v, line, j, tw);
+        else line_fft<R, H, -1, TC>(v, line, j, tw);
+    }
 
     if (a.output == OUT_COMPLEX) {
         cpx<R>* out = static_cast<cpx<R>*>(a.out) + off;
@@ -394,73 +391,34 @@ SLM_DEV void col_plain_tile(const PlainColArgs& a, int b, int tile, int tiles, c
     }
 }
 
-// Shared driver of both column kernels.  BODY(b, tile, v) processes one tile; SKIP(b) says whether plane b rests.
-template <typename R, int H, int PERSIST, class Skip, class Body>
-SLM_DEV void col_tiles(const void* in, int B, int W, const TileMap& tm, unsigned char* raw, Skip skip, Body body) {
+// One CTA per column tile: points straight from global memory (64-byte row segments), CTA-wide barriers.
+// Used where the warp-specialised kernel (col_groups.cuh) does not apply: intensity outputs, the
+// complex64 setup inside an fp64 context, line lengths whose tile rows are not 32 or 64 bytes.
+template <typename R, int H, class Skip, class Body>
+SLM_DEV void col_tiles(const void* in, int W, unsigned char* raw, Skip skip, Body body) {
     using G = ColGeom<R, H>;
     using P = FftPlan<H>;
     constexpr int E = P::E, M = P::M, TC = G::TC;
     const int tiles = W / TC;
     const int t = threadIdx.x, c = t % TC, j = t / TC;
     cpx<R> v[E];
-    if (!PERSIST) {
-        const int b = blockIdx.x / tiles, tile = blockIdx.x % tiles;
-        if (skip(b)) return;
-        const cpx<R>* X = static_cast<const cpx<R>*>(in) + (size_t)b * H * W + (size_t)j * W + tile * TC + c;
+    const int b = blockIdx.x / tiles, tile = blockIdx.x % tiles;
+    if (skip(b)) return;
+    const cpx<R>* X = static_cast<const cpx<R>*>(in) + (size_t)b * H * W + (size_t)j * W + tile * TC + c;
 #pragma unroll
-        for (int r = 0; r < E; ++r) v[r] = ld_plane(X + (size_t)r * M * W);
-        body(b, tile, tiles, v, reinterpret_cast<cpx<R>*>(raw) + c, t, c, j);
-        return;
-    }
-    // persistent: [dense buffer 0][dense buffer 1][exchange][2 barriers]; the dynamic shared memory
-    // window is declared 128-byte aligned (TMA destination requirement)
-    unsigned char* base = raw;
-    constexpr size_t DENSE = ColSmem<R, H>::DENSE;
-    cpx<R>* const dense0 = reinterpret_cast<cpx<R>*>(base);
-    cpx<R>* const dense1 = reinterpret_cast<cpx<R>*>(base + DENSE);
-    cpx<R>* const line = reinterpret_cast<cpx<R>*>(base + 2 * DENSE) + c;
-    TileBarrier* const bar = reinterpret_cast<TileBarrier*>(base + 2 * DENSE + G::SMEM);
-    const long long total = (long long)B * tiles;
-    if (t == 0) { tile_barrier_init(bar); tile_barrier_init(bar + 1); tile_barrier_fence(); }
-    sync_cta();
-    unsigned uses0 = 0, uses1 = 0;      // completed uses of each buffer's barrier (uniform across the CTA)
-    int cur = 0;
-    long long g = blockIdx.x;
-    auto fetch = [&](long long gt, int buf) {       // thread 0 only
-        const int fb = (int)(gt / tiles), ft = (int)(gt % tiles);
-        tile_prefetch(tm, buf ? dense1 : dense0, bar + buf, (long long)fb * H, H, ft * TC, TC, (int)sizeof(cpx<R>));
-    };
-    // The next tile is always requested (a finished plane's tile is fetched and dropped: rare, and it
-    // keeps one wait per fetch); whether a plane rests is looked up while its tile is in flight.
-    if (g < total && t == 0) fetch(g, 0);
-    while (g < total) {
-        const long long gn = g + gridDim.x;
-        if (gn < total && t == 0) fetch(gn, cur ^ 1);   // buffer cur^1 was drained before the barriers of the previous tile
-        const int b = (int)(g / tiles), tile = (int)(g % tiles);
-        const bool rest = skip(b);
-        tile_wait(bar + cur, cur ? uses1 : uses0);
-        if (cur) uses1++; else uses0++;
-        if (!rest) {
-            const cpx<R>* src = (cur ? dense1 : dense0) + (size_t)j * TC + c;
-#pragma unroll
-            for (int r = 0; r < E; ++r) v[r] = src[(size_t)r * M * TC];
-            body(b, tile, tiles, v, line, t, c, j);
-        }
-        sync_cta();                      // everyone is out of this tile (static smem of the reductions, buffer cur)
-        g = gn;
-        cur ^= 1;
-    }
+    for (int r = 0; r < E; ++r) v[r] = ld_plane(X + (size_t)r * M * W);
+    body(b, tile, tiles, v, reinterpret_cast<cpx<R>*>(raw) + c, t, c, j);
 }
 
-template <typename R, int H, int ALG, int PERSIST>
-SLM_GLOBAL void SLM_LAUNCH_BOUNDS((ColGeom<R, H>::THREADS), 1) col_pass_kernel(ColArgs a, const SLM_GRID_CONSTANT TileMap tm) {
+template <typename R, int H, int ALG>
+SLM_GLOBAL void SLM_LAUNCH_BOUNDS((ColGeom<R, H>::THREADS), 1) col_pass_kernel(ColArgs a) {
     SLM_DYN_SMEM(raw);
     SLM_STATIC_SMEM R lut_s[256];
     if (a.T8) {                                                 // visible after the first barrier of the transform
         const R* lut = static_cast<const R*>(a.lut);
         for (int i = threadIdx.x; i < 256; i += ColGeom<R, H>::THREADS) lut_s[i] = ld_ro(lut + i);
     }
-    col_tiles<R, H, PERSIST>(a.X, a.B, a.W, tm, raw,
+    col_tiles<R, H>(a.X, a.W, raw,
         [&](int b) { return ld_cg(&a.stats[b].done) != 0; },
         [&](int b, int tile, int tiles, cpx<R>* v, cpx<R>* line, int t, int c, int j) {
             col_pass_tile<R, H, ALG>(a, b, tile, tiles, v, line, lut_s, t, c, j);
@@ -477,6 +435,7 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), 1) row_plain_kernel(
     const int t = threadIdx.x, rr = t / M, j = t % M;
     const long long grow = (long long)blockIdx.x * G::NR + rr;
     cpx<R>* line = reinterpret_cast<cpx<R>*>(raw) + (size_t)rr * P::NP;
+    const typename G::Sync sync{1 + rr / G::LPG};
     const cpx<R>* tw = static_cast<const cpx<R>*>(a.tw);
     const size_t base = (size_t)grow * W + j;
     cpx<R> v[E];
@@ -497,90 +456,22 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), 1) row_plain_kernel(
 #pragma unroll
         for (int r = 0; r < E; ++r) { const double h = ld_ro(in + r * M); v[r].x = (R)cos(h); v[r].y = (R)sin(h); }
     }
-    if (a.inverse) line_fft<R, W, +1, 1>(v, line, j, tw);
-    else line_fft<R, W, -1, 1>(v, line, j, tw);
+    if (a.inverse) line_fft<R, W, +1, 1>(v, line, j, tw, sync);
+    else line_fft<R, W, -1, 1>(v, line, j, tw, sync);
     cpx<R>* out = static_cast<cpx<R>*>(a.out) + base;
 #pragma unroll
     for (int r = 0; r < E; ++r) st_plane(out + r * M, v[r]);
 }
 
 // ---- plain column transform kernel -------------------------------------------------------------------
-template <typename R, int H, int PERSIST>
-SLM_GLOBAL void SLM_LAUNCH_BOUNDS((ColGeom<R, H>::THREADS), 1) col_plain_kernel(PlainColArgs a, const SLM_GRID_CONSTANT TileMap tm) {
+template <typename R, int H>
+SLM_GLOBAL void SLM_LAUNCH_BOUNDS((ColGeom<R, H>::THREADS), 1) col_plain_kernel(PlainColArgs a) {
     SLM_DYN_SMEM(raw);
-    col_tiles<R, H, PERSIST>(a.in, a.B, a.W, tm, raw,
+    col_tiles<R, H>(a.in, a.W, raw,
         [&](int b) { return a.output == OUT_STATS && ld_cg(&a.stats[b].done) != 0; },   // in-loop use (GD): finished planes rest
         [&](int b, int tile, int tiles, cpx<R>* v, cpx<R>* line, int t, int c, int j) {
             col_plain_tile<R, H>(a, b, tile, tiles, v, line, t, c, j);
         });
 }
-
-// ---- host-side launchers ----------------------------------------------------------------------------
-template <typename R, int L> struct LineOps {
-    using RG = RowGeom<R, L>;
-    using CG = ColGeom<R, L>;
-    static constexpr size_t PSMEM = ColSmem<R, L>::PERSIST_BYTES;
-    static int check() { cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? 0 : -(int)e - 1000; }
-    static void prepare() {
-        cudaFuncSetAttribute(row_pass_kernel<R, L, ALG_GS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
-        cudaFuncSetAttribute(row_pass_kernel<R, L, ALG_GS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
-        cudaFuncSetAttribute(row_pass_kernel<R, L, ALG_GD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
-        cudaFuncSetAttribute(row_pass_kernel<R, L, ALG_GD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
-        cudaFuncSetAttribute(row_plain_kernel<R, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
-        cudaFuncSetAttribute(col_pass_kernel<R, L, ALG_GS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG::SMEM);
-        cudaFuncSetAttribute(col_pass_kernel<R, L, ALG_GD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG::SMEM);
-        cudaFuncSetAttribute(col_plain_kernel<R, L, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG::SMEM);
-        cudaFuncSetAttribute(col_pass_kernel<R, L, ALG_GS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PSMEM);
-        cudaFuncSetAttribute(col_pass_kernel<R, L, ALG_GD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PSMEM);
-        cudaFuncSetAttribute(col_plain_kernel<R, L, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PSMEM);
-    }
-    static int row_pass(int alg, const RowArgs& a, cudaStream_t s) {
-        const dim3 grid((unsigned)((long long)a.B * a.H / RG::NR)), block(RG::THREADS);
-        if (alg == ALG_GS) {
-            if (a.final_pass) SLM_LAUNCH((row_pass_kernel<R, L, ALG_GS, 1>), grid, block, RG::SMEM, s, a);
-            else SLM_LAUNCH((row_pass_kernel<R, L, ALG_GS, 0>), grid, block, RG::SMEM, s, a);
-        } else {
-            if (a.final_pass) SLM_LAUNCH((row_pass_kernel<R, L, ALG_GD, 1>), grid, block, RG::SMEM, s, a);
-            else SLM_LAUNCH((row_pass_kernel<R, L, ALG_GD, 0>), grid, block, RG::SMEM, s, a);
-        }
-        return check();
-    }
-    static int row_plain(const PlainRowArgs& a, cudaStream_t s) {
-        const dim3 grid((unsigned)((long long)a.B * a.H / RG::NR)), block(RG::THREADS);
-        SLM_LAUNCH((row_plain_kernel<R, L>), grid, block, RG::SMEM, s, a);
-        return check();
-    }
-    // a.tile_map != null selects the persistent TMA kernel on min(tiles, a.persist_ctas) resident CTAs
-    static int col_pass(int alg, const ColArgs& a, cudaStream_t s) {
-        const long long tiles = (long long)a.B * (a.W / CG::TC);
-        const dim3 block(CG::THREADS);
-        if (a.tile_map) {
-            const TileMap& tm = *static_cast<const TileMap*>(a.tile_map);
-            const dim3 grid((unsigned)(tiles < a.persist_ctas ? tiles : a.persist_ctas));
-            if (alg == ALG_GS) SLM_LAUNCH((col_pass_kernel<R, L, ALG_GS, 1>), grid, block, PSMEM, s, a, tm);
-            else SLM_LAUNCH((col_pass_kernel<R, L, ALG_GD, 1>), grid, block, PSMEM, s, a, tm);
-        } else {
-            const TileMap tm{};
-            const dim3 grid((unsigned)tiles);
-            if (alg == ALG_GS) SLM_LAUNCH((col_pass_kernel<R, L, ALG_GS, 0>), grid, block, CG::SMEM, s, a, tm);
-            else SLM_LAUNCH((col_pass_kernel<R, L, ALG_GD, 0>), grid, block, CG::SMEM, s, a, tm);
-        }
-        return check();
-    }
-    static int col_plain(const PlainColArgs& a, cudaStream_t s) {
-        const long long tiles = (long long)a.B * (a.W / CG::TC);
-        const dim3 block(CG::THREADS);
-        if (a.tile_map) {
-            const TileMap& tm = *static_cast<const TileMap*>(a.tile_map);
-            const dim3 grid((unsigned)(tiles < a.persist_ctas ? tiles : a.persist_ctas));
-            SLM_LAUNCH((col_plain_kernel<R, L, 1>), grid, block, PSMEM, s, a, tm);
-        } else {
-            const TileMap tm{};
-            const dim3 grid((unsigned)tiles);
-            SLM_LAUNCH((col_plain_kernel<R, L, 0>), grid, block, CG::SMEM, s, a, tm);
-        }
-        return check();
-    }
-};
 
 }  // namespace slm

@@ -65,6 +65,7 @@ struct State {
     Fibre* cur = nullptr;
     unsigned n = 0, alive = 0;
     unsigned bar_count = 0, bar_gen = 0;
+    unsigned named_count[16] = {0}, named_gen[16] = {0};
     dim3 block_idx, block_dim, grid_dim;
     unsigned char* smem = nullptr;
     void (*body)(void*) = nullptr;
@@ -92,6 +93,14 @@ inline void sync_cta() {
     s.progress++;
     if (++s.bar_count == s.alive) { s.bar_count = 0; s.bar_gen++; return; }
     while (s.bar_gen == gen) yield();
+}
+inline void sync_named(int id, int nthreads) {
+    State& s = S();
+    if (id < 1 || id > 15 || nthreads % 32) { fprintf(stderr, "emu: bad named barrier %d/%d\n", id, nthreads); abort(); }
+    unsigned gen = s.named_gen[id];
+    s.progress++;
+    if (++s.named_count[id] == (unsigned)nthreads) { s.named_count[id] = 0; s.named_gen[id]++; return; }
+    while (s.named_gen[id] == gen) yield();
 }
 inline unsigned warp_lanes(unsigned w) { State& s = S(); unsigned r = s.n - w * 32; return r < 32 ? r : 32; }
 inline void sync_warp() {
@@ -142,6 +151,7 @@ template <class F> void run_cta(dim3 bidx, dim3 grid, dim3 block, size_t smem_by
     s.warps.assign((n + 31) / 32, WarpSlot{});
     s.n = s.alive = n;
     s.bar_count = 0;
+    for (int i = 0; i < 16; ++i) s.named_count[i] = 0;
     s.block_idx = bidx; s.block_dim = block; s.grid_dim = grid;
     std::vector<unsigned char> smem(smem_bytes + 256, 0xFF);
     s.smem = (unsigned char*)(((uintptr_t)smem.data() + 127) & ~(uintptr_t)127);
@@ -203,11 +213,14 @@ template <typename T> inline T ld_ro(const T* p) { return *p; }
 template <typename T> inline T ld_cg(const T* p) { return *p; }
 template <typename T> inline void st_cg(T* p, T v) { *p = v; }
 inline void fence_device() {}
+inline void fence_block() {}
+inline unsigned atomic_add_shared(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 inline unsigned atomic_inc_wrap(unsigned* p, unsigned limit) { unsigned o = *p; *p = (o >= limit) ? 0 : o + 1; return o; }
 inline float shfl_xor(float v, int m) { return emu::shfl_xor(v, m); }
 inline double shfl_xor(double v, int m) { return emu::shfl_xor(v, m); }
 inline unsigned shfl_idx(unsigned v, int src) { return emu::shfl_idx(v, src); }
 inline void sync_cta() { emu::sync_cta(); }
+inline void sync_named(int id, int nthreads) { emu::sync_named(id, nthreads); }
 // compiled with -ffp-contract=off, so plain operators are single IEEE operations
 inline double mul_rn(double a, double b) { return a * b; }
 inline double add_rn(double a, double b) { return a + b; }
@@ -219,4 +232,5 @@ inline double rsqrt_fast(double a) { return 1.0 / std::sqrt(a); }
 }  // namespace slm
 
 struct float2 { float x, y; };
+struct uint2 { unsigned x, y; };
 struct alignas(16) double2 { double x, y; };
