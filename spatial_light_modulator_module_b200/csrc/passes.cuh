@@ -127,7 +127,10 @@ template <typename R, int L> struct RowGeom {
     static constexpr int NR = floor_pow2(256 / M);           // rows per CTA (power of two)
     static constexpr int THREADS = NR * M;
     static constexpr size_t SMEM = (size_t)NR * P::NP * sizeof(cpx<R>);
-    static constexpr int MIN_CTAS = sizeof(R) == 4 ? (512 / THREADS > 0 ? 512 / THREADS : 1) : 1;   // fp32: <= 128 registers
+#ifndef SLM_ROW_THREADS_PER_SM
+#define SLM_ROW_THREADS_PER_SM 768
+#endif
+    static constexpr int MIN_CTAS = sizeof(R) == 4 ? (SLM_ROW_THREADS_PER_SM / THREADS > 0 ? SLM_ROW_THREADS_PER_SM / THREADS : 1) : 1;   // fp32 register budget
     // rows are transformed independently: the threads of LPG rows (whole warps) share a named barrier
     static constexpr int LPG = M % 32 == 0 ? 1 : (M % 16 == 0 ? 2 : (M % 8 == 0 ? 4 : 8));
     static constexpr int GROUPS = NR / LPG;
