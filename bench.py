@@ -51,6 +51,7 @@ def parse():
     p.add_argument("--e2e-steps", type=int, default=5)
     p.add_argument("--cpu-loops", type=int, default=40, help="iterations of the CPU baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-movie", action="store_true")
     return p.parse_args()
 
 
@@ -81,6 +82,16 @@ def kernel_bytes_per_px(kind, alg, precision):
     if kind == "col_stats":
         return c                               # read X
     raise KeyError(kind)
+
+
+def measured_traffic(kind, alg, precision, shape, batch):
+    """DRAM bytes (read + write) per launch of the dominant kernel from the committed ncu capture
+    (profiles/traffic.json), if one exists for exactly this configuration."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    key = f"{kind}|{alg}|{precision}|{shape[0]}x{shape[1]}|batch{batch}"
+    return json.load(open(path)).get(key)
 
 
 def measured_peak():
@@ -267,9 +278,12 @@ def run_b200(a):
     for kind in kernels:
         kernels[kind]["share"] = prof[kind][0] / tsum
     dom = max(kernels, key=lambda k: prof[k][0])
-    roof = {"bound": "hbm", "kernel": {"col_pass": "col_pass_kernel", "row_pass": "row_pass_kernel", "col_stats": "col_plain_kernel"}[dom],
+    names = {"col_pass": f"col_group_kernel<{'GS' if a.alg == 'gs' else 'GD_POST'}> (Fourier-plane pass)",
+             "row_pass": "row_pass_kernel (SLM-plane pass)", "col_stats": "col_group_kernel<STATS> (max pre-pass)"}
+    roof = {"bound": "hbm", "kernel": names[dom],
             "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-            "frac": kernels[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+            "frac": kernels[dom]["achieved_gbs"] / peak, "traffic": measured_traffic(dom, a.alg, a.precision, shape, a.batch),
+            "peak_source": peak_src,
             "alg_bytes_per_launch": kernels[dom]["alg_bytes"], "avg_launch_ms": kernels[dom]["avg_ms"],
             "share_of_step": kernels[dom]["share"]}
     iter_bytes = bytes_per_px(a.alg, a.precision) * npx
@@ -302,6 +316,26 @@ def run_b200(a):
               "frac_of_hbm_roofline": iter_bytes * a.loops / (lat_ms * 1e-3) / 1e9 / peak,
               "note": "batch 1: working set fits in L2, launch/latency bound"}
     eng1.close()
+
+    # ---- config 3 sample: optical-trap movie frames, GS 50 iterations at the SLM shape -----------------------
+    movie = None
+    if not a.no_movie:
+        mshape, mframes, mloops = (768, 1024), 64, 50
+        engm = Engine(mshape, a.precision, mframes)
+        frames_dev = torch.from_numpy(synthetic.movie_frames(mframes)).to(dev)
+        mnorms = np.full(mframes, 255.0)
+        for _ in range(2):
+            engm.gs(frames_dev, mloops, want_expected=False, norms=mnorms)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            engm.gs(frames_dev, mloops, want_expected=False, norms=mnorms)
+        e1.record()
+        torch.cuda.synchronize()
+        mt = e0.elapsed_time(e1) / 3 * 1e-3
+        movie = {"workload": f"{mframes} trap frames {mshape[0]}x{mshape[1]}, GS {mloops} iterations, device resident",
+                 "holograms_per_s": mframes / mt, "iterations_per_s": mframes * mloops / mt}
+        engm.close()
 
     # ---- end to end through the drop-in API with host buffers ----------------------------------------
     ns = argparse.Namespace(incomming_intensity="uniform", tolerance=0, max_loops=a.loops, gif=False, print_info=False,
@@ -347,7 +381,7 @@ def run_b200(a):
                    "seeds": "targets default_rng(1000*rank+i), mask default_rng(1)"},
         "holograms_per_s": a.batch * a.steps * world / (ms * 1e-3),
         "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof,
-        "iteration_roofline": iteration_roofline, "kernels": kernels, "single_hologram": single, "cpu_baseline": cpu,
+        "iteration_roofline": iteration_roofline, "kernels": kernels, "single_hologram": single, "movie_config3_sample": movie, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
     if world > 1:

@@ -90,6 +90,11 @@ int slm_gd_run(slm_ctx* ctx, int batch, const uint8_t* target_u8, const void* ta
 int slm_fourier_guess(slm_ctx* ctx, int batch, const uint8_t* target_u8, const void* amp_real, const double* amp_lut,
                       const void* inc_amp, int setup_c64, void* x_out);
 
+/* make_initial_guess("random" | "zeros", ...) -- algorithms.py:118-124,145-151: exp(1j*2*pi*u) / divide_by
+ * from the MT19937 stream `u` (device double[n], drawn on the host exactly as random.random() does);
+ * x_out: device complex<R>[n]. */
+int slm_random_phasor(slm_ctx* ctx, const double* u, void* x_out, long long n, double divide_by);
+
 /* error_evolution and its length per plane (algorithms.py:25,39,93) of the last run.
  * err: host double[batch][max_loops]; iters: host int[batch].  Synchronises the stream. */
 int slm_read_curves(slm_ctx* ctx, int batch, int max_loops, double* err, int* iters);

@@ -33,6 +33,7 @@ SIGNATURES = {
     "slm_gs_run": (_i, [_vp, _i, _vp, _vp, _vp, _dp, _dp, _vp, _vp, _i, _i, _d, _vp, _vp]),
     "slm_gd_run": (_i, [_vp, _i, _vp, _vp, _vp, _dp, _dp, _vp, _vp, _dp, _i, _d, _vp, _vp]),
     "slm_fourier_guess": (_i, [_vp, _i, _vp, _vp, _dp, _vp, _i, _vp]),
+    "slm_random_phasor": (_i, [_vp, _vp, _vp, _ll, _d]),
     "slm_read_curves": (_i, [_vp, _i, _i, _dp, _ip]),
     "slm_expected_outcome": (_i, [_vp, _i, _vp, _dp, _vp]),
     "slm_deflect_phase": (_i, [_vp, _i, _i, _d, _d, _d, _vp]),

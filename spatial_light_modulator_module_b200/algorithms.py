@@ -103,6 +103,10 @@ def make_initial_guess(initial_guess_type, incomming_amplitude, demanded_output,
     MT19937 stream as the reference's per-pixel ``random.random()`` calls; "fourier" runs on the
     device."""
     target = np.asarray(demanded_output)
+    if _device:                       # called from gradient_descent: exp(2*pi*i*u) is evaluated on the device
+        stream = hl.uniform_stream_guess(initial_guess_type, target.shape, seed)
+        if stream is not None:
+            return _engine_hint.random_phasor_guess(stream[0], stream[1])
     guess = hl.host_initial_guess(initial_guess_type, target.shape, seed)
     if guess is not None:
         return guess

@@ -106,6 +106,19 @@ SLM_GLOBAL void phasor_field_kernel(const cpx<RA>* A, const R* inc, cpx<R>* x, l
     }
 }
 
+// initial guesses "random" / "zeros" (algorithms.py:118-124,145-151): exp(1j*2*pi*u) [/100] from the
+// host-drawn MT19937 stream u.  The argument 2*pi*u is rounded to double first, as numpy does.
+template <typename R>
+SLM_GLOBAL void random_phasor_kernel(const double* u, cpx<R>* x, long long n, double divide_by) {
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        const double arg = mul_rn(mul_rn(2.0, 3.141592653589793), u[p]);
+        double re = cos(arg), im = sin(arg);
+        if (divide_by != 1.0) { re = div_rn(re, divide_by); im = div_rn(im, divide_by); }
+        cpx<R> o; o.x = (R)re; o.y = (R)im;
+        x[p] = o;
+    }
+}
+
 // complex<R> <-> complex128 / real conversions at the boundary (numpy hands over complex128)
 template <typename TS, typename TD>
 SLM_GLOBAL void convert_kernel(const TS* in, TD* out, long long n) {

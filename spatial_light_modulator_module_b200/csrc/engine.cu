@@ -475,6 +475,20 @@ extern "C" int slm_fourier_guess(slm_ctx* c, int batch, const uint8_t* T8, const
     return 0;
 }
 
+extern "C" int slm_random_phasor(slm_ctx* c, const double* u, void* x_out, long long n, double divide_by) {
+    if (!c) return fail(SLM_ERR_ARG, "slm_random_phasor: null context");
+    SLM_CUDA(cudaSetDevice(c->device));
+    if (!u || !x_out || n < 1 || divide_by == 0.0) return fail(SLM_ERR_ARG, "slm_random_phasor: bad argument");
+    const dim3 grid(ew_blocks(n)), block(kEwThreads);
+    {
+        LaunchTimer t_(c, K_ELEMENTWISE);
+        if (c->prec == PREC_F32) SLM_LAUNCH((random_phasor_kernel<float>), grid, block, 0, c->stream, u, static_cast<cpx<float>*>(x_out), n, divide_by);
+        else SLM_LAUNCH((random_phasor_kernel<double>), grid, block, 0, c->stream, u, static_cast<cpx<double>*>(x_out), n, divide_by);
+    }
+    SLM_CUDA(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int slm_read_curves(slm_ctx* c, int batch, int max_loops, double* err, int* iters) {
     SLM_TRY(check_batch(c, batch, "slm_read_curves"));
     if (max_loops < 1 || max_loops > c->loops_cap) return fail(SLM_ERR_ARG, "slm_read_curves: max_loops does not match the last run");

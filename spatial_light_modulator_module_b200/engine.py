@@ -88,6 +88,12 @@ class Engine:
         torch = self._torch
         host = torch.from_numpy(np.ascontiguousarray(array))
         with torch.cuda.stream(self._stream):
+            if host.numel() * host.element_size() >= (1 << 20):       # large planes: stage through pinned memory
+                pinned = torch.empty(host.shape, dtype=host.dtype, pin_memory=True)
+                pinned.copy_(host)
+                dev = pinned.to(self._dev, non_blocking=True)
+                self._stream.synchronize()                             # the pinned staging buffer is released below
+                return dev
             return host.to(self._dev, non_blocking=False)
 
     def _mem_is_device(self, obj) -> bool:
@@ -97,8 +103,12 @@ class Engine:
         return C.c_void_p(buf.data_ptr()) if buf is not None else C.c_void_p(0)
 
     def _mem_download(self, buf) -> np.ndarray:
+        torch = self._torch
+        with torch.cuda.stream(self._stream):
+            host = torch.empty(buf.shape, dtype=buf.dtype, pin_memory=True)
+            host.copy_(buf, non_blocking=True)
         self._stream.synchronize()
-        return buf.cpu().numpy()
+        return host.numpy()
 
     def _mem_np_dtype(self, buf):
         return np.dtype(str(buf.dtype).replace("torch.", ""))
@@ -209,6 +219,17 @@ class Engine:
             self._dp(norms), self._mem_ptr(inc_dev), self._mem_ptr(x), self._dp(lr), int(max_loops), float(tolerance),
             self._mem_ptr(holo), self._mem_ptr(exp)))
         return self._collect(batch, max_loops, holo, exp), x
+
+    def random_phasor_guess(self, u, divide_by=1.0):
+        """exp(1j*2*pi*u)/divide_by on the device from a host-drawn uniform stream ``u`` [B,H,W] or [H,W]
+        (make_initial_guess "random" / "zeros", algorithms.py:118-124,145-151)."""
+        ud = self._as_device(u, np.float64, "u")
+        if len(ud.shape) == 2:
+            ud = ud[None]
+        self._shape_check(tuple(ud.shape[1:]))
+        x = self._mem_empty(ud.shape, self.complex_dtype)
+        self._check(self._lib.slm_random_phasor(self._ctx, self._mem_ptr(ud), self._mem_ptr(x), _numel(ud), float(divide_by)))
+        return x
 
     def fourier_guess(self, targets, inc_amp=None):
         """make_initial_guess("fourier") (algorithms.py:154-157) on the device -> complex [B,H,W]."""

@@ -86,6 +86,17 @@ def python_random_stream(seed, count: int) -> np.ndarray:
     return out
 
 
+def uniform_stream_guess(kind: str, shape, seed):
+    """For the families that are exp(1j*2*pi*u)[/100] ("random", "zeros"): the uniform plane u and
+    the divisor, so the exponential can be evaluated on the device.  None for other kinds."""
+    h, w = shape
+    if kind == "random":
+        return python_random_stream(seed, h * w).reshape(h, w), 1.0
+    if kind == "zeros":
+        return python_random_stream(seed, h * w).reshape(h, w), 100.0
+    return None
+
+
 def host_initial_guess(kind: str, shape, seed):
     """The random families of make_initial_guess (algorithms.py:115-153) as complex128 planes.
     Returns None for "fourier" (computed on the device) and raises ValueError for unknown kinds."""

@@ -269,3 +269,21 @@ def check_expected_outcome(make_engine, golden, precision):
     tol = 1e-12 if precision == "fp64" else 1e-5
     assert np.abs(out - g["preview"]).max() <= tol * 255
     eng.close()
+
+
+def check_random_phasor_guess(make_engine, golden, precision):
+    """make_initial_guess "random"/"zeros": exp(1j*2*pi*u)[/100] evaluated on the device from the
+    host-drawn MT19937 stream equals the reference's planes (golden) to rounding."""
+    g = golden("initial_guess_24x40")
+    shape = (64, 64)
+    eng = make_engine(shape, precision, 1)
+    tol = 4e-16 if precision == "fp64" else 2e-7
+    for kind in ("random", "zeros"):
+        u, div = hl.uniform_stream_guess(kind, shape, 42)
+        x = eng.to_host(eng.random_phasor_guess(u, div))[0]
+        ref = hl.host_initial_guess(kind, shape, 42)
+        assert np.abs(x - ref).max() <= tol * np.abs(ref).max()
+    # the stream itself is the reference's: first 24*40 draws reproduce the golden plane
+    u, _ = hl.uniform_stream_guess("random", (24, 40), 42)
+    np.testing.assert_array_equal(np.exp(1j * 2 * np.pi * u), g["random"])
+    eng.close()

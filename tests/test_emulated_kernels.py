@@ -68,3 +68,8 @@ def test_analytic_and_quantisers_bit_exact(golden):
 @pytest.mark.parametrize("precision", ["fp32", "fp64"])
 def test_expected_outcome(golden, precision):
     pc.check_expected_outcome(make_engine, golden, precision)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_random_phasor_guess(golden, precision):
+    pc.check_random_phasor_guess(make_engine, golden, precision)

@@ -289,3 +289,8 @@ def test_sequence_driver_files(tmp_path, monkeypatch):
         np.testing.assert_array_equal(h, eng.to_host(r.hologram)[0])
         assert (tmp_path / "images" / "moving_traps" / "seq_v1_preview" / f"{i}.png").exists()
     eng.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_random_phasor_guess(golden, precision):
+    pc.check_random_phasor_guess(make_engine, golden, precision)
