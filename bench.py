@@ -102,48 +102,49 @@ def measured_peak():
 
 
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle-reason samples DURING the timed region, taken with NVML from a background
+    thread (an `nvidia-smi -lms` child process perturbed the timed region on this pool: bimodal step times)."""
+    THROTTLE = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
 
-    def __init__(self, index):
-        self.index, self.proc, self.path = index, None, None
+    def __init__(self, index, period_s=0.05):
+        self.index, self.period, self.samples, self._stop, self.thread, self.err = index, period_s, [], False, None, None
 
     def start(self):
+        import threading
         try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+        except Exception as exc:
+            self.err = f"nvml unavailable: {exc}"
+            return
 
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        for line in open(self.path):
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        os.unlink(self.path)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(power)}
+        def loop():
+            nv, h = self.nv, self.h
+            while not self._stop:
+                try:
+                    self.samples.append((time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
+                                         nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM),
+                                         nv.nvmlDeviceGetCurrentClocksEventReasons(h), nv.nvmlDeviceGetPowerUsage(h) / 1000.0))
+                except Exception as exc:
+                    self.err = str(exc)
+                    return
+                time.sleep(self.period)
+        self.thread = threading.Thread(target=loop, daemon=True)
+        self.thread.start()
+
+    def stop(self, t_begin=None, t_end=None):
+        self._stop = True
+        if self.thread:
+            self.thread.join(timeout=2)
+        rows = [r for r in self.samples if t_begin is None or t_begin - 0.05 <= r[0] <= t_end + 0.05] or self.samples[-1:]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "no samples"]}
+        reasons = sorted(k for k, bit in self.THROTTLE.items() if any(r[3] & bit for r in rows))
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": float(max(r[2] for r in rows)),
+                "reasons": reasons, "samples": len(rows), "power_w_max": max(r[4] for r in rows), "source": "nvml"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -228,23 +229,25 @@ def run_b200(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(a.warmup, 3)):
-        step()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(max(a.warmup, 3)):
+        step()
+    barrier()
     n0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    wall0 = time.time()
     e0.record()
     for _ in range(a.steps):
         q = step()
     e1.record()
     barrier()
+    wall1 = time.time()
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count() - n0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     if world > 1:
         tmax = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)

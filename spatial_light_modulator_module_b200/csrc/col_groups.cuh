@@ -16,6 +16,21 @@
 
 namespace slm {
 
+// Optional device timeline (-DSLM_TRACE): lane 0 of compute warp 0 / of the producer warp stamps
+// globaltimer at the phase boundaries of each tile into slm_trace_buf[cta][tile][event].
+#if defined(SLM_TRACE) && !defined(SLM_EMULATE)
+SLM_DEV void trace_stamp(unsigned long long* buf, bool who, unsigned k, int ev) {
+    if (buf && who && k < 64) {
+        unsigned long long tns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+        buf[((size_t)blockIdx.x * 64 + k) * 16 + ev] = tns;
+    }
+}
+#define SLM_STAMP(who, k, ev) trace_stamp(ga.trace, who, k, ev)
+#else
+#define SLM_STAMP(who, k, ev)
+#endif
+
 constexpr int lines_per_group(int m) { return m % 32 == 0 ? 1 : (m % 16 == 0 ? 2 : (m % 8 == 0 ? 4 : 8)); }
 
 template <typename R, int H> struct ColGroupGeom {
@@ -24,7 +39,11 @@ template <typename R, int H> struct ColGroupGeom {
     static constexpr int E = P::E, M = P::M, TC = CG::TC;
     static constexpr int COMPUTE = TC * M;                        // compute threads
     static constexpr int NW = COMPUTE / 32;                       // compute warps
-    static constexpr int THREADS = COMPUTE + 32;                  // + producer warp
+    // producer warp-group (4 warps): lane 0 drives TMA, warps 0-2 stage the 8-bit target rows, warp 3 is the
+    // PUBLISHER: it takes each finished tile's partial sums to global memory and closes a plane's iteration
+    static constexpr int PRODUCERS = 128;
+    static constexpr int COPIERS = 96;
+    static constexpr int THREADS = COMPUTE + PRODUCERS;
     static constexpr int ROWB = TC * (int)sizeof(cpx<R>);         // bytes of one tile row
     static constexpr int LPG = lines_per_group(M);
     static constexpr int GROUPS = TC / LPG;
@@ -40,17 +59,36 @@ template <typename R, int H> struct ColGroupGeom {
     static constexpr size_t OFF_LUT = OFF_GREY + 2 * GREY;
     static constexpr size_t OFF_RED = OFF_LUT + 256 * sizeof(R);
     static constexpr size_t OFF_CNT = OFF_RED + 2 * 32 * sizeof(Partial);
-    static constexpr size_t OFF_BAR = OFF_CNT + 16;
-    static constexpr size_t SMEM = OFF_BAR + 4 * 16;
+    static constexpr size_t OFF_TOT = OFF_CNT + 16;                // Partial tile_total[2]
+    static constexpr size_t OFF_BAR = OFF_TOT + 2 * sizeof(Partial);
+    static constexpr size_t SMEM = OFF_BAR + 6 * 16;
     using Sync = GroupSync<GROUP_THREADS>;
 };
 
-// copy TC bytes (one tile row of the 8-bit target)
-template <int TC> SLM_DEV void copy_grey_row(const uint8_t* src, uint8_t* dst) {
-    if (TC == 8) *reinterpret_cast<uint2*>(dst) = ld_ro(reinterpret_cast<const uint2*>(src));
-    else if (TC == 4) *reinterpret_cast<unsigned*>(dst) = ld_ro(reinterpret_cast<const unsigned*>(src));
-    else if (TC == 2) *reinterpret_cast<unsigned short*>(dst) = ld_ro(reinterpret_cast<const unsigned short*>(src));
-    else *dst = ld_ro(src);
+// One lane's share of a tile of the 8-bit target: rows lane, lane+32, ... (TC bytes each).  Every
+// load is issued before the first store so the whole tile is one DRAM round trip.
+template <int TC> struct GreyWord;
+template <> struct GreyWord<8> { using type = uint2; };
+template <> struct GreyWord<4> { using type = unsigned; };
+template <> struct GreyWord<2> { using type = unsigned short; };
+template <> struct GreyWord<1> { using type = unsigned char; };
+template <int TC, int H, int NT> SLM_DEV void copy_grey_tile(const uint8_t* src, size_t pitch, uint8_t* dst, int lane) {
+    using Wd = typename GreyWord<TC>::type;
+    constexpr int ROWS = (H + NT - 1) / NT, CH = ROWS < 16 ? ROWS : 16;
+#pragma unroll 1
+    for (int r0 = 0; r0 < ROWS; r0 += CH) {
+        Wd w[CH];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            const int row = lane + NT * (r0 + i);
+            if (row < H) w[i] = ld_ro(reinterpret_cast<const Wd*>(src + (size_t)row * pitch));
+        }
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            const int row = lane + NT * (r0 + i);
+            if (row < H) *reinterpret_cast<Wd*>(dst + (size_t)row * TC) = w[i];
+        }
+    }
 }
 
 template <typename R, int H, int MODE>
@@ -74,13 +112,16 @@ col_group_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const S
     unsigned* const cnt = reinterpret_cast<unsigned*>(raw + G::OFF_CNT);
     TileBarrier* const full = reinterpret_cast<TileBarrier*>(raw + G::OFF_BAR);       // [2]
     TileBarrier* const done = full + 2;                                                // [2]
+    TileBarrier* const pubfree = full + 4;                                             // [2] tile_total[s] has been taken
+    Partial* const tile_total = reinterpret_cast<Partial*>(raw + G::OFF_TOT);          // [2]
 
     const int t = threadIdx.x;
     const int tiles = a.W / TC;
     const long long total = (long long)a.B * tiles;
     const bool use_t8 = HAS_T && a.T8 != nullptr;
     if (t == 0) {
-        mbar_init(full + 0, use_t8 ? 33u : 1u); mbar_init(full + 1, use_t8 ? 33u : 1u);
+        mbar_init(full + 0, use_t8 ? 1u + G::COPIERS : 1u); mbar_init(full + 1, use_t8 ? 1u + G::COPIERS : 1u);
+        mbar_init(pubfree + 0, 1u); mbar_init(pubfree + 1, 1u);
         mbar_init(done + 0, (unsigned)G::COMPUTE); mbar_init(done + 1, (unsigned)G::COMPUTE);
         cnt[0] = 0; cnt[1] = 0;
         mbar_fence_init();
@@ -92,38 +133,90 @@ col_group_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const S
     sync_cta();
     auto rests = [&](int b) { return MODE != CGM_COMPLEX && ld_cg(&a.stats[b].done) != 0; };
 
+    constexpr bool HAS_STATS = MODE != CGM_COMPLEX;
+    constexpr int FIELDS = MODE == CGM_GS ? F_ALL : (IS_GD ? F_A : F_MX);
+    if (t >= G::COMPUTE + G::COPIERS) {
+        // ================= publisher warp =================
+        if (!HAS_STATS) return;
+        const int lane = t - G::COMPUTE - G::COPIERS;
+        const double hw = (double)H * (double)a.W;
+        unsigned k = 0;
+        for (long long g = blockIdx.x; g < total; g += gridDim.x) {
+            const int b = (int)(g / tiles), tile = (int)(g % tiles);
+            if (rests(b)) continue;
+            const int s = (int)(k & 1u);
+            PlaneStats* st = a.stats + b;
+            // values the closing formulas need, read before this launch can change them
+            const double s0 = ld_cg(&st->scale), norm = ld_ro(a.norm + b);
+            mbar_wait(done + s, (k >> 1) & 1u);              // every compute thread is through tile k (totals are in shared memory)
+            Partial q = tile_total[s];
+            shfl_idx(0u, 0);                                 // all lanes hold their copy before the slot is released
+            if (lane == 0) mbar_arrive(pubfree + s);
+            Partial* plane_partials = a.partial + (size_t)b * tiles;
+            unsigned ticket = 0;
+            if (lane == 0) ticket = publish_partial(q, plane_partials, tile, tiles, a.counter + b);
+            Partial tot;
+            if (collect_if_last<FIELDS>(ticket, lane, plane_partials, tiles, tot) && lane == 0) {
+                if (IS_STATS) {
+                    st->imax = tot.mx; st->scale = norm / tot.mx;
+                } else {
+                    double err;
+                    if (MODE == CGM_GS) {
+                        const double sN = norm / tot.mx;                 // algorithms.py:37
+                        const double s0u = (double)(R)s0;                // the scale the tiles actually used
+                        const double dl = (s0u != 0.0) ? sN / s0u - 1.0 : 0.0;
+                        err = (tot.a + 2.0 * dl * tot.b + dl * dl * tot.c) / hw;   // == sum((s*I - T)^2)/HW, :38,:162
+                        st->imax = tot.mx; st->scale = sN;
+                    } else {
+                        err = tot.a / hw;                                // algorithms.py:92
+                    }
+                    const int it = st->iters;
+                    a.err_curve[(size_t)b * a.max_loops + it] = err;
+                    st->err = err; st->iters = it + 1;
+                    st->done = !(err > a.tolerance);                     // loop condition, algorithms.py:29,83
+                }
+            }
+            ++k;
+        }
+        return;
+    }
     if (t >= G::COMPUTE) {
-        // ================= producer warp =================
+        // ================= producer warps (TMA + target staging) =================
         const int lane = t - G::COMPUTE;
-        auto issue = [&](long long g, int s) {
+        auto issue = [&](long long g, int s, unsigned kk) {
             const int b = (int)(g / tiles), tile = (int)(g % tiles);
             if (lane == 0) {
+                SLM_STAMP(true, kk, 8);
                 tile_store_wait_read();          // the store that last read this buffer has drained it
+                SLM_STAMP(true, kk, 9);
                 tile_load(tm_in, s ? tile1 : tile0, full + s, (long long)b * H, H, (long long)tile * ROWB, ROWB, (int)sizeof(R));
             }
             if (use_t8) {
-                shfl_idx(0u, 0);                 // warp convergence point: lane 0's wait covers the grey buffer too
+                sync_named(15, G::COPIERS);      // lane 0's wait (the store has drained) covers the grey buffer too
                 const uint8_t* src = a.T8 + (size_t)b * H * a.W + (size_t)tile * TC;
                 uint8_t* dst = s ? grey1 : grey0;
-#pragma unroll 8
-                for (int row = lane; row < H; row += 32) copy_grey_row<TC>(src + (size_t)row * a.W, dst + (size_t)row * TC);
+                copy_grey_tile<TC, H, G::COPIERS>(src, (size_t)a.W, dst, lane);
                 mbar_arrive(full + s);
+                SLM_STAMP(lane == 0, kk, 10);
             }
         };
         long long g = blockIdx.x;
         while (g < total && rests((int)(g / tiles))) g += gridDim.x;
-        if (g < total) issue(g, 0);
+        if (g < total) issue(g, 0, 0);
         unsigned k = 0;
         while (g < total) {
             long long gn = g + gridDim.x;
             while (gn < total && rests((int)(gn / tiles))) gn += gridDim.x;
             const int s = (int)(k & 1u);
-            if (gn < total) issue(gn, s ^ 1);
+            if (gn < total) issue(gn, s ^ 1, k + 1);
+            SLM_STAMP(lane == 0, k, 11);
             mbar_wait(done + s, (k >> 1) & 1u);
+            SLM_STAMP(lane == 0, k, 12);
             if (HAS_OUT && lane == 0) {
                 const int b = (int)(g / tiles), tile = (int)(g % tiles);
                 tile_store(tm_out, s ? tile1 : tile0, (long long)b * H, H, (long long)tile * ROWB, ROWB, (int)sizeof(R));
                 tile_store_commit();
+                SLM_STAMP(true, k, 13);
             }
             g = gn;
             ++k;
@@ -137,7 +230,6 @@ col_group_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const S
     const typename G::Sync sync{1 + c / G::LPG};
     cpx<R>* const line = reinterpret_cast<cpx<R>*>(raw + G::OFF_XCH) + (size_t)c * P::NP;
     const cpx<R>* tw = static_cast<const cpx<R>*>(a.tw);
-    const double hw = (double)H * (double)a.W;
     cpx<R> v[E];
     unsigned k = 0;
     // the "plane rests" flag of a tile is requested one tile ahead, so its L2 round trip is never waited for
@@ -152,7 +244,9 @@ col_group_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const S
         PlaneStats* st = a.stats ? a.stats + b : nullptr;
         double s0 = 0, imax = 0, norm = 0;
         if (MODE == CGM_GS || IS_GD) { s0 = ld_cg(&st->scale); imax = ld_cg(&st->imax); norm = ld_ro(a.norm + b); }
+        SLM_STAMP(t == 0, k, 0);
         mbar_wait(full + s, (k >> 1) & 1u);
+        SLM_STAMP(t == 0, k, 1);
 #pragma unroll
         for (int r = 0; r < E; ++r)
             v[r] = *reinterpret_cast<const cpx<R>*>(buf + tile_swizzle<ROWB>((unsigned)((j + r * M) * ROWB + c * CS)));
@@ -167,6 +261,7 @@ col_group_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const S
         if (MODE == CGM_COMPLEX && ga.mode_inverse) line_fft<R, H, +1, 1>(v, line, j, tw, sync);
         else if (MODE != CGM_GD_POST) line_fft<R, H, -1, 1>(v, line, j, tw, sync);
 
+        SLM_STAMP(t == 0, k, 2);
         // ---- pointwise step and per-thread sums ----
         R mx = 0, sa = 0, sb = 0, sc = 0;
         const R s0r = (R)s0;
@@ -202,12 +297,10 @@ col_group_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const S
             for (int r = 0; r < E; ++r) v[r] = cscale(v[r], sc_out);
         }
 
-        // ---- tile reduction without a CTA barrier: the last warp to arrive sums the warps' partials ----
-        constexpr int FIELDS = MODE == CGM_GS ? F_ALL : (IS_GD ? F_A : F_MX);
-        bool tail_warp = false;
-        unsigned ticket = 0;
-        Partial* plane_partials = nullptr;
-        if (MODE != CGM_COMPLEX) {
+        SLM_STAMP(t == 0, k, 3);
+        // ---- tile reduction without a CTA barrier: the last warp to arrive sums the warps' partials and leaves
+        //      the tile total in shared memory for the publisher warp (nothing global on the compute path) ----
+        if (HAS_STATS) {
             Partial p; p.mx = (double)mx; p.a = (double)sa; p.b = (double)sb; p.c = (double)sc;
             p = warp_reduce<FIELDS>(p);
             unsigned arrived = 0;
@@ -217,18 +310,22 @@ col_group_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const S
                 arrived = atomic_add_shared(cnt + s, 1u);
             }
             arrived = shfl_idx(arrived, 0);
-            tail_warp = arrived == (unsigned)G::NW - 1;
-            if (tail_warp) {
+            if (arrived == (unsigned)G::NW - 1) {
                 fence_block();
                 Partial q; q.mx = 0; q.a = 0; q.b = 0; q.c = 0;
                 if (lane < G::NW) q = red[s * 32 + lane];
                 q = warp_reduce<FIELDS>(q);
-                plane_partials = a.partial + (size_t)b * tiles;
-                if (lane == 0) { cnt[s] = 0; ticket = publish_partial(q, plane_partials, tile, tiles, a.counter + b); }
+                if (lane == 0) {
+                    cnt[s] = 0;
+                    if (k >= 2) mbar_wait(pubfree + s, ((k >> 1) - 1u) & 1u);   // the publisher has taken this slot's previous total
+                    tile_total[s] = q;
+                }
             }
         }
 
+        SLM_STAMP(t == 0, k, 4);
         if (MODE == CGM_GS || IS_GD) line_fft<R, H, +1, 1>(v, line, j, tw, sync);
+        SLM_STAMP(t == 0, k, 5);
         if (HAS_OUT) {
 #pragma unroll
             for (int r = 0; r < E; ++r)
@@ -236,31 +333,9 @@ col_group_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const S
             fence_async_smem();
         }
         mbar_arrive(done + s);
+        SLM_STAMP(t == 0, k, 6);
         ++k;
 
-        if (tail_warp) {
-            Partial tot;
-            if (collect_if_last<FIELDS>(ticket, lane, plane_partials, tiles, tot) && lane == 0) {
-                if (IS_STATS) {
-                    st->imax = tot.mx; st->scale = ld_ro(a.norm + b) / tot.mx;
-                } else {
-                    double err;
-                    if (MODE == CGM_GS) {
-                        const double sN = norm / tot.mx;
-                        const double s0u = (double)s0r;
-                        const double dl = (s0u != 0.0) ? sN / s0u - 1.0 : 0.0;
-                        err = (tot.a + 2.0 * dl * tot.b + dl * dl * tot.c) / hw;
-                        st->imax = tot.mx; st->scale = sN;
-                    } else {
-                        err = tot.a / hw;
-                    }
-                    const int it = st->iters;
-                    a.err_curve[(size_t)b * a.max_loops + it] = err;
-                    st->err = err; st->iters = it + 1;
-                    st->done = !(err > a.tolerance);
-                }
-            }
-        }
     }
 }
 

@@ -167,11 +167,29 @@ static int setup_groups(slm_ctx* c) {
     return 0;
 }
 
+#ifdef SLM_TRACE
+// developer tooling (trace builds only): arm / read the column kernel's device timeline
+static unsigned long long* g_trace = nullptr;
+static int g_trace_mode = -1;
+extern "C" int slm_trace_arm(int mode) {
+    if (!g_trace) cudaMalloc((void**)&g_trace, 148 * 64 * 16 * sizeof(unsigned long long));
+    cudaMemset(g_trace, 0, 148 * 64 * 16 * sizeof(unsigned long long));
+    g_trace_mode = mode;
+    return 0;
+}
+extern "C" int slm_trace_read(unsigned long long* out) {
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpy(out, g_trace, 148 * 64 * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+}
+#endif
 // Launch one mode of the warp-specialised column kernel over X (in) -> map_out.
 static int launch_group(slm_ctx* c, int mode, int batch, const ColArgs* loop, const TileMap* map_out, int inverse, double scale) {
     ColGroupArgs ga{};
     if (loop) ga.c = *loop;
     ga.mode_inverse = inverse; ga.scale = scale;
+#ifdef SLM_TRACE
+    if (mode == g_trace_mode) { ga.trace = g_trace; g_trace_mode = -1; }      // trace the next launch of that mode only
+#endif
     ga.c.B = batch; ga.c.W = c->W; ga.c.stats = c->stats; ga.c.partial = c->partial; ga.c.counter = c->counter;
     ga.c.norm = c->norm; ga.c.tw = c->tw_col;
     const int kind = (mode == CGM_STATS || mode == CGM_STATS_KEEP) ? K_COL_STATS : (mode == CGM_COMPLEX ? K_COL_PLAIN : K_COL_PASS);

@@ -78,6 +78,7 @@ enum ColGroupMode {
 struct ColGroupArgs {
     int mode_inverse;        // CGM_COMPLEX: transform direction
     double scale;            // CGM_COMPLEX: output scale
+    unsigned long long* trace;   // -DSLM_TRACE builds: [ctas][64 tiles][16 events] globaltimer stamps, else null
     ColArgs c;               // loop arguments; B, W, stats, partial, counter, norm, tw are used by every mode
 };
 
