@@ -95,6 +95,17 @@ int slm_fourier_guess(slm_ctx* ctx, int batch, const uint8_t* target_u8, const v
  * x_out: device complex<R>[n]. */
 int slm_random_phasor(slm_ctx* ctx, const double* u, void* x_out, long long n, double divide_by);
 
+/* inc_amp * exp(1j*phase): B of algorithms.py:30 from a hologram angle(A), to continue a GS run (used for the
+ * per-iteration GIF snapshots, algorithms.py:40-41).  phase: device double[n]; inc_amp: device real<R>[plane] or NULL. */
+int slm_phase_phasor(slm_ctx* ctx, const double* phase, const void* inc_amp, void* x_out, long long n, long long plane);
+
+/* move_traps.update_hologram -- move_traps.py:64-68: np.angle(ifft2(one_hot(row, col))) in closed form. */
+int slm_single_trap_phase(slm_ctx* ctx, int H, int W, int row, int col, double* out);
+
+/* traps_images.make_traps_image / dot -- traps_images.py:10-16,87-91, batched: zero `frames`
+ * (device uint8 [n_frames][H][W]) and set the pixels listed in frame_y_x (device int[n_dots][3]) to 255. */
+int slm_trap_frames(slm_ctx* ctx, uint8_t* frames, int n_frames, int H, int W, const int* frame_y_x, int n_dots);
+
 /* error_evolution and its length per plane (algorithms.py:25,39,93) of the last run.
  * err: host double[batch][max_loops]; iters: host int[batch].  Synchronises the stream. */
 int slm_read_curves(slm_ctx* ctx, int batch, int max_loops, double* err, int* iters);

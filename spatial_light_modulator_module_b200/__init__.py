@@ -13,4 +13,4 @@ There is no CPU fallback.
 __version__ = "0.1.0"
 
 __all__ = ["algorithms", "constants", "display_holograms", "engine", "generate_hologram",
-           "generate_hologram_sequence", "host_logic", "synthetic", "wavefront_correction"]
+           "generate_hologram_sequence", "host_logic", "move_traps", "synthetic", "wavefront_correction"]

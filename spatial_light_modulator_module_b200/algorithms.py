@@ -10,7 +10,9 @@ reference's signature:
 Differences a caller can observe are limited to: the ``\\rloop i/N`` progress text is printed once
 at the end instead of after every iteration (the loop runs on the device without host round
 trips), and floating-point results agree with numpy within the tolerances in DESIGN.md rather
-than bit for bit.
+than bit for bit.  With ``args.gif`` the loop is run in chunks that end at the iterations the
+reference snapshots (``i % gif_skip == 0``, algorithms.py:40-41,94-101) and the same PNG frames
+are written.
 """
 from __future__ import annotations
 
@@ -60,15 +62,17 @@ def gerchberg_saxton(demanded_output, args):
         print()
         raise UnboundLocalError("cannot access local variable 'expected_outcome' where it is not associated with a value")
     eng = _engine(target.shape, args)
-    res = eng.gs(target, int(args.max_loops), float(args.tolerance), inc_amp=inc)
-    errors = [np.float64(e) for e in res.errors[0]]
     if getattr(args, "gif", False):
-        _gif_unsupported()
+        hologram, expected, errors = _gs_with_snapshots(eng, target, inc, args)
+    else:
+        res = eng.gs(target, int(args.max_loops), float(args.tolerance), inc_amp=inc)
+        errors = [np.float64(e) for e in res.errors[0]]
+        hologram, expected = eng.to_host(res.hologram)[0], eng.to_host(res.expected)[0]
     _progress(len(errors), args.max_loops)
     if args.print_info:
         print()
         printout(errors[-1], len(errors), errors, args.plot_error)
-    return eng.to_host(res.hologram)[0], eng.to_host(res.expected)[0], errors
+    return hologram, expected, errors
 
 
 def gradient_descent(demanded_output, args):
@@ -85,17 +89,19 @@ def gradient_descent(demanded_output, args):
         print()
         raise UnboundLocalError("cannot access local variable 'output' where it is not associated with a value")
     during, after = hl.learning_rate_schedule(args.learning_rate, args.unsettle, int(args.max_loops))
-    res, x = eng.gd(target, x0, during, int(args.max_loops), float(args.tolerance),
-                    white_attention=args.white_attention, inc_amp=inc)
-    errors = [np.float64(e) for e in res.errors[0]]
-    args.learning_rate = after[len(errors)]
     if getattr(args, "gif", False):
-        _gif_unsupported()
+        hologram, expected, errors = _gd_with_snapshots(eng, target, x0, during, inc, args)
+    else:
+        res, _x = eng.gd(target, x0, during, int(args.max_loops), float(args.tolerance),
+                         white_attention=args.white_attention, inc_amp=inc)
+        errors = [np.float64(e) for e in res.errors[0]]
+        hologram, expected = eng.to_host(res.hologram)[0], eng.to_host(res.expected)[0]
+    args.learning_rate = after[len(errors)]
     _progress(len(errors), args.max_loops)
     if args.print_info:
         print()
         printout(errors[-1], len(errors), errors, args.plot_error)
-    return eng.to_host(res.hologram)[0], eng.to_host(res.expected)[0], errors
+    return hologram, expected, errors
 
 
 def make_initial_guess(initial_guess_type, incomming_amplitude, demanded_output, seed, _engine_hint=None, _device=False):
@@ -161,7 +167,45 @@ def add_gif_image(args, expected_outcome, A, i):
     img.convert("L").save(f"{args.gif_source_dir}/{i // args.gif_skip}.png")
 
 
-def _gif_unsupported():
-    raise NotImplementedError(
-        "per-iteration GIF frames (args.gif) need a device->host snapshot every gif_skip iterations; "
-        "run the loop in chunks with Engine.gs(..., phasor0=...) or disable -gif")
+def _save_snapshot(args, expected, hologram, i):
+    """One GIF source frame exactly as the reference writes it (algorithms.py:52-57 / :94-101)."""
+    import PIL.Image as im
+    if args.gif_type == "h":
+        img = im.fromarray((hologram + np.pi) * args.correspond_to2pi / (2 * np.pi))
+    if args.gif_type == "i":
+        img = im.fromarray(expected)
+    img.convert("L").save(f"{args.gif_source_dir}/{i // args.gif_skip}.png")
+
+
+def _gs_with_snapshots(eng, target, inc, args):
+    """GS in chunks ending at the snapshot iterations; each chunk restarts from B = inc*exp(1j*angle(A))
+    (algorithms.py:30), which is what the next iteration of an uninterrupted run computes."""
+    errors, done, phasor, hologram, expected = [], 0, None, None, None
+    for n in hl.snapshot_chunks(int(args.max_loops), int(args.gif_skip)):
+        res = eng.gs(target, n, float(args.tolerance), inc_amp=inc, phasor0=phasor)
+        errors += [np.float64(e) for e in res.errors[0]]
+        hologram, expected = eng.to_host(res.hologram)[0], eng.to_host(res.expected)[0]
+        last = done + len(res.errors[0]) - 1
+        if last % args.gif_skip == 0:
+            _save_snapshot(args, expected, hologram, last)
+        done += n
+        if len(res.errors[0]) < n:
+            break
+        phasor = eng.phase_phasor(res.hologram, inc)
+    return hologram, expected, errors
+
+
+def _gd_with_snapshots(eng, target, x0, during, inc, args):
+    errors, done, x, hologram, expected = [], 0, x0, None, None
+    for n in hl.snapshot_chunks(int(args.max_loops), int(args.gif_skip)):
+        res, x = eng.gd(target, x, during[done:done + n], n, float(args.tolerance),
+                        white_attention=args.white_attention, inc_amp=inc)
+        errors += [np.float64(e) for e in res.errors[0]]
+        hologram, expected = eng.to_host(res.hologram)[0], eng.to_host(res.expected)[0]
+        last = done + len(res.errors[0]) - 1
+        if last % args.gif_skip == 0:
+            _save_snapshot(args, expected, hologram, last)
+        done += n
+        if len(res.errors[0]) < n:
+            break
+    return hologram, expected, errors

@@ -119,6 +119,37 @@ SLM_GLOBAL void random_phasor_kernel(const double* u, cpx<R>* x, long long n, do
     }
 }
 
+// inc * exp(1j*phase): restart a GS run from a hologram (B of algorithms.py:30 with angle(A) = phase)
+template <typename R>
+SLM_GLOBAL void phase_phasor_kernel(const double* phase, const R* inc, cpx<R>* x, long long n, long long plane) {
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        const double h = phase[p];
+        const R s = inc ? inc[p % plane] : (R)1;
+        cpx<R> o; o.x = (R)cos(h) * s; o.y = (R)sin(h) * s;
+        x[p] = o;
+    }
+}
+
+// move_traps.update_hologram (move_traps.py:64-68): angle(ifft2(one-hot at (row, col))) in closed form,
+// 2*pi*(row*i/H + col*j/W) wrapped into (-pi, pi]
+SLM_GLOBAL void single_trap_kernel(double* out, int H, int W, int row, int col) {
+    const long long n = (long long)H * W;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(p / W), j = (int)(p % W);
+        // exact integer phase fractions: (row*i mod H)/H + (col*j mod W)/W
+        const double f = (double)(((long long)row * i) % H) / (double)H + (double)(((long long)col * j) % W) / (double)W;
+        double fr = f - floor(f);                       // in [0, 1)
+        if (fr > 0.5) fr -= 1.0;                        // (-0.5, 0.5]
+        out[p] = fr * 6.283185307179586;
+    }
+}
+
+// trap frames (traps_images.py:10-16,87-91): white single pixels at (frame, y, x) on a black stack
+SLM_GLOBAL void scatter_dots_kernel(unsigned char* frames, const int* fyx, int n_dots, long long plane, int W) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < n_dots) frames[(long long)fyx[3 * d] * plane + (long long)fyx[3 * d + 1] * W + fyx[3 * d + 2]] = 255;
+}
+
 // complex<R> <-> complex128 / real conversions at the boundary (numpy hands over complex128)
 template <typename TS, typename TD>
 SLM_GLOBAL void convert_kernel(const TS* in, TD* out, long long n) {

@@ -507,6 +507,42 @@ extern "C" int slm_random_phasor(slm_ctx* c, const double* u, void* x_out, long 
     return 0;
 }
 
+extern "C" int slm_phase_phasor(slm_ctx* c, const double* phase, const void* inc_amp, void* x_out, long long n, long long plane) {
+    if (!c) return fail(SLM_ERR_ARG, "slm_phase_phasor: null context");
+    SLM_CUDA(cudaSetDevice(c->device));
+    if (!phase || !x_out || n < 1 || plane < 1) return fail(SLM_ERR_ARG, "slm_phase_phasor: bad argument");
+    const dim3 grid(ew_blocks(n)), block(kEwThreads);
+    {
+        LaunchTimer t_(c, K_ELEMENTWISE);
+        if (c->prec == PREC_F32) SLM_LAUNCH((phase_phasor_kernel<float>), grid, block, 0, c->stream, phase, static_cast<const float*>(inc_amp), static_cast<cpx<float>*>(x_out), n, plane);
+        else SLM_LAUNCH((phase_phasor_kernel<double>), grid, block, 0, c->stream, phase, static_cast<const double*>(inc_amp), static_cast<cpx<double>*>(x_out), n, plane);
+    }
+    SLM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int slm_single_trap_phase(slm_ctx* c, int H, int W, int row, int col, double* out) {
+    if (!c) return fail(SLM_ERR_ARG, "slm_single_trap_phase: null context");
+    SLM_CUDA(cudaSetDevice(c->device));
+    if (!out || H < 1 || W < 1 || row < 0 || row >= H || col < 0 || col >= W) return fail(SLM_ERR_ARG, "slm_single_trap_phase: bad argument");
+    { LaunchTimer t_(c, K_ELEMENTWISE); SLM_LAUNCH(single_trap_kernel, dim3(ew_blocks((long long)H * W)), dim3(kEwThreads), 0, c->stream, out, H, W, row, col); }
+    SLM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int slm_trap_frames(slm_ctx* c, uint8_t* frames, int n_frames, int H, int W, const int* frame_y_x, int n_dots) {
+    if (!c) return fail(SLM_ERR_ARG, "slm_trap_frames: null context");
+    SLM_CUDA(cudaSetDevice(c->device));
+    if (!frames || n_frames < 1 || H < 1 || W < 1 || n_dots < 0 || (n_dots && !frame_y_x)) return fail(SLM_ERR_ARG, "slm_trap_frames: bad argument");
+    SLM_CUDA(cudaMemsetAsync(frames, 0, (size_t)n_frames * H * W, c->stream));
+    if (n_dots) {
+        LaunchTimer t_(c, K_ELEMENTWISE);
+        SLM_LAUNCH(scatter_dots_kernel, dim3((unsigned)((n_dots + 255) / 256)), dim3(256), 0, c->stream, frames, frame_y_x, n_dots, (long long)H * W, W);
+    }
+    SLM_CUDA(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int slm_read_curves(slm_ctx* c, int batch, int max_loops, double* err, int* iters) {
     SLM_TRY(check_batch(c, batch, "slm_read_curves"));
     if (max_loops < 1 || max_loops > c->loops_cap) return fail(SLM_ERR_ARG, "slm_read_curves: max_loops does not match the last run");

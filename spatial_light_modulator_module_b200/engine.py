@@ -80,7 +80,7 @@ class Engine:
         torch = self._torch
         tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
                np.dtype(np.complex64): torch.complex64, np.dtype(np.complex128): torch.complex128,
-               np.dtype(np.uint8): torch.uint8}[np.dtype(dtype)]
+               np.dtype(np.uint8): torch.uint8, np.dtype(np.int32): torch.int32}[np.dtype(dtype)]
         with torch.cuda.stream(self._stream):
             return torch.empty(tuple(shape), dtype=tdt, device=self._dev)
 
@@ -230,6 +230,37 @@ class Engine:
         x = self._mem_empty(ud.shape, self.complex_dtype)
         self._check(self._lib.slm_random_phasor(self._ctx, self._mem_ptr(ud), self._mem_ptr(x), _numel(ud), float(divide_by)))
         return x
+
+    def phase_phasor(self, phase, inc_amp=None):
+        """inc * exp(1j*phase) as complex<R> on the device (continue a GS run from a hologram)."""
+        pd = self._as_device(phase, np.float64, "phase")
+        if len(pd.shape) == 2:
+            pd = pd[None]
+        self._shape_check(tuple(pd.shape[1:]))
+        inc_dev = self._as_device(inc_amp, self.real_dtype, "inc_amp")
+        x = self._mem_empty(pd.shape, self.complex_dtype)
+        self._check(self._lib.slm_phase_phasor(self._ctx, self._mem_ptr(pd), self._mem_ptr(inc_dev), self._mem_ptr(x),
+                                               _numel(pd), self.shape[0] * self.shape[1]))
+        return x
+
+    def single_trap_phase(self, row, col, shape=None):
+        """np.angle(ifft2(one-hot at (row, col))) in closed form (move_traps.py:64-68)."""
+        h, w = shape or self.shape
+        out = self._mem_empty((h, w), np.float64)
+        self._check(self._lib.slm_single_trap_phase(self._ctx, h, w, int(row), int(col), self._mem_ptr(out)))
+        return out
+
+    def trap_frames(self, dots, n_frames, shape=None):
+        """uint8 [n_frames,H,W] stack on the device with the pixels ``dots`` = int array [n,3] of
+        (frame, y, x) set to 255 (traps_images.py:10-16,87-91 without the PNG round trip)."""
+        h, w = shape or self.shape
+        dots = np.ascontiguousarray(dots, dtype=np.int32).reshape(-1, 3)
+        if dots.size and (dots.min() < 0 or dots[:, 0].max() >= n_frames or dots[:, 1].max() >= h or dots[:, 2].max() >= w):
+            raise IndexError("trap position outside the frame")       # numpy raises IndexError at traps_images.py:89
+        frames = self._mem_empty((n_frames, h, w), np.uint8)
+        ddev = self._mem_upload(dots) if dots.size else None
+        self._check(self._lib.slm_trap_frames(self._ctx, self._mem_ptr(frames), int(n_frames), h, w, self._mem_ptr(ddev), len(dots)))
+        return frames
 
     def fourier_guess(self, targets, inc_amp=None):
         """make_initial_guess("fourier") (algorithms.py:154-157) on the device -> complex [B,H,W]."""

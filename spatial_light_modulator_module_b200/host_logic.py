@@ -70,6 +70,21 @@ def learning_rate_schedule(learning_rate, unsettle, max_loops) -> Tuple[np.ndarr
     return during, after
 
 
+def snapshot_chunks(max_loops: int, gif_skip: int) -> List[int]:
+    """Iteration counts of consecutive runs that end exactly at the iterations i with i % gif_skip == 0
+    (where algorithms.py:40,94 dump a GIF frame), plus the remainder."""
+    if gif_skip < 1:
+        raise ZeroDivisionError("integer modulo by zero")          # i % 0 in the reference
+    ends = [i for i in range(max_loops) if i % gif_skip == 0]       # snapshot after iteration i (0-based)
+    chunks, done = [], 0
+    for e in ends:
+        chunks.append(e + 1 - done)
+        done = e + 1
+    if done < max_loops:
+        chunks.append(max_loops - done)
+    return chunks
+
+
 def python_random_stream(seed, count: int) -> np.ndarray:
     """``count`` successive ``random.random()`` values after ``random.seed(seed)``.
 

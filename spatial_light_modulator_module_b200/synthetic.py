@@ -80,3 +80,15 @@ def random_mask(shape, seed=1) -> np.ndarray:
     """Stand-in wavefront-correction mask: uniform [0, 2pi) float64 (passes the range check at
     display_holograms.py:237)."""
     return np.random.default_rng(seed).uniform(0, 2 * np.pi, size=shape)
+
+
+def movie_frame_dots(number_of_frames, rescale_parameter=360 / 1024, parametrization=two_circulating_dots,
+                     shape=(c.slm_height, c.slm_width), first=0) -> np.ndarray:
+    """(frame, y, x) of every white pixel of :func:`movie_frames`, for rasterising the movie directly on
+    the device (Engine.trap_frames) instead of going through PNG files."""
+    h, w = shape
+    dots = []
+    for k in range(number_of_frames):
+        for (x, y) in parametrization(rescale_parameter * (first + k), w, h):
+            dots.append((k, round(y), round(x)))
+    return np.array(dots, dtype=np.int32).reshape(-1, 3)

@@ -13,6 +13,7 @@ Tolerances (stated once, used by both suites):
 from __future__ import annotations
 
 import numpy as np
+import pytest
 from scipy.fft import fft2, ifft2
 
 from oracle import numpy_port as P
@@ -286,4 +287,41 @@ def check_random_phasor_guess(make_engine, golden, precision):
     # the stream itself is the reference's: first 24*40 draws reproduce the golden plane
     u, _ = hl.uniform_stream_guess("random", (24, 40), 42)
     np.testing.assert_array_equal(np.exp(1j * 2 * np.pi * u), g["random"])
+    eng.close()
+
+
+def check_gif_snapshots(make_engine_unused, precision, tmp_path, gs_fn, gd_fn, ns):
+    """args.gif: the chunked run writes the reference's frames and returns the uninterrupted result."""
+    import PIL.Image as im
+    t = synthetic.shapes_target((128, 128))
+    for fn, kw in ((gs_fn, {}), (gd_fn, dict(learning_rate=0.01))):
+        for gtype in ("i", "h"):
+            d = tmp_path / f"{fn.__name__}_{gtype}"
+            d.mkdir()
+            a = ns(max_loops=7, gif=True, gif_skip=3, gif_type=gtype, gif_source_dir=str(d), precision=precision, **kw)
+            holo, exp, errs = fn(t, a)
+            b = ns(max_loops=7, precision=precision, **kw)
+            holo0, exp0, errs0 = fn(t, b)
+            assert sorted(p.name for p in d.iterdir()) == ["0.png", "1.png", "2.png"]      # iterations 0, 3, 6
+            assert len(errs) == 7
+            tol = 1e-9 if precision == "fp64" else 2e-3
+            assert np.max(np.abs(np.array(errs) - np.array(errs0)) / np.array(errs0)) < tol
+            # the last frame is the final state (iteration 6)
+            last = np.array(im.open(d / "2.png"))
+            ref = (P.preview_to_L(exp) if gtype == "i" else P.preview_to_L((holo + np.pi) * 256 / (2 * np.pi)))
+            assert np.mean(last != ref) < 1e-3
+
+
+def check_single_trap_and_frames(make_engine, golden):
+    g = golden("preview_trap")
+    r, cc = [int(v) for v in g["trap_rc"]]
+    eng = make_engine((64, 64), "fp64", 1)
+    ph = eng.to_host(eng.single_trap_phase(r, cc, (192, 256)))
+    assert circ(ph, g["trap_phase"]).max() < 1e-11
+    assert np.all(ph > -np.pi - 1e-15) and np.all(ph <= np.pi + 1e-15)
+    dots = synthetic.movie_frame_dots(6, rescale_parameter=13.0)
+    frames = eng.to_host(eng.trap_frames(dots, 6, (768, 1024)))
+    np.testing.assert_array_equal(frames, synthetic.movie_frames(6, rescale_parameter=13.0))
+    with pytest.raises(IndexError):
+        eng.trap_frames(np.array([[0, 800, 3]]), 1, (768, 1024))
     eng.close()

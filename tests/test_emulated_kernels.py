@@ -73,3 +73,7 @@ def test_expected_outcome(golden, precision):
 @pytest.mark.parametrize("precision", ["fp32", "fp64"])
 def test_random_phasor_guess(golden, precision):
     pc.check_random_phasor_guess(make_engine, golden, precision)
+
+
+def test_single_trap_and_device_frames(golden):
+    pc.check_single_trap_and_frames(make_engine, golden)

@@ -294,3 +294,26 @@ def test_sequence_driver_files(tmp_path, monkeypatch):
 @pytest.mark.parametrize("precision", ["fp32", "fp64"])
 def test_random_phasor_guess(golden, precision):
     pc.check_random_phasor_guess(make_engine, golden, precision)
+
+
+def test_single_trap_and_device_frames(golden):
+    pc.check_single_trap_and_frames(make_engine, golden)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_gif_snapshots(tmp_path, precision):
+    from spatial_light_modulator_module_b200 import algorithms
+    pc.check_gif_snapshots(None, precision, tmp_path,
+                           lambda t, a: quiet(algorithms.gerchberg_saxton, t, a),
+                           lambda t, a: quiet(algorithms.gradient_descent, t, a), ns)
+
+
+def test_move_traps_update_hologram(golden):
+    from spatial_light_modulator_module_b200 import move_traps
+    g = golden("preview_trap")
+    r, c = [int(v) for v in g["trap_rc"]]
+    img = np.zeros((192, 256), dtype=np.uint8)
+    h = move_traps.update_hologram(img, [(r, c), (5, 5)], 0)
+    assert pc.circ(h, g["trap_phase"]).max() < 1e-11
+    with pytest.raises(IndexError):
+        move_traps.update_hologram(img, [(500, 1)], 0)

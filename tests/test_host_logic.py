@@ -89,3 +89,17 @@ def test_scalars():
     assert sy == np.sin(2.0 * c.u) and sx == np.sin(1.0 * c.u)
     k, f2 = hl.lens_scalars(0.5, c.wavelength)
     assert k == 2 * np.pi * 0.5 / c.wavelength and f2 == 0.25
+
+
+def test_snapshot_chunks():
+    assert hl.snapshot_chunks(7, 3) == [1, 3, 3]
+    assert hl.snapshot_chunks(10, 1) == [1] * 10
+    assert hl.snapshot_chunks(5, 10) == [1, 4]
+    assert hl.snapshot_chunks(1, 4) == [1]
+    for loops, skip in ((20, 6), (9, 2), (3, 7)):
+        ch = hl.snapshot_chunks(loops, skip)
+        assert sum(ch) == loops
+        ends = np.cumsum(ch) - 1
+        assert [e for e in ends if e % skip == 0] == [i for i in range(loops) if i % skip == 0]
+    with pytest.raises(ZeroDivisionError):
+        hl.snapshot_chunks(5, 0)
