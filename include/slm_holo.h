@@ -106,6 +106,31 @@ int slm_single_trap_phase(slm_ctx* ctx, int H, int W, int row, int col, double* 
  * (device uint8 [n_frames][H][W]) and set the pixels listed in frame_y_x (device int[n_dots][3]) to 255. */
 int slm_trap_frames(slm_ctx* ctx, uint8_t* frames, int n_frames, int H, int W, const int* frame_y_x, int n_dots);
 
+/* ---- one very large plane split by rows over the ranks (BASELINE config 5): slab-decomposed 2-D transform ----
+ * Rank p owns `rows` = N/P rows of the N x N field.  A 2-D transform is: line transforms on the row slab,
+ * exchange (pack -> all-to-all -> the peers' blocks side by side = the "exchange layout"), line transforms
+ * on the received columns (now contiguous lines), exchange back.  The library supplies the kernels; the
+ * all-to-all and the 4-scalar all-reduce are the caller's (NCCL through torch.distributed in slab.py).
+ * GS does not depend on the transform's scale (only angle(A) is used), so these transforms are unnormalised. */
+int slm_rows_create(slm_ctx** out, int device, int rows, int W, int precision, void* cuda_stream);
+/* plain line transforms of every row: `in` complex<R> (or in_u8 + host lut[256] -> real input, algorithms.py:21,27);
+ * block_in/block_out = 0 for [rows][W], else the exchange layout's block width (= rows). */
+int slm_rows_fft(slm_ctx* ctx, const void* in, const uint8_t* in_u8, const double* lut, void* out, int inverse,
+                 int block_in, int block_out);
+/* SLM-plane step on a row slab (algorithms.py:30,34): in_is_field = 0: finish ifft2 along the rows first;
+ * 1: `in` is the field A itself (complex<R>); 2: A as complex64 whatever the context's precision (the
+ * reference's first ifft2 runs in complex64 for 8-bit targets) -- phasor taken in fp32.
+ * final_pass: write angle(A) to `hologram` (device double [rows][W]) instead of starting the next fft2. */
+int slm_rows_gs_row_pass(slm_ctx* ctx, const void* in, void* out, const void* inc_amp, int in_is_field, int final_pass,
+                         double* hologram);
+/* Fourier-plane step (algorithms.py:31-38) on received columns in the exchange layout: finishes fft2, replaces
+ * the amplitude, starts ifft2; per-line sums (max |C|^2, sum r^2, sum r*u, sum u^2 against scale_prev) go to
+ * partial[rows][4]; intensity (nullable, device double, same layout) receives |C|^2. */
+int slm_rows_gs_fourier_pass(slm_ctx* ctx, const void* in, void* out, int block_w, const uint8_t* target_u8,
+                             const double* amp_lut, double scale_prev, double* partial, double* intensity);
+/* row slab [rows][W] <-> exchange layout [W/rows][rows][rows] (each block transposed); elem_bytes 1, 8 or 16. */
+int slm_transpose_blocks(slm_ctx* ctx, const void* in, void* out, int rows, int W, int elem_bytes, int from_exchange);
+
 /* error_evolution and its length per plane (algorithms.py:25,39,93) of the last run.
  * err: host double[batch][max_loops]; iters: host int[batch].  Synchronises the stream. */
 int slm_read_curves(slm_ctx* ctx, int batch, int max_loops, double* err, int* iters);

@@ -150,6 +150,31 @@ SLM_GLOBAL void scatter_dots_kernel(unsigned char* frames, const int* fyx, int n
     if (d < n_dots) frames[(long long)fyx[3 * d] * plane + (long long)fyx[3 * d + 1] * W + fyx[3 * d + 2]] = 255;
 }
 
+// Slab exchange layout <-> row slab (slab-decomposed 2-D transform).  With h lines per rank and P = W/h peers:
+//   to_exchange : out[q][c][i] = in[i][q*h + c]     (block q is what peer q receives; each block transposed)
+//   from_exchange: out[i][q*h + c] = in[q][c][i]
+// 32x32 tiles through padded shared memory, coalesced on both sides.
+template <typename T>
+SLM_GLOBAL void transpose_blocks_kernel(const T* in, T* out, int h, int W, int from_exchange) {
+    SLM_STATIC_SMEM T tile[32][33];
+    const int q = blockIdx.z, tc = blockIdx.y * 32, ti = blockIdx.x * 32;    // block, first column c, first row i
+    const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;                   // 32 x 8 threads
+    const size_t blk = (size_t)q * h * h;
+    if (!from_exchange) {
+#pragma unroll
+        for (int k = 0; k < 32; k += 8) tile[ty + k][tx] = in[(size_t)(ti + ty + k) * W + (size_t)q * h + tc + tx];     // [i][c]
+        sync_cta();
+#pragma unroll
+        for (int k = 0; k < 32; k += 8) out[blk + (size_t)(tc + ty + k) * h + ti + tx] = tile[tx][ty + k];              // [c][i]
+    } else {
+#pragma unroll
+        for (int k = 0; k < 32; k += 8) tile[ty + k][tx] = in[blk + (size_t)(tc + ty + k) * h + ti + tx];               // [c][i]
+        sync_cta();
+#pragma unroll
+        for (int k = 0; k < 32; k += 8) out[(size_t)(ti + ty + k) * W + (size_t)q * h + tc + tx] = tile[tx][ty + k];    // [i][c]
+    }
+}
+
 // complex<R> <-> complex128 / real conversions at the boundary (numpy hands over complex128)
 template <typename TS, typename TD>
 SLM_GLOBAL void convert_kernel(const TS* in, TD* out, long long n) {

@@ -292,6 +292,7 @@ extern "C" long long slm_ctx_launch_count(const slm_ctx* c) { return c ? c->laun
 
 static int check_batch(slm_ctx* c, int batch, const char* who) {
     if (!c) return fail(SLM_ERR_ARG, std::string(who) + ": null context");
+    if (!c->col) return fail(SLM_ERR_ARG, std::string(who) + ": this is a row-slab context (slm_rows_create)");
     if (batch < 1 || batch > c->max_batch) return fail(SLM_ERR_ARG, std::string(who) + ": batch exceeds the context's max_batch");
     SLM_CUDA(cudaSetDevice(c->device));
     return 0;
@@ -538,6 +539,83 @@ extern "C" int slm_trap_frames(slm_ctx* c, uint8_t* frames, int n_frames, int H,
     if (n_dots) {
         LaunchTimer t_(c, K_ELEMENTWISE);
         SLM_LAUNCH(scatter_dots_kernel, dim3((unsigned)((n_dots + 255) / 256)), dim3(256), 0, c->stream, frames, frame_y_x, n_dots, (long long)H * W, W);
+    }
+    SLM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---- row-slab API: one very large plane split by rows over the ranks (slab-decomposed transform) ---------
+extern "C" int slm_rows_create(slm_ctx** out, int device, int rows, int W, int precision, void* stream) {
+    if (!out || rows < 1 || (precision != PREC_F32 && precision != PREC_F64)) return fail(SLM_ERR_ARG, "slm_rows_create: bad argument");
+    const LineTable* row = find_line_table(W, precision);
+    if (!row) return fail(SLM_ERR_SHAPE, "unsupported line length " + std::to_string(W));
+    if (rows % row->rows_per_cta != 0 || rows % 32 != 0) return fail(SLM_ERR_SHAPE, "slab rows must be a multiple of 32 and of the CTA row tile");
+    SLM_CUDA(cudaSetDevice(device));
+    slm_ctx* c = new slm_ctx;
+    c->device = device; c->H = rows; c->W = W; c->max_batch = 1; c->prec = precision;
+    c->stream = (cudaStream_t)stream;
+    c->row = row; c->col = nullptr;
+    row->prepare();
+    int rc = 0;
+    auto A = [&](void** p, size_t n) { if (!rc) rc = dev_alloc(c, p, n); };
+    A((void**)&c->stats, sizeof(PlaneStats));
+    A(&c->lut, 256 * real_size(precision));
+    A((void**)&c->lut32, 256 * sizeof(float));
+    if (!rc) rc = make_twiddles(c, W, precision, &c->tw_row);
+    if (!rc && cudaMemset(c->stats, 0, sizeof(PlaneStats)) != cudaSuccess) rc = fail(SLM_ERR_CUDA, "cudaMemset(stats)");
+    if (rc) { std::string keep = g_err; slm_ctx_destroy(c); g_err = keep; return rc; }
+    *out = c;
+    return 0;
+}
+
+extern "C" int slm_rows_fft(slm_ctx* c, const void* in, const uint8_t* in_u8, const double* lut, void* out, int inverse,
+                            int block_in, int block_out) {
+    if (!c || !out || (!in && !in_u8) || (in_u8 && !lut)) return fail(SLM_ERR_ARG, "slm_rows_fft: bad argument");
+    SLM_CUDA(cudaSetDevice(c->device));
+    if (in_u8) SLM_TRY(upload_lut(c, lut));
+    PlainRowArgs ra{};
+    ra.B = 1; ra.H = c->H; ra.inverse = inverse; ra.block_in = block_in; ra.block_out = block_out; ra.out = out; ra.tw = c->tw_row;
+    if (in_u8) { ra.input = IN_LUT_U8; ra.T8 = in_u8; ra.lut = c->lut; } else { ra.input = IN_COMPLEX; ra.in = in; }
+    SLM_TIMED(K_ROW_PLAIN, c->row->row_plain(ra, c->stream));
+    return 0;
+}
+
+extern "C" int slm_rows_gs_row_pass(slm_ctx* c, const void* in, void* out, const void* inc_amp, int in_is_field, int final_pass,
+                                    double* hologram) {
+    if (!c || !in || (final_pass ? !hologram : !out)) return fail(SLM_ERR_ARG, "slm_rows_gs_row_pass: bad argument");
+    SLM_CUDA(cudaSetDevice(c->device));
+    RowArgs ra{};
+    ra.B = 1; ra.H = c->H; ra.Y = in; ra.field = in; ra.X = out; ra.inc = inc_amp; ra.stats = c->stats; ra.hologram = hologram;
+    ra.inv_hw = 1.0; ra.tw = c->tw_row; ra.final_pass = final_pass;
+    ra.A32 = in;
+    ra.source = in_is_field == 2 ? ROW_FROM_A32 : (in_is_field ? ROW_FROM_A : ROW_FROM_Y);
+    SLM_TIMED(K_ROW_PASS, c->row->row_pass(ALG_GS, ra, c->stream));
+    return 0;
+}
+
+extern "C" int slm_rows_gs_fourier_pass(slm_ctx* c, const void* in, void* out, int block_w, const uint8_t* target_u8,
+                                        const double* amp_lut, double scale_prev, double* partial, double* intensity) {
+    if (!c || !in || !out || !target_u8 || !amp_lut || !partial) return fail(SLM_ERR_ARG, "slm_rows_gs_fourier_pass: bad argument");
+    SLM_CUDA(cudaSetDevice(c->device));
+    SLM_TRY(upload_lut(c, amp_lut));
+    RowFourierArgs fa{};
+    fa.rows = c->H; fa.block_w = block_w; fa.in = in; fa.out = out; fa.T8 = target_u8; fa.lut = c->lut; fa.s0 = scale_prev;
+    fa.partial = partial; fa.intensity = intensity; fa.tw = c->tw_row;
+    SLM_TIMED(K_COL_PASS, c->row->row_fourier(fa, c->stream));
+    return 0;
+}
+
+extern "C" int slm_transpose_blocks(slm_ctx* c, const void* in, void* out, int rows, int W, int elem_bytes, int from_exchange) {
+    if (!c || !in || !out || in == out) return fail(SLM_ERR_ARG, "slm_transpose_blocks: bad argument");
+    if (rows < 32 || rows % 32 || W % rows) return fail(SLM_ERR_SHAPE, "slm_transpose_blocks: rows must be a multiple of 32 dividing W");
+    SLM_CUDA(cudaSetDevice(c->device));
+    const dim3 grid(rows / 32, rows / 32, W / rows), block(256);
+    {
+        LaunchTimer t_(c, K_ELEMENTWISE);
+        if (elem_bytes == 16) SLM_LAUNCH((transpose_blocks_kernel<cpx<double>>), grid, block, 0, c->stream, static_cast<const cpx<double>*>(in), static_cast<cpx<double>*>(out), rows, W, from_exchange);
+        else if (elem_bytes == 8) SLM_LAUNCH((transpose_blocks_kernel<double>), grid, block, 0, c->stream, static_cast<const double*>(in), static_cast<double*>(out), rows, W, from_exchange);
+        else if (elem_bytes == 1) SLM_LAUNCH((transpose_blocks_kernel<unsigned char>), grid, block, 0, c->stream, static_cast<const unsigned char*>(in), static_cast<unsigned char*>(out), rows, W, from_exchange);
+        else return fail(SLM_ERR_ARG, "slm_transpose_blocks: elem_bytes must be 1, 8 or 16");
     }
     SLM_CUDA(cudaGetLastError());
     return 0;

@@ -93,6 +93,7 @@ struct PlainRowArgs {
     int B, H;
     int input;               // PlainRowInput
     int inverse;
+    int block_in, block_out; // 0: plain [row][W] layout; else the slab-exchange layout of width block_* (slab.cuh)
     const void* in;          // complex<R> / real<R> / double, by `input`
     const uint8_t* T8;
     const void* lut;         // R[256]
@@ -121,6 +122,20 @@ struct PlainColArgs {
     const void* tw;
 };
 
+// ---- Fourier-plane step on ROWS of a transposed slab (slab-decomposed 2-D transform, slab.cuh) -----------
+struct RowFourierArgs {
+    int rows;                // local lines (columns of the global plane owned by this rank)
+    int block_w;             // exchange-layout block width (0: plain [rows][W])
+    const void* in;          // complex<R>: lines after the first transform + exchange
+    void* out;               // complex<R>: lines ready for the return exchange
+    const uint8_t* T8;       // target, same layout as `in`
+    const void* lut;         // R[256] amplitude by grey level
+    double s0;               // scale of the previous iteration (algorithms.py:37)
+    double* partial;         // device [rows][4]: max |C|^2, sum r^2, sum r*u, sum u^2 per line
+    double* intensity;       // device double, same layout, or null: |C|^2 (final expected_outcome, unscaled)
+    const void* tw;
+};
+
 // ---- launch table: one entry per (line length, precision), see gen_lines.py ----------------------
 struct LineTable {
     int L, prec;
@@ -134,6 +149,8 @@ struct LineTable {
     // warp-specialised persistent column kernel (col_groups.cuh); group_ok == 0: not built for this length
     int group_ok, group_row_bytes;
     int (*col_group)(int mode, const ColGroupArgs&, const void* map_in, const void* map_out, int ctas, cudaStream_t);
+    int (*row_fourier)(const RowFourierArgs&, cudaStream_t);     // fp32/fp64 GS Fourier-plane step on rows
+    int rows_only;                                               // long lines (>= 8192): no column kernels
 };
 const LineTable* find_line_table(int L, int prec);
 int supported_lengths(int* out, int cap);

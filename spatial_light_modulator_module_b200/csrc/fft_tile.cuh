@@ -161,12 +161,46 @@ template <int DIR, typename R> SLM_DEV void dft16(cpx<R>* v) {
 #pragma unroll
         for (int b = a + 1; b < 4; ++b) { cpx<R> t = v[4 * a + b]; v[4 * a + b] = v[4 * b + a]; v[4 * b + a] = t; }
 }
+// multiply by exp(DIR * 2*pi*i * P/32)
+template <int DIR, int P, typename R> SLM_DEV cpx<R> mul_w32(cpx<R> a) {
+    constexpr int p = ((P % 32) + 32) % 32;
+    if constexpr (p % 2 == 0) return mul_w16<DIR, p / 2>(a);
+    else {
+        constexpr double C32[8] = {0.98078528040323044913, 0.83146961230254523708, 0.55557023301960222474, 0.19509032201612826785,
+                                   -0.19509032201612826785, -0.55557023301960222474, -0.83146961230254523708, -0.98078528040323044913};
+        constexpr double S32[8] = {0.19509032201612826785, 0.55557023301960222474, 0.83146961230254523708, 0.98078528040323044913,
+                                   0.98078528040323044913, 0.83146961230254523708, 0.55557023301960222474, 0.19509032201612826785};
+        // odd p = 2q+1, q = 0..15: angle (2q+1)*pi/16; second half of the circle by symmetry
+        constexpr int q = p / 2;
+        constexpr double c = q < 8 ? C32[q] : -C32[q - 8];
+        constexpr double sn = q < 8 ? S32[q] : -S32[q - 8];
+        return cmul(a, mk<R>((R)c, (R)(DIR < 0 ? -sn : sn)));
+    }
+}
+template <int DIR, int K, typename R> struct Dft32Combine {
+    static SLM_DEV void run(cpx<R>* v, const cpx<R>* e, const cpx<R>* o) {
+        const cpx<R> t = mul_w32<DIR, K>(o[K]);
+        v[K] = cadd(e[K], t);
+        v[K + 16] = csub(e[K], t);
+        if constexpr (K + 1 < 16) Dft32Combine<DIR, K + 1, R>::run(v, e, o);
+    }
+};
+template <int DIR, typename R> SLM_DEV void dft32(cpx<R>* v) {
+    // 32 = 2 x 16 (decimation in time): X[k] = E[k] + W32^k O[k], X[k+16] = E[k] - W32^k O[k]
+    cpx<R> e[16], o[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) { e[m] = v[2 * m]; o[m] = v[2 * m + 1]; }
+    dft16<DIR>(e);
+    dft16<DIR>(o);
+    Dft32Combine<DIR, 0, R>::run(v, e, o);
+}
 template <int RAD, int DIR, typename R> SLM_DEV void dft_small(cpx<R>* v) {
     if constexpr (RAD == 2) dft2<DIR>(v[0], v[1]);
     else if constexpr (RAD == 3) dft3<DIR>(v[0], v[1], v[2]);
     else if constexpr (RAD == 4) dft4<DIR>(v[0], v[1], v[2], v[3]);
     else if constexpr (RAD == 8) dft8<DIR>(v);
     else if constexpr (RAD == 16) dft16<DIR>(v);
+    else if constexpr (RAD == 32) dft32<DIR>(v);
     else static_assert(RAD == 2, "unsupported radix");
 }
 
@@ -186,7 +220,7 @@ template <int RAD, typename R> SLM_DEV void twiddle_powers(cpx<R>* w, cpx<R> w1)
 
 // ---- line FFT ----------------------------------------------------------------------------
 template <int N> struct FftPlan {
-    static constexpr int E = (N >= 256) ? 16 : 8;      // points per thread
+    static constexpr int E = (N >= 8192) ? 32 : (N >= 256) ? 16 : 8;      // points per thread
     static constexpr int M = N / E;                    // threads per line
     static constexpr int MID = N / (E * E);            // middle radix (1 = none)
     static constexpr int NP = N + N / E;               // padded line length in shared memory

@@ -32,10 +32,9 @@ template <typename R, int L> struct GroupLaunch<R, L, true> {
     }
 };
 
-template <typename R, int L> struct LineOps {
+// Row (line-contiguous) kernels: available for every line length.
+template <typename R, int L> struct RowLaunch {
     using RG = RowGeom<R, L>;
-    using CG = ColGeom<R, L>;
-    using GG = ColGroupGeom<R, L>;
     static int check() { cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? 0 : -(int)e - 1000; }
     static void prepare() {
         cudaFuncSetAttribute(row_pass_kernel<R, L, ALG_GS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
@@ -43,10 +42,7 @@ template <typename R, int L> struct LineOps {
         cudaFuncSetAttribute(row_pass_kernel<R, L, ALG_GD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
         cudaFuncSetAttribute(row_pass_kernel<R, L, ALG_GD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
         cudaFuncSetAttribute(row_plain_kernel<R, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
-        cudaFuncSetAttribute(col_pass_kernel<R, L, ALG_GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG::SMEM);
-        cudaFuncSetAttribute(col_pass_kernel<R, L, ALG_GD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG::SMEM);
-        cudaFuncSetAttribute(col_plain_kernel<R, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG::SMEM);
-        GroupLaunch<R, L>::prepare();
+        cudaFuncSetAttribute(row_fourier_kernel<R, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
     }
     static int row_pass(int alg, const RowArgs& a, cudaStream_t s) {
         const dim3 grid((unsigned)((long long)a.B * a.H / RG::NR)), block(RG::THREADS);
@@ -63,6 +59,24 @@ template <typename R, int L> struct LineOps {
         const dim3 grid((unsigned)((long long)a.B * a.H / RG::NR)), block(RG::THREADS);
         SLM_LAUNCH((row_plain_kernel<R, L>), grid, block, RG::SMEM, s, a);
         return check();
+    }
+    static int row_fourier(const RowFourierArgs& a, cudaStream_t s) {
+        const dim3 grid((unsigned)(a.rows / RG::NR)), block(RG::THREADS);
+        SLM_LAUNCH((row_fourier_kernel<R, L>), grid, block, RG::SMEM, s, a);
+        return check();
+    }
+};
+
+// Column kernels: line lengths up to 4096.
+template <typename R, int L> struct ColLaunch {
+    using CG = ColGeom<R, L>;
+    using GG = ColGroupGeom<R, L>;
+    static int check() { cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? 0 : -(int)e - 1000; }
+    static void prepare() {
+        cudaFuncSetAttribute(col_pass_kernel<R, L, ALG_GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG::SMEM);
+        cudaFuncSetAttribute(col_pass_kernel<R, L, ALG_GD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG::SMEM);
+        cudaFuncSetAttribute(col_plain_kernel<R, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CG::SMEM);
+        GroupLaunch<R, L>::prepare();
     }
     static int col_pass(int alg, const ColArgs& a, cudaStream_t s) {
         const dim3 grid((unsigned)((long long)a.B * (a.W / CG::TC))), block(CG::THREADS);

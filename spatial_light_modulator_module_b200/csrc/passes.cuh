@@ -130,7 +130,10 @@ template <typename R, int L> struct RowGeom {
 #ifndef SLM_ROW_THREADS_PER_SM
 #define SLM_ROW_THREADS_PER_SM 768
 #endif
-    static constexpr int MIN_CTAS = sizeof(R) == 4 ? (SLM_ROW_THREADS_PER_SM / THREADS > 0 ? SLM_ROW_THREADS_PER_SM / THREADS : 1) : 1;   // fp32 register budget
+    // fp32 register budget: 3 x 256 threads (<= 80 registers) for 16 points per thread, 512 threads
+    // (<= 128 registers) for the 32-point long lines
+    static constexpr int BUDGET = P::E == 32 ? 512 : SLM_ROW_THREADS_PER_SM;
+    static constexpr int MIN_CTAS = sizeof(R) == 4 ? (BUDGET / THREADS > 0 ? BUDGET / THREADS : 1) : 1;
     // rows are transformed independently: the threads of LPG rows (whole warps) share a named barrier
     static constexpr int LPG = M % 32 == 0 ? 1 : (M % 16 == 0 ? 2 : (M % 8 == 0 ? 4 : 8));
     static constexpr int GROUPS = NR / LPG;
@@ -428,6 +431,13 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((ColGeom<R, H>::THREADS), 1) col_pass_kernel(C
         });
 }
 
+// Element n of local line `row` in the slab-exchange layout of block width wb (rows = lines per rank):
+// block n / wb holds [rows][wb], i.e. what one peer sends or receives in the all-to-all (slab.cuh).
+SLM_DEV size_t line_offset(int wb, int rows, int W, long long row, int n) {
+    if (wb == 0) return (size_t)row * W + n;
+    return (size_t)(n / wb) * ((size_t)rows * wb) + (size_t)row * wb + (n % wb);
+}
+
 // ---- plain row transform (setup, preview, slm_fft2) --------------------------------------------------
 template <typename R, int W>
 SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), 1) row_plain_kernel(PlainRowArgs a) {
@@ -440,30 +450,95 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), 1) row_plain_kernel(
     cpx<R>* line = reinterpret_cast<cpx<R>*>(raw) + (size_t)rr * P::NP;
     const typename G::Sync sync{1 + rr / G::LPG};
     const cpx<R>* tw = static_cast<const cpx<R>*>(a.tw);
-    const size_t base = (size_t)grow * W + j;
+    const long long total_rows = (long long)a.B * a.H;
     cpx<R> v[E];
     if (a.input == IN_COMPLEX) {
-        const cpx<R>* in = static_cast<const cpx<R>*>(a.in) + base;
+        const cpx<R>* in = static_cast<const cpx<R>*>(a.in);
 #pragma unroll
-        for (int r = 0; r < E; ++r) v[r] = ld_plane(in + r * M);
+        for (int r = 0; r < E; ++r) v[r] = ld_plane(in + line_offset(a.block_in, (int)total_rows, W, grow, j + r * M));
     } else if (a.input == IN_LUT_U8) {
         const R* lut = static_cast<const R*>(a.lut);
 #pragma unroll
-        for (int r = 0; r < E; ++r) { v[r].x = ld_ro(lut + ld_ro(a.T8 + base + r * M)); v[r].y = 0; }
+        for (int r = 0; r < E; ++r) { v[r].x = ld_ro(lut + ld_ro(a.T8 + line_offset(a.block_in, (int)total_rows, W, grow, j + r * M))); v[r].y = 0; }
     } else if (a.input == IN_REAL) {
-        const R* in = static_cast<const R*>(a.in) + base;
+        const R* in = static_cast<const R*>(a.in);
 #pragma unroll
-        for (int r = 0; r < E; ++r) { v[r].x = ld_ro(in + r * M); v[r].y = 0; }
+        for (int r = 0; r < E; ++r) { v[r].x = ld_ro(in + line_offset(a.block_in, (int)total_rows, W, grow, j + r * M)); v[r].y = 0; }
     } else {
-        const double* in = static_cast<const double*>(a.in) + base;
+        const double* in = static_cast<const double*>(a.in);
 #pragma unroll
-        for (int r = 0; r < E; ++r) { const double h = ld_ro(in + r * M); v[r].x = (R)cos(h); v[r].y = (R)sin(h); }
+        for (int r = 0; r < E; ++r) { const double h = ld_ro(in + line_offset(a.block_in, (int)total_rows, W, grow, j + r * M)); v[r].x = (R)cos(h); v[r].y = (R)sin(h); }
     }
     if (a.inverse) line_fft<R, W, +1, 1>(v, line, j, tw, sync);
     else line_fft<R, W, -1, 1>(v, line, j, tw, sync);
-    cpx<R>* out = static_cast<cpx<R>*>(a.out) + base;
+    cpx<R>* out = static_cast<cpx<R>*>(a.out);
 #pragma unroll
-    for (int r = 0; r < E; ++r) st_plane(out + r * M, v[r]);
+    for (int r = 0; r < E; ++r) st_plane(out + line_offset(a.block_out, (int)total_rows, W, grow, j + r * M), v[r]);
+}
+
+// ---- GS Fourier-plane step on the rows of a transposed slab (slab-decomposed transform) ------------------
+// Same arithmetic as col_pass_tile<GS>; a line here is one COLUMN of the global plane, held by this rank
+// after the all-to-all.  Per-line partial sums go to `partial`; the ranks' totals are combined by the
+// caller (NCCL all-reduce), which also closes the iteration (scale, error).
+template <typename R, int W>
+SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), (RowGeom<R, W>::MIN_CTAS)) row_fourier_kernel(RowFourierArgs a) {
+    using G = RowGeom<R, W>;
+    using P = FftPlan<W>;
+    constexpr int E = P::E, M = P::M;
+    SLM_DYN_SMEM(raw);
+    const int t = threadIdx.x, rr = t / M, j = t % M;
+    const long long row = (long long)blockIdx.x * G::NR + rr;
+    cpx<R>* line = reinterpret_cast<cpx<R>*>(raw) + (size_t)rr * P::NP;
+    const typename G::Sync sync{1 + rr / G::LPG};
+    const cpx<R>* tw = static_cast<const cpx<R>*>(a.tw);
+    const cpx<R>* in = static_cast<const cpx<R>*>(a.in);
+    const R* lut = static_cast<const R*>(a.lut);
+    cpx<R> v[E];
+    int grey[E];
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const size_t off = line_offset(a.block_w, a.rows, W, row, j + r * M);
+        v[r] = ld_plane(in + off);
+        grey[r] = ld_ro(a.T8 + off);
+    }
+    line_fft<R, W, -1, 1>(v, line, j, tw, sync);              // second half of C = fft2(B)
+    R mx = 0, sa = 0, sb = 0, sc = 0;
+    const R s0r = (R)a.s0;
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const R m2 = cnorm2(v[r]);
+        const R amp = ld_ro(lut + grey[r]);
+        const R u = s0r * m2, d = u - (R)grey[r];
+        mx = fmax(mx, m2); sa += d * d; sb += d * u; sc += u * u;
+        if (a.intensity) a.intensity[line_offset(a.block_w, a.rows, W, row, j + r * M)] = (double)m2;
+        v[r] = (m2 == (R)0) ? mk<R>(copysign(amp, v[r].x), (R)0) : cscale(v[r], amp * rsqrt_fast(m2));   // algorithms.py:33
+    }
+    line_fft<R, W, +1, 1>(v, line, j, tw, sync);              // first half of A = ifft2(D)
+    cpx<R>* out = static_cast<cpx<R>*>(a.out);
+#pragma unroll
+    for (int r = 0; r < E; ++r) st_plane(out + line_offset(a.block_w, a.rows, W, row, j + r * M), v[r]);
+
+    // per-line reduction over its M threads
+    Partial p; p.mx = (double)mx; p.a = (double)sa; p.b = (double)sb; p.c = (double)sc;
+    Partial q; q.mx = 0; q.a = 0; q.b = 0; q.c = 0;
+    if (M >= 32) {                                            // a line is whole warps
+        SLM_STATIC_SMEM Partial red[32];
+        p = warp_reduce<F_ALL>(p);
+        if (t % 32 == 0) red[t / 32] = p;
+        sync_cta();
+        if (j == 0)
+            for (int w = 0; w < M / 32; ++w) q = combine<F_ALL>(q, red[rr * (M / 32) + w]);
+    } else {                                                  // several short lines share a warp
+        SLM_STATIC_SMEM Partial pt[M >= 32 ? 1 : G::THREADS];
+        pt[M >= 32 ? 0 : t] = p;
+        sync_cta();
+        if (j == 0)
+            for (int i = 0; i < M; ++i) q = combine<F_ALL>(q, pt[M >= 32 ? 0 : t + i]);
+    }
+    if (j == 0) {
+        double* dst = a.partial + 4 * row;
+        dst[0] = q.mx; dst[1] = q.a; dst[2] = q.b; dst[3] = q.c;
+    }
 }
 
 // ---- plain column transform kernel -------------------------------------------------------------------

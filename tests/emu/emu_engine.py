@@ -60,3 +60,21 @@ class EmuEngine(Engine):
 
     def _mem_np_dtype(self, buf):
         return buf.dtype
+
+
+from spatial_light_modulator_module_b200.slab import SlabEngine  # noqa: E402
+
+
+class EmuSlabEngine(EmuEngine, SlabEngine):
+    """Row-slab engine over the host emulation; torch CPU tensors (gloo) view the numpy buffers."""
+
+    def _as_torch(self, buf):
+        import torch
+        t = torch.from_numpy(np.asarray(buf))
+        return torch.view_as_real(t) if t.is_complex() else t
+
+    def _sync(self):
+        pass
+
+    def _copy(self, src, dst):
+        np.copyto(np.asarray(dst), np.asarray(src))

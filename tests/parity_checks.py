@@ -294,9 +294,9 @@ def check_gif_snapshots(make_engine_unused, precision, tmp_path, gs_fn, gd_fn, n
     """args.gif: the chunked run writes the reference's frames and returns the uninterrupted result."""
     import PIL.Image as im
     t = synthetic.shapes_target((128, 128))
-    for fn, kw in ((gs_fn, {}), (gd_fn, dict(learning_rate=0.01))):
+    for which, (fn, kw) in enumerate(((gs_fn, {}), (gd_fn, dict(learning_rate=0.01)))):
         for gtype in ("i", "h"):
-            d = tmp_path / f"{fn.__name__}_{gtype}"
+            d = tmp_path / f"alg{which}_{gtype}"
             d.mkdir()
             a = ns(max_loops=7, gif=True, gif_skip=3, gif_type=gtype, gif_source_dir=str(d), precision=precision, **kw)
             holo, exp, errs = fn(t, a)

@@ -317,3 +317,52 @@ def test_move_traps_update_hologram(golden):
     assert pc.circ(h, g["trap_phase"]).max() < 1e-11
     with pytest.raises(IndexError):
         move_traps.update_hologram(img, [(500, 1)], 0)
+
+
+# ---- one large plane, slab-decomposed (BASELINE config 5) ------------------------------------------------
+@pytest.mark.parametrize("n,precision", [(8192, "fp32"), (16384, "fp32"), (8192, "fp64")])
+def test_long_line_transforms(n, precision):
+    from scipy.fft import fft, ifft
+    from spatial_light_modulator_module_b200.slab import SlabEngine
+    rows = 64
+    eng = SlabEngine(n, n // rows, 0, precision)
+    rng = np.random.default_rng(2)
+    x = (rng.standard_normal((rows, n)) + 1j * rng.standard_normal((rows, n))).astype(eng.complex_dtype)
+    tol = 3e-6 if precision == "fp32" else 5e-14
+    xd, out = eng._mem_upload(x), eng._mem_empty((rows, n), eng.complex_dtype)
+    for inverse in (False, True):
+        eng._rows_fft(xd, out, inverse)
+        ref = (ifft(x.astype(np.complex128), axis=1) * n) if inverse else fft(x.astype(np.complex128), axis=1)
+        assert np.abs(eng.to_host(out) - ref).max() / np.abs(ref).max() < tol
+    eng.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_slab_gs_single_rank_equals_plane_engine(precision):
+    from spatial_light_modulator_module_b200.slab import SlabEngine
+    n = 1024
+    t = synthetic.shapes_target((n, n))
+    ref = make_engine((n, n), precision, 1)
+    r = ref.gs(t, 6)
+    eng = SlabEngine(n, 1, 0, precision)
+    h, e, errs = eng.gs(t, 6)
+    # same arithmetic per element; only the order of the error sums differs
+    np.testing.assert_array_equal(h, ref.to_host(r.hologram)[0])
+    np.testing.assert_allclose(e, ref.to_host(r.expected)[0], rtol=1e-12)
+    assert np.max(np.abs(np.array(errs) - r.errors[0]) / r.errors[0]) < (1e-5 if precision == "fp32" else 1e-12)
+    eng.close(); ref.close()
+
+
+def test_slab_gs_8192_invariants():
+    """A plane only the slab path can hold as lines (8192 points): GS on a trap target converges to a fixed
+    point, |hologram| <= pi, max(expected) == max(target), error == error_f(expected, target)."""
+    from spatial_light_modulator_module_b200 import algorithms
+    from spatial_light_modulator_module_b200.slab import SlabEngine
+    n = 8192
+    t = synthetic.traps_target((n, n), [(1000, 2000), (6000, 5000), (4096, 700)])
+    eng = SlabEngine(n, 1, 0, "fp32")
+    h, e, errs = eng.gs(t, 6)
+    assert np.all(np.abs(h) <= np.pi) and abs(e.max() - 255.0) < 1e-9
+    assert abs(algorithms.error_f(e, t, t.size) - errs[-1]) < 1e-5 * errs[-1]
+    assert abs(errs[-1] - errs[-2]) < 1e-4 * errs[-1]
+    eng.close()

@@ -1,0 +1,105 @@
+"""Slab-decomposed transform of one large plane (BASELINE config 5) on CPU: the row-slab kernels run in
+the host emulation, the all-to-all transposes and the 4-scalar all-reduce over gloo with 2 ranks."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+from scipy.fft import fft, ifft
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _slab_factory(n, world, rank, precision, *a):
+    from tests.emu.emu_engine import EmuSlabEngine
+    return EmuSlabEngine(n, world, rank, precision)
+
+
+@pytest.mark.parametrize("n,precision", [(8192, "fp32"), (16384, "fp32"), (8192, "fp64"), (1024, "fp32")])
+def test_long_line_transforms(n, precision):
+    """Lines of 8192 / 16384 points (32 points per thread, fft_tile.cuh) against scipy, both directions,
+    plain and exchange-layout addressing."""
+    from tests.emu.emu_engine import EmuSlabEngine
+    rows = 32
+    eng = EmuSlabEngine(n, n // rows, 0, precision)
+    rng = np.random.default_rng(2)
+    x = (rng.standard_normal((rows, n)) + 1j * rng.standard_normal((rows, n))).astype(eng.complex_dtype)
+    tol = 3e-6 if precision == "fp32" else 5e-14
+    xd, out = eng._mem_upload(x), eng._mem_empty((rows, n), eng.complex_dtype)
+    for inverse in (False, True):
+        eng._rows_fft(xd, out, inverse)
+        ref = (ifft(x.astype(np.complex128), axis=1) * n) if inverse else fft(x.astype(np.complex128), axis=1)
+        assert np.abs(eng.to_host(out) - ref).max() / np.abs(ref).max() < tol
+    # exchange layout in and out: block q holds [rows][rows] = elements q*rows .. of every line
+    xb = np.ascontiguousarray(x.reshape(rows, n // rows, rows).transpose(1, 0, 2))
+    ob = eng._mem_empty(xb.shape, eng.complex_dtype)
+    eng._rows_fft(eng._mem_upload(xb), ob, False, block_in=rows, block_out=rows)
+    got = eng.to_host(ob).transpose(1, 0, 2).reshape(rows, n)
+    ref = fft(x.astype(np.complex128), axis=1)
+    assert np.abs(got - ref).max() / np.abs(ref).max() < tol
+    eng.close()
+
+
+def test_transpose_blocks_roundtrip():
+    from tests.emu.emu_engine import EmuSlabEngine
+    n, world = 256, 4
+    eng = EmuSlabEngine(n, world, 0, "fp32")
+    h = n // world
+    for dtype, eb in ((np.complex64, 8), (np.uint8, 1), (np.complex128, 16)):
+        a = (np.arange(h * n) % 251).reshape(h, n).astype(dtype)
+        send, back = eng._mem_empty((world, h, h), dtype), eng._mem_empty((h, n), dtype)
+        eng._transpose(eng._mem_upload(a), send, eb, False)
+        s = eng.to_host(send)
+        for q in range(world):
+            np.testing.assert_array_equal(s[q], a[:, q * h:(q + 1) * h].T)
+        eng._transpose(send, back, eb, True)
+        np.testing.assert_array_equal(eng.to_host(back), a)
+    eng.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_slab_gs_single_rank_equals_plane_engine(precision):
+    """world = 1: the slab path is the same arithmetic as the ordinary engine, bit for bit."""
+    from spatial_light_modulator_module_b200 import synthetic
+    from tests.emu.emu_engine import EmuEngine, EmuSlabEngine
+    n = 256
+    t = synthetic.shapes_target((n, n))
+    ref = EmuEngine((n, n), precision, 1)
+    r = ref.gs(t, 4)
+    eng = EmuSlabEngine(n, 1, 0, precision)
+    h, e, errs = eng.gs(t, 4)
+    np.testing.assert_array_equal(h, ref.to_host(r.hologram)[0])
+    np.testing.assert_array_equal(e, ref.to_host(r.expected)[0])
+    assert np.max(np.abs(np.array(errs) - r.errors[0]) / r.errors[0]) < 1e-12
+    eng.close(); ref.close()
+
+
+def _worker(rank, world, port, n, loops, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from spatial_light_modulator_module_b200 import slab, synthetic
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        t = synthetic.noise_target((n, n), seed=6)
+        h, e, errs = slab.gerchberg_saxton_slab(t, loops, precision="fp32", engine_factory=_slab_factory)
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), h=h, e=e, errs=np.array(errs))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_slab_gs_matches_single_rank(tmp_path):
+    from spatial_light_modulator_module_b200 import synthetic
+    from tests.emu.emu_engine import EmuSlabEngine
+    n, loops = 256, 4
+    mp.spawn(_worker, args=(2, 29800 + os.getpid() % 150, n, loops, str(tmp_path)), nprocs=2, join=True)
+    t = synthetic.noise_target((n, n), seed=6)
+    eng = EmuSlabEngine(n, 1, 0, "fp32")
+    h, e, errs = eng.gs(t, loops)
+    r0, r1 = np.load(tmp_path / "r0.npz"), np.load(tmp_path / "r1.npz")
+    np.testing.assert_array_equal(np.concatenate([r0["h"], r1["h"]]), h)      # fields are bit-identical
+    np.testing.assert_allclose(np.concatenate([r0["e"], r1["e"]]), e, rtol=1e-12)
+    np.testing.assert_array_equal(r0["errs"], r1["errs"])                     # every rank closes the loop identically
+    assert np.max(np.abs(r0["errs"] - np.array(errs)) / np.array(errs)) < 1e-12
+    eng.close()
