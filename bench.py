@@ -52,6 +52,8 @@ def parse():
     p.add_argument("--cpu-loops", type=int, default=40, help="iterations of the CPU baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-movie", action="store_true")
+    p.add_argument("--workload", default="batch", choices=["batch", "slab"],
+                   help="batch: configs[1] (default).  slab: ONE size^2 plane row-split over the ranks (configs[4]), GS")
     return p.parse_args()
 
 
@@ -392,9 +394,66 @@ def run_b200(a):
         dist.destroy_process_group()
 
 
+def run_slab(a):
+    """BASELINE configs[4]: one size^2 GS hologram, slab-decomposed over the ranks (strong scaling)."""
+    import torch
+    import torch.distributed as dist
+    rank, local_rank, world = env_rank()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from spatial_light_modulator_module_b200.slab import SlabEngine
+    n, loops = a.size, a.loops
+    rows = n // world
+    eng = SlabEngine(n, world, rank, a.precision)
+    slab = eng._mem_upload((np.random.default_rng(100 + rank).random((rows, n)) * 255).astype(np.uint8))   # resident in HBM
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(max(a.warmup, 1)):
+        eng.gs(slab, 2, want_expected=False, on_device=True)
+    barrier()
+    n0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        holo, _, errs = eng.gs(slab, loops, want_expected=False, on_device=True)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tmax = torch.tensor([ms], device=torch.device("cuda", local_rank), dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    launches = eng.launch_count() - n0
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        c = 8 if a.precision == "fp32" else 16
+        it_bytes = (8 * c + 4) * n * n
+        per_it = ms * 1e-3 / (a.steps * loops)
+        print(json.dumps({
+            "metric": f"GS iterations/sec on one {n}^2 plane (slab-decomposed)", "value": 1.0 / per_it, "unit": "iterations/s",
+            "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 1), "ms_per_step": ms / a.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32" if a.precision == "fp32" else "f64", "data": "synthetic",
+            "config": {"workload": f"gerchberg_saxton, one {n}x{n} uint8 noise target, {loops} iterations incl. setup and the final "
+                                   f"hologram read-back, rows split over {world} GPU(s), 2 all-to-alls + 1 all-reduce per iteration "
+                                   f"(BASELINE.json configs[4])"},
+            "gpu_launches": int(launches), "final_error": float(errs[-1]),
+            "iteration_roofline": {"alg_bytes_per_iteration": it_bytes, "achieved": it_bytes / per_it / 1e9 / world, "peak": peak,
+                                   "unit": "GB/s per GPU", "frac": it_bytes / per_it / 1e9 / world / peak, "peak_source": peak_src},
+        }))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "slab":
+        run_slab(args)
     else:
         run_b200(args)

@@ -88,7 +88,7 @@ class Engine:
         torch = self._torch
         host = torch.from_numpy(np.ascontiguousarray(array))
         with torch.cuda.stream(self._stream):
-            if host.numel() * host.element_size() >= (1 << 20):       # large planes: stage through pinned memory
+            if (1 << 20) <= host.numel() * host.element_size() <= (1 << 30):   # large planes: stage through pinned memory
                 pinned = torch.empty(host.shape, dtype=host.dtype, pin_memory=True)
                 pinned.copy_(host)
                 dev = pinned.to(self._dev, non_blocking=True)
@@ -104,6 +104,10 @@ class Engine:
 
     def _mem_download(self, buf) -> np.ndarray:
         torch = self._torch
+        nbytes = buf.numel() * buf.element_size()
+        if nbytes < (1 << 20) or nbytes > (1 << 30):       # tiny: not worth a pinned allocation; huge: pinning costs more than it saves
+            self._stream.synchronize()
+            return buf.cpu().numpy()
         with torch.cuda.stream(self._stream):
             host = torch.empty(buf.shape, dtype=buf.dtype, pin_memory=True)
             host.copy_(buf, non_blocking=True)

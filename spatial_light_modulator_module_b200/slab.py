@@ -93,11 +93,17 @@ class SlabEngine(Engine):
 
     def _exchange(self, slab, send, recv, elem_bytes):
         """row slab -> exchange layout of the columns this rank owns (in ``recv``)."""
+        if self.world == 1:
+            self._transpose(slab, recv, elem_bytes, False)
+            return
         self._transpose(slab, send, elem_bytes, False)
         self._all_to_all(send, recv)
 
     def _exchange_back(self, lines, recv, slab, elem_bytes):
         """exchange layout (after a pass over the owned columns) -> row slab."""
+        if self.world == 1:
+            self._transpose(lines, slab, elem_bytes, True)
+            return
         self._all_to_all(lines, recv)
         self._transpose(recv, slab, elem_bytes, True)
 
@@ -113,18 +119,24 @@ class SlabEngine(Engine):
         return float(mx), sums
 
     # ---- Gerchberg-Saxton on the distributed plane --------------------------------------------------------------
-    def gs(self, target_slab, max_loops: int, tolerance: float = 0.0, want_expected: bool = True):
-        """``target_slab``: this rank's uint8 rows [rows, N] of the target.  Returns
-        ``(hologram_slab float64 [rows, N], expected_slab or None, error_evolution list)``; the error
-        curve is identical on every rank."""
+    def gs(self, target_slab, max_loops: int, tolerance: float = 0.0, want_expected: bool = True, on_device: bool = False):
+        """``target_slab``: this rank's uint8 rows [rows, N] of the target (host array or device buffer).
+        Returns ``(hologram_slab float64 [rows, N], expected_slab or None, error_evolution list)``; the error
+        curve is identical on every rank.  ``on_device`` leaves hologram / expected in device memory."""
         if max_loops < 1:
             raise UnboundLocalError("cannot access local variable 'expected_outcome' where it is not associated with a value")
-        t = np.ascontiguousarray(target_slab)
-        if t.dtype != np.uint8 or t.shape != self.shape:
-            raise ValueError(f"target slab must be uint8 {self.shape}")
+        if self._mem_is_device(target_slab):
+            T, t = target_slab, None
+            if tuple(T.shape) != self.shape or self._mem_np_dtype(T) != np.uint8:
+                raise ValueError(f"target slab must be uint8 {self.shape}")
+            local_max = float(self.to_host(T.max() if hasattr(T, "is_cuda") else np.asarray(T).max()))
+        else:
+            t = np.ascontiguousarray(target_slab)
+            if t.dtype != np.uint8 or t.shape != self.shape:
+                raise ValueError(f"target slab must be uint8 {self.shape}")
+            T, local_max = self._mem_upload(t), float(t.max())
         h, n, cs = self.rows, self.n, np.dtype(self.complex_dtype).itemsize
-        norm = float(self._all_reduce(np.array([float(t.max())]), "max")[0])
-        T = self._mem_upload(t)
+        norm = float(self._all_reduce(np.array([local_max]), "max")[0])
         Tx_send, Tx = self._mem_empty((self.world, h, h), np.uint8), self._mem_empty((self.world, h, h), np.uint8)
         self._exchange(T, Tx_send, Tx, 1)                                    # target columns, once
         X = self._mem_empty(self.shape, self.complex_dtype)                  # row slab
@@ -139,7 +151,7 @@ class SlabEngine(Engine):
         else:
             helper = type(self)(self.n, self.world, self.rank, "fp32", self._device_index, None, self.group)
             A0 = helper._mem_empty(self.shape, np.complex64)
-            helper._setup_field(helper._mem_upload(t), A0, helper._mem_empty((self.world, h, h), np.complex64),
+            helper._setup_field(T, A0, helper._mem_empty((self.world, h, h), np.complex64),
                                 helper._mem_empty((self.world, h, h), np.complex64))
             helper._sync()
             helper.close()
@@ -179,8 +191,12 @@ class SlabEngine(Engine):
             exp_slab = self._mem_empty(self.shape, np.float64)
             self._all_to_all(inten, recv_i)
             self._transpose(recv_i, exp_slab, 8, True)
-            expected = self.to_host(exp_slab) * s_prev                        # expected_outcome *= norm / max, :37
-        return self.to_host(holo), expected, errors
+            if on_device:
+                exp_slab *= s_prev                                            # expected_outcome *= norm / max, :37
+                expected = exp_slab
+            else:
+                expected = self.to_host(exp_slab) * s_prev
+        return (holo if on_device else self.to_host(holo)), expected, errors
 
     def _setup_field(self, T, X, S, Rv):
         """A = ifft2(amplitude) of the distributed target into the row slab X (this engine's precision)."""
