@@ -95,6 +95,12 @@ int slm_fourier_guess(slm_ctx* ctx, int batch, const uint8_t* target_u8, const v
  * x_out: device complex<R>[n]. */
 int slm_random_phasor(slm_ctx* ctx, const double* u, void* x_out, long long n, double divide_by);
 
+/* n successive random.random() values (algorithms.py:121,129,139,147) on the device: MT19937 continued from
+ * `state` (host uint32[624], random.getstate()[1][:624]) at read position `pos` (even; 624 right after
+ * random.seed).  u: device double[n].  state_out: host uint32[625] = final state words + final position,
+ * so the caller can leave the module-level generator where the reference's loop would.  Synchronises. */
+int slm_mt19937_uniform(slm_ctx* ctx, const uint32_t* state, int pos, double* u, long long n, uint32_t* state_out);
+
 /* inc_amp * exp(1j*phase): B of algorithms.py:30 from a hologram angle(A), to continue a GS run (used for the
  * per-iteration GIF snapshots, algorithms.py:40-41).  phase: device double[n]; inc_amp: device real<R>[plane] or NULL. */
 int slm_phase_phasor(slm_ctx* ctx, const double* phase, const void* inc_amp, void* x_out, long long n, long long plane);

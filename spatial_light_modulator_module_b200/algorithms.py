@@ -109,10 +109,10 @@ def make_initial_guess(initial_guess_type, incomming_amplitude, demanded_output,
     MT19937 stream as the reference's per-pixel ``random.random()`` calls; "fourier" runs on the
     device."""
     target = np.asarray(demanded_output)
-    if _device:                       # called from gradient_descent: exp(2*pi*i*u) is evaluated on the device
-        stream = hl.uniform_stream_guess(initial_guess_type, target.shape, seed)
-        if stream is not None:
-            return _engine_hint.random_phasor_guess(stream[0], stream[1])
+    if _device and initial_guess_type in ("random", "zeros"):
+        # called from gradient_descent: the MT19937 stream and exp(2*pi*i*u) are both produced on the device
+        u = _engine_hint.python_random_uniform(seed, target.shape)
+        return _engine_hint.random_phasor_guess(u, 100.0 if initial_guess_type == "zeros" else 1.0)
     guess = hl.host_initial_guess(initial_guess_type, target.shape, seed)
     if guess is not None:
         return guess

@@ -119,6 +119,58 @@ SLM_GLOBAL void random_phasor_kernel(const double* u, cpx<R>* x, long long n, do
     }
 }
 
+// Python's random.random() stream on the device (make_initial_guess, algorithms.py:117-150): MT19937 continued
+// from a 624-word state.  One CTA; a block of 624 words is regenerated in three data-parallel steps (word k
+// depends on old words k, k+1 and on word k+397, which is old for k < 227 and new -- from the previous
+// step -- otherwise), tempered, and paired into 53-bit doubles (a>>5, b>>6) exactly as genrand_res53 does.
+// `pos` (even) is the read position inside the incoming block; state_out = final block + final position.
+SLM_GLOBAL void mt19937_uniform_kernel(const unsigned* state_in, int pos, double* u, long long n, unsigned* state_out) {
+    SLM_STATIC_SMEM unsigned mt[2][624];
+    SLM_STATIC_SMEM unsigned tw[624];
+    const int t = threadIdx.x;                       // 256 threads
+    int cur = 0;
+    for (int i = t; i < 624; i += 256) mt[0][i] = state_in[i];
+    sync_cta();
+    long long produced = 0;                          // doubles written so far
+    while (produced < n) {
+        if (pos >= 624) {                            // regenerate: mt[cur] -> mt[cur^1]
+            const unsigned* o = mt[cur];
+            unsigned* w = mt[cur ^ 1];
+            auto twist = [](unsigned a, unsigned b, unsigned c) {
+                const unsigned y = (a & 0x80000000u) | (b & 0x7fffffffu);
+                return c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            };
+            if (t < 227) w[t] = twist(o[t], o[t + 1], o[t + 397]);
+            sync_cta();
+            if (t < 227) w[227 + t] = twist(o[227 + t], o[228 + t], w[t]);
+            sync_cta();
+            if (t < 169) w[454 + t] = twist(o[454 + t], o[455 + t], w[227 + t]);
+            if (t == 169) w[623] = twist(o[623], w[0], w[396]);
+            sync_cta();
+            cur ^= 1;
+            pos = 0;
+        }
+        for (int i = t; i < 624; i += 256) {
+            unsigned y = mt[cur][i];
+            y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+            tw[i] = y;
+        }
+        sync_cta();
+        const int avail = (624 - pos) / 2;           // doubles this block can give
+        const long long want = n - produced;
+        const int take = want < avail ? (int)want : avail;
+        for (int i = t; i < take; i += 256) {
+            const unsigned a = tw[pos + 2 * i] >> 5, b = tw[pos + 2 * i + 1] >> 6;
+            u[produced + i] = ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
+        }
+        produced += take;
+        pos += 2 * take;
+        sync_cta();
+    }
+    for (int i = t; i < 624; i += 256) state_out[i] = mt[cur][i];
+    if (t == 0) state_out[624] = (unsigned)pos;
+}
+
 // inc * exp(1j*phase): restart a GS run from a hologram (B of algorithms.py:30 with angle(A) = phase)
 template <typename R>
 SLM_GLOBAL void phase_phasor_kernel(const double* phase, const R* inc, cpx<R>* x, long long n, long long plane) {

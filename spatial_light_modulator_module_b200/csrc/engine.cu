@@ -508,6 +508,24 @@ extern "C" int slm_random_phasor(slm_ctx* c, const double* u, void* x_out, long 
     return 0;
 }
 
+extern "C" int slm_mt19937_uniform(slm_ctx* c, const uint32_t* state, int pos, double* u, long long n, uint32_t* state_out) {
+    if (!c) return fail(SLM_ERR_ARG, "slm_mt19937_uniform: null context");
+    SLM_CUDA(cudaSetDevice(c->device));
+    if (!state || !u || !state_out || n < 1 || pos < 0 || pos > 624 || (pos & 1)) return fail(SLM_ERR_ARG, "slm_mt19937_uniform: bad argument (pos must be even)");
+    unsigned* dev = nullptr;                         // [624 in][625 out]
+    SLM_CUDA(cudaMalloc((void**)&dev, (624 + 625) * sizeof(unsigned)));
+    cudaError_t e = cudaMemcpyAsync(dev, state, 624 * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        { LaunchTimer t_(c, K_ELEMENTWISE); SLM_LAUNCH(mt19937_uniform_kernel, dim3(1), dim3(256), 0, c->stream, dev, pos, u, n, dev + 624); }
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(state_out, dev + 624, 625 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(dev);
+    if (e != cudaSuccess) return fail(SLM_ERR_CUDA, std::string("slm_mt19937_uniform: ") + cudaGetErrorString(e));
+    return 0;
+}
+
 extern "C" int slm_phase_phasor(slm_ctx* c, const double* phase, const void* inc_amp, void* x_out, long long n, long long plane) {
     if (!c) return fail(SLM_ERR_ARG, "slm_phase_phasor: null context");
     SLM_CUDA(cudaSetDevice(c->device));

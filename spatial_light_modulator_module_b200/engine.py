@@ -235,6 +235,25 @@ class Engine:
         self._check(self._lib.slm_random_phasor(self._ctx, self._mem_ptr(ud), self._mem_ptr(x), _numel(ud), float(divide_by)))
         return x
 
+    def python_random_uniform(self, seed, shape):
+        """``prod(shape)`` successive ``random.random()`` draws after ``random.seed(seed)`` as a device
+        float64 array (MT19937 continued on the device from CPython's own state); the module-level
+        generator is left where the reference's per-pixel loop leaves it (algorithms.py:117-150)."""
+        import random
+        random.seed(seed)
+        version, words, gauss = random.getstate()
+        state = np.array(words[:624], dtype=np.uint32)
+        pos = int(words[624])
+        n = int(np.prod(shape))
+        if pos & 1:                                    # not reachable right after seed(); keep the host path for it
+            return self._mem_upload(hl.python_random_stream(seed, n).reshape(shape))
+        u = self._mem_empty(tuple(shape), np.float64)
+        out = np.empty(625, dtype=np.uint32)
+        self._check(self._lib.slm_mt19937_uniform(self._ctx, state.ctypes.data_as(C.c_void_p), pos, self._mem_ptr(u), n,
+                                                  out.ctypes.data_as(C.c_void_p)))
+        random.setstate((version, tuple(int(w) for w in out[:624]) + (int(out[624]),), gauss))
+        return u
+
     def phase_phasor(self, phase, inc_amp=None):
         """inc * exp(1j*phase) as complex<R> on the device (continue a GS run from a hologram)."""
         pd = self._as_device(phase, np.float64, "phase")

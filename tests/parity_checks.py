@@ -325,3 +325,18 @@ def check_single_trap_and_frames(make_engine, golden):
     with pytest.raises(IndexError):
         eng.trap_frames(np.array([[0, 800, 3]]), 1, (768, 1024))
     eng.close()
+
+
+def check_device_mt19937(make_engine):
+    """The device continuation of CPython's MT19937 equals random.random() draw for draw, and leaves the
+    module-level generator in the same state."""
+    import random
+    eng = make_engine((64, 64), "fp64", 1)
+    for seed, shape in ((42, (64, 64)), (7, (3, 1000)), (2**40 + 12345, (1, 311)), (42.0, (2, 312)), (0, (1, 1))):
+        u = eng.to_host(eng.python_random_uniform(seed, shape))
+        after = random.random()
+        random.seed(seed)
+        ref = np.array([random.random() for _ in range(int(np.prod(shape)))]).reshape(shape)
+        np.testing.assert_array_equal(u, ref)
+        assert after == random.random()
+    eng.close()

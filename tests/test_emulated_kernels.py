@@ -77,3 +77,7 @@ def test_random_phasor_guess(golden, precision):
 
 def test_single_trap_and_device_frames(golden):
     pc.check_single_trap_and_frames(make_engine, golden)
+
+
+def test_device_mt19937_stream():
+    pc.check_device_mt19937(make_engine)

@@ -366,3 +366,7 @@ def test_slab_gs_8192_invariants():
     assert abs(algorithms.error_f(e, t, t.size) - errs[-1]) < 1e-5 * errs[-1]
     assert abs(errs[-1] - errs[-2]) < 1e-4 * errs[-1]
     eng.close()
+
+
+def test_device_mt19937_stream():
+    pc.check_device_mt19937(make_engine)
