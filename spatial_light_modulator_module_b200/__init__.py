@@ -12,5 +12,5 @@ There is no CPU fallback.
 """
 __version__ = "0.1.0"
 
-__all__ = ["algorithms", "constants", "display_holograms", "engine", "generate_hologram",
-           "generate_hologram_sequence", "host_logic", "move_traps", "synthetic", "wavefront_correction"]
+__all__ = ["algorithms", "compare_error_evolution_algorithms", "constants", "display_holograms", "engine", "generate_hologram",
+           "generate_hologram_sequence", "host_logic", "move_traps", "slab", "synthetic", "wavefront_correction"]

@@ -370,3 +370,20 @@ def test_slab_gs_8192_invariants():
 
 def test_device_mt19937_stream():
     pc.check_device_mt19937(make_engine)
+
+
+def test_batched_algorithm_comparison_matches_single_calls():
+    """Config-4 shape at reduced size: batched GD + GS curves equal the one-target-at-a-time drop-in calls."""
+    from spatial_light_modulator_module_b200 import algorithms, compare_error_evolution_algorithms as cmp
+    shape = (256, 256)
+    targets = np.stack([synthetic.noise_target(shape, seed=1), synthetic.shapes_target(shape), synthetic.traps_target(shape)])
+    a = ns(max_loops=8, precision="fp64")
+    cmp.fill_unnecessary_args(a)
+    gd, gs = cmp.error_evolution_curves(targets, a, batch=2)
+    assert len(gd) == len(gs) == 3
+    for i, t in enumerate(targets):
+        b = ns(max_loops=8, precision="fp64")
+        _, _, e_gd = quiet(algorithms.gradient_descent, t, b)
+        _, _, e_gs = quiet(algorithms.gerchberg_saxton, t, b)
+        np.testing.assert_allclose(gd[i], np.array(e_gd), rtol=1e-12)
+        np.testing.assert_allclose(gs[i], np.array(e_gs), rtol=1e-12)
