@@ -108,7 +108,7 @@ class ClockSampler:
     thread (an `nvidia-smi -lms` child process perturbed the timed region on this pool: bimodal step times)."""
     THROTTLE = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
 
-    def __init__(self, index, period_s=0.05):
+    def __init__(self, index, period_s=0.2):
         self.index, self.period, self.samples, self._stop, self.thread, self.err = index, period_s, [], False, None, None
 
     def start(self):

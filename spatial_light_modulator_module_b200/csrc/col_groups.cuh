@@ -45,7 +45,11 @@ template <typename R, int H> struct ColGroupGeom {
     static constexpr int COPIERS = 96;
     static constexpr int THREADS = COMPUTE + PRODUCERS;
     static constexpr int ROWB = TC * (int)sizeof(cpx<R>);         // bytes of one tile row
-    static constexpr int LPG = lines_per_group(M);
+    // PAIRED: a warp covers 16 rows x 2 adjacent columns (lanes 0-15 / 16-31).  With 64-byte swizzled tile rows
+    // that makes the tile reads/writes and the grey-level reads bank-conflict free (one column alone is 2-way:
+    // 16-byte swizzle chunks cannot separate the two 8-byte halves); the sync group is then the column pair.
+    static constexpr bool PAIRED = (M % 16 == 0) && (TC % 2 == 0);
+    static constexpr int LPG = PAIRED ? 2 : lines_per_group(M);
     static constexpr int GROUPS = TC / LPG;
     static constexpr int GROUP_THREADS = LPG * M;
     static constexpr bool OK = (ROWB == 64 || ROWB == 32) && COMPUTE % 32 == 0 && TC % LPG == 0 && GROUPS <= 14 &&
@@ -61,7 +65,10 @@ template <typename R, int H> struct ColGroupGeom {
     static constexpr size_t OFF_CNT = OFF_RED + 2 * 32 * sizeof(Partial);
     static constexpr size_t OFF_TOT = OFF_CNT + 16;                // Partial tile_total[2]
     static constexpr size_t OFF_BAR = OFF_TOT + 2 * sizeof(Partial);
-    static constexpr size_t SMEM = OFF_BAR + 6 * 16;
+    static constexpr size_t OFF_TW = OFF_BAR + 6 * 32;             // column twiddle table, when it fits
+    static constexpr size_t TW_BYTES = (size_t)H * sizeof(cpx<R>);
+    static constexpr bool TW_SHARED = OFF_TW + TW_BYTES <= 232448; // 227 KB of shared memory per CTA
+    static constexpr size_t SMEM = OFF_TW + (TW_SHARED ? TW_BYTES : 0);
     using Sync = GroupSync<GROUP_THREADS>;
 };
 
@@ -129,6 +136,11 @@ col_group_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const S
     if (use_t8) {
         const R* lut = static_cast<const R*>(a.lut);
         for (int i = t; i < 256; i += G::THREADS) lut_s[i] = ld_ro(lut + i);
+    }
+    if (G::TW_SHARED) {                                     // twiddles next to the data: no global round trip inside the transforms
+        cpx<R>* tws = reinterpret_cast<cpx<R>*>(raw + G::OFF_TW);
+        const cpx<R>* twg = static_cast<const cpx<R>*>(a.tw);
+        for (int i = t; i < H; i += G::THREADS) tws[i] = ld_const(twg + i);
     }
     sync_cta();
     auto rests = [&](int b) { return MODE != CGM_COMPLEX && ld_cg(&a.stats[b].done) != 0; };
@@ -226,24 +238,46 @@ col_group_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const S
     }
 
     // ================= compute warps =================
-    const int c = t / M, j = t % M, lane = t % 32, warp = t / 32;
+    const int lane = t % 32, warp = t / 32;
+    int c, j;
+    if (G::PAIRED) {                                   // pair group pg: M/16 warps, each 16 rows x 2 columns
+        const int pg = t / (2 * M), w = (t % (2 * M)) / 32;
+        c = 2 * pg + (lane >> 4);
+        j = 16 * w + (lane & 15);
+    } else {
+        c = t / M; j = t % M;
+    }
     const typename G::Sync sync{1 + c / G::LPG};
     cpx<R>* const line = reinterpret_cast<cpx<R>*>(raw + G::OFF_XCH) + (size_t)c * P::NP;
-    const cpx<R>* tw = static_cast<const cpx<R>*>(a.tw);
+    const cpx<R>* tw = G::TW_SHARED ? reinterpret_cast<const cpx<R>*>(raw + G::OFF_TW) : static_cast<const cpx<R>*>(a.tw);
+    using Sy = typename G::Sync;
     cpx<R> v[E];
     unsigned k = 0;
-    // the "plane rests" flag of a tile is requested one tile ahead, so its L2 round trip is never waited for
-    bool rest_next = blockIdx.x < total ? rests((int)(blockIdx.x / tiles)) : true;
+    // Per-plane scalars (rest flag, previous scale, max, norm) of a tile are requested ONE TILE AHEAD and
+    // only looked at in the next trip of the loop, so their L2 round trips overlap a whole tile of work.
+    struct PlaneInfo { int done; double scale, imax, norm; };
+    auto fetch_info = [&](long long gg) {
+        PlaneInfo pi; pi.done = 1; pi.scale = 0; pi.imax = 0; pi.norm = 0;
+        if (gg < total) {
+            const int bb = (int)(gg / tiles);
+            pi.done = 0;
+            if (MODE != CGM_COMPLEX) {
+                const PlaneStats* ps = a.stats + bb;
+                pi.done = ld_cg(&ps->done);
+                if (MODE == CGM_GS || IS_GD) { pi.scale = ld_cg(&ps->scale); pi.imax = ld_cg(&ps->imax); pi.norm = ld_ro(a.norm + bb); }
+            }
+        }
+        return pi;
+    };
+    PlaneInfo nxt = fetch_info(blockIdx.x);
     for (long long g = blockIdx.x; g < total; g += gridDim.x) {
         const int b = (int)(g / tiles), tile = (int)(g % tiles);
-        const bool rest_cur = rest_next;
-        rest_next = (g + gridDim.x < total) ? rests((int)((g + gridDim.x) / tiles)) : true;
-        if (rest_cur) continue;
+        const PlaneInfo info = nxt;
+        nxt = fetch_info(g + gridDim.x);
+        if (info.done) continue;
         const int s = (int)(k & 1u);
         unsigned char* const buf = s ? tile1 : tile0;
-        PlaneStats* st = a.stats ? a.stats + b : nullptr;
-        double s0 = 0, imax = 0, norm = 0;
-        if (MODE == CGM_GS || IS_GD) { s0 = ld_cg(&st->scale); imax = ld_cg(&st->imax); norm = ld_ro(a.norm + b); }
+        const double s0 = info.scale, imax = info.imax, norm = info.norm;
         SLM_STAMP(t == 0, k, 0);
         mbar_wait(full + s, (k >> 1) & 1u);
         SLM_STAMP(t == 0, k, 1);
@@ -258,8 +292,8 @@ col_group_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const S
 #pragma unroll
             for (int r = 0; r < E; ++r) { tv[r] = ld_ro(T + (size_t)r * M * a.W); aux[r] = ld_ro(Q + (size_t)r * M * a.W); }
         }
-        if (MODE == CGM_COMPLEX && ga.mode_inverse) line_fft<R, H, +1, 1>(v, line, j, tw, sync);
-        else if (MODE != CGM_GD_POST) line_fft<R, H, -1, 1>(v, line, j, tw, sync);
+        if (MODE == CGM_COMPLEX && ga.mode_inverse) line_fft<R, H, +1, 1, Sy, G::TW_SHARED>(v, line, j, tw, sync);
+        else if (MODE != CGM_GD_POST) line_fft<R, H, -1, 1, Sy, G::TW_SHARED>(v, line, j, tw, sync);
 
         SLM_STAMP(t == 0, k, 2);
         // ---- pointwise step and per-thread sums ----
@@ -324,7 +358,7 @@ col_group_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const S
         }
 
         SLM_STAMP(t == 0, k, 4);
-        if (MODE == CGM_GS || IS_GD) line_fft<R, H, +1, 1>(v, line, j, tw, sync);
+        if (MODE == CGM_GS || IS_GD) line_fft<R, H, +1, 1, Sy, G::TW_SHARED>(v, line, j, tw, sync);
         SLM_STAMP(t == 0, k, 5);
         if (HAS_OUT) {
 #pragma unroll

@@ -206,8 +206,9 @@ template <int RAD, int DIR, typename R> SLM_DEV void dft_small(cpx<R>* v) {
 
 // ---- twiddles ----------------------------------------------------------------------------
 // tw[q] = exp(-2*pi*i*q/N), q in [0,N), computed in extended precision on the host.
-template <int DIR, typename R> SLM_DEV cpx<R> tw_load(const cpx<R>* tw, int q) {
-    cpx<R> w = ld_const(tw + q);
+// TW_SHARED: the table has been copied to shared memory (plain load); otherwise read-only global path.
+template <int DIR, bool TW_SHARED, typename R> SLM_DEV cpx<R> tw_load(const cpx<R>* tw, int q) {
+    cpx<R> w = TW_SHARED ? tw[q] : ld_const(tw + q);
     if (DIR > 0) w.y = -w.y;
     return w;
 }
@@ -249,7 +250,7 @@ template <int THREADS> struct GroupSync {          // THREADS == 0: whole CTA
     SLM_DEV void operator()() const { if (THREADS == 0) sync_cta(); else sync_named(id, THREADS); }
 };
 
-template <typename R, int N, int DIR, int STRIDE, class Sync = CtaSync>
+template <typename R, int N, int DIR, int STRIDE, class Sync = CtaSync, bool TW_SHARED = false>
 SLM_DEV void line_fft(cpx<R>* v, cpx<R>* line, int j, const cpx<R>* SLM_RESTRICT tw, Sync sync = Sync()) {
     using P = FftPlan<N>;
     constexpr int E = P::E, M = P::M, MID = P::MID;
@@ -267,7 +268,7 @@ SLM_DEV void line_fft(cpx<R>* v, cpx<R>* line, int j, const cpx<R>* SLM_RESTRICT
         const int jh = j / E, jl = j % E;
         cpx<R>* const stm = line + (jh * BLK + jl) * STRIDE;
         cpx<R> w[MID];
-        twiddle_powers<MID>(w, tw_load<DIR>(tw, jl * E));      // exp(-+2 pi i jl / (E*MID)), same for every q
+        twiddle_powers<MID>(w, tw_load<DIR, TW_SHARED>(tw, jl * E));      // exp(-+2 pi i jl / (E*MID)), same for every q
         if constexpr (MID != 3) {
             constexpr int Q = E / MID;                           // butterflies per thread
 #pragma unroll
@@ -314,7 +315,7 @@ SLM_DEV void line_fft(cpx<R>* v, cpx<R>* line, int j, const cpx<R>* SLM_RESTRICT
     sync();                      // the tile may be overwritten by the next transform
     {
         cpx<R> w[E];
-        twiddle_powers<E>(w, tw_load<DIR>(tw, j));
+        twiddle_powers<E>(w, tw_load<DIR, TW_SHARED>(tw, j));
 #pragma unroll
         for (int r = 1; r < E; ++r) v[r] = cmul(v[r], w[r]);
     }
