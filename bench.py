@@ -108,7 +108,8 @@ class ClockSampler:
     thread (an `nvidia-smi -lms` child process perturbed the timed region on this pool: bimodal step times)."""
     THROTTLE = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
 
-    def __init__(self, index, period_s=0.2):
+    def __init__(self, index, period_s=None):
+        period_s = float(os.environ.get("SLM_BENCH_SAMPLER_PERIOD", "0.2")) if period_s is None else period_s
         self.index, self.period, self.samples, self._stop, self.thread, self.err = index, period_s, [], False, None, None
 
     def start(self):
@@ -241,13 +242,16 @@ def run_b200(a):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     wall0 = time.time()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
     e0.record()
-    for _ in range(a.steps):
+    for i in range(a.steps):
         q = step()
+        marks[i].record()
     e1.record()
     barrier()
     wall1 = time.time()
     ms = e0.elapsed_time(e1)
+    step_ms = [round(([e0] + marks)[i].elapsed_time(marks[i]), 3) for i in range(a.steps)]
     launches = eng.launch_count() - n0
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     if world > 1:
@@ -379,7 +383,7 @@ def run_b200(a):
 
     line = {
         "metric": "GS/GD iterations/sec at 1024^2", "value": value, "unit": "iterations/s", "n_gpus": world,
-        "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
+        "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "step_ms": step_ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32" if a.precision == "fp32" else "f64", "data": "synthetic",
         "config": {"workload": workload_name(a, shape), "algorithm": a.alg, "shape": list(shape), "batch_per_gpu": a.batch,
                    "iterations": a.loops, "l2": f"inputs larger than L2: {3 * a.batch * npx * csz / 2**20:.0f} MiB of field planes per GPU",

@@ -30,7 +30,7 @@ def nvcc() -> str:
 
 def line_lengths():
     text = open(os.path.join(CSRC, "line_list.h")).read()
-    return [int(x) for x in re.findall(r"X\((\d+)\)", text.split("#define SLM_LINE_LENGTHS(X)")[1])]
+    return [int(x) for x in re.findall(r"X\((\d+)\)", text.split("#define SLM_LINE_LENGTHS(X)")[1].split("\n")[0])]
 
 
 def _sources():
@@ -57,6 +57,8 @@ def _build(force, verbose, defines, OBJ, LIB, lengths):
     os.makedirs(OBJ, exist_ok=True)
     cc = nvcc()
     base = [cc, "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-I", CSRC] + ARCH + defines
+    if lengths:
+        base.append("-DSLM_LINE_LENGTHS(X)=" + " ".join(f"X({n})" for n in lengths))
     if verbose:
         base += ["-Xptxas", "-v"]
     jobs = [(os.path.join(CSRC, "engine.cu"), os.path.join(OBJ, "engine.o"), []),

@@ -126,6 +126,7 @@ col_group_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const S
     const int tiles = a.W / TC;
     const long long total = (long long)a.B * tiles;
     const bool use_t8 = HAS_T && a.T8 != nullptr;
+    griddep_launch();                                 // programmatic dependent launch: see griddep_wait below
     if (t == 0) {
         mbar_init(full + 0, use_t8 ? 1u + G::COPIERS : 1u); mbar_init(full + 1, use_t8 ? 1u + G::COPIERS : 1u);
         mbar_init(pubfree + 0, 1u); mbar_init(pubfree + 1, 1u);
@@ -142,6 +143,9 @@ col_group_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const S
         const cpx<R>* twg = static_cast<const cpx<R>*>(a.tw);
         for (int i = t; i < H; i += G::THREADS) tws[i] = ld_const(twg + i);
     }
+    // everything above (barriers, tables: constant inputs) overlapped the tail of the previous pass; from here
+    // on the field, the per-plane state and the partial sums of that pass are read
+    griddep_wait();
     sync_cta();
     auto rests = [&](int b) { return MODE != CGM_COMPLEX && ld_cg(&a.stats[b].done) != 0; };
 

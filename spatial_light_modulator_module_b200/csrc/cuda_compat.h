@@ -12,6 +12,7 @@
 #else
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #define SLM_HD __host__ __device__ __forceinline__
 #define SLM_DEV __device__ __forceinline__
@@ -23,8 +24,26 @@
 #define SLM_STATIC_SMEM __shared__
 #define SLM_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #define SLM_RESTRICT __restrict__
+// Programmatic dependent launch: the kernel may start while its predecessor in the stream drains; it must
+// call griddep_wait() before touching anything the predecessor wrote.
+#define SLM_LAUNCH_PDL(kernel, grid, block, smem, stream, ...) slm::launch_pdl(kernel, grid, block, smem, stream, __VA_ARGS__)
 
 namespace slm {
+// Set by the engine per run (registry.cu): short, latency-bound passes (a single SLM-size plane) gain from the
+// overlap; on large batches the early-resident dependents cost a few percent (measured), so they launch plainly.
+extern thread_local bool tl_pdl;
+template <class K, class... A> inline void launch_pdl(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A... args) {
+    if (!tl_pdl) { kernel<<<grid, block, smem, stream>>>(args...); return; }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+SLM_DEV void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+SLM_DEV void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 template <typename T> SLM_DEV T ld_ro(const T* p) { return __ldg(p); }     // immutable during the launch
 template <typename T> SLM_DEV T ld_cg(const T* p) { return __ldcg(p); }    // streamed plane data (L2 only)
 template <typename T> SLM_DEV void st_cg(T* p, T v) { __stcg(p, v); }
@@ -36,6 +55,7 @@ SLM_DEV float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, 
 SLM_DEV double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 SLM_DEV unsigned shfl_idx(unsigned v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 SLM_DEV void sync_cta() { __syncthreads(); }
+SLM_DEV void sync_warp() { __syncwarp(); }
 // named barrier `id` (1..15) over `nthreads` threads (whole warps) of the CTA
 SLM_DEV void sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 // IEEE operations that must not be contracted into FMAs (bit parity with numpy)

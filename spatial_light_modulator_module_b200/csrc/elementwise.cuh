@@ -120,54 +120,64 @@ SLM_GLOBAL void random_phasor_kernel(const double* u, cpx<R>* x, long long n, do
 }
 
 // Python's random.random() stream on the device (make_initial_guess, algorithms.py:117-150): MT19937 continued
-// from a 624-word state.  One CTA; a block of 624 words is regenerated in three data-parallel steps (word k
-// depends on old words k, k+1 and on word k+397, which is old for k < 227 and new -- from the previous
-// step -- otherwise), tempered, and paired into 53-bit doubles (a>>5, b>>6) exactly as genrand_res53 does.
+// from a 624-word state.  One CTA.  The recurrence  x[k+624] = x[k+397] ^ tw(x[k], x[k+1])  is linear over
+// GF(2), so a whole block of 624 new words is written in terms of the OLD block only -- word i is the XOR of
+// one old word and the tw() terms of i, i-227, i-454 (as many as exist) -- and needs ONE barrier per block
+// instead of one per 227-word dependency step.  Thread t owns words 2t and 2t+1 of each block, i.e. exactly
+// the pair genrand_res53 turns into a double (a>>5, b>>6), tempered in registers.
 // `pos` (even) is the read position inside the incoming block; state_out = final block + final position.
+constexpr int kMtThreads = 320;                      // 312 word pairs per block
+SLM_DEV unsigned mt_tw(unsigned a, unsigned b) {
+    const unsigned y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+SLM_DEV unsigned mt_temper(unsigned y) {
+    y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+    return y;
+}
+SLM_DEV double mt_res53(unsigned w0, unsigned w1) {
+    const unsigned a = mt_temper(w0) >> 5, b = mt_temper(w1) >> 6;
+    return ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
+}
+// word i of the next block from the old block o[0..623]
+SLM_DEV unsigned mt_next_word(const unsigned* o, int i) {
+    if (i < 227) return o[i + 397] ^ mt_tw(o[i], o[i + 1]);
+    if (i < 454) return o[i + 170] ^ mt_tw(o[i - 227], o[i - 226]) ^ mt_tw(o[i], o[i + 1]);
+    if (i < 623) return o[i - 57] ^ mt_tw(o[i - 454], o[i - 453]) ^ mt_tw(o[i - 227], o[i - 226]) ^ mt_tw(o[i], o[i + 1]);
+    const unsigned n0 = o[397] ^ mt_tw(o[0], o[1]);                                       // new word 0
+    const unsigned n396 = o[566] ^ mt_tw(o[169], o[170]) ^ mt_tw(o[396], o[397]);         // new word 396
+    return n396 ^ mt_tw(o[623], n0);
+}
 SLM_GLOBAL void mt19937_uniform_kernel(const unsigned* state_in, int pos, double* u, long long n, unsigned* state_out) {
     SLM_STATIC_SMEM unsigned mt[2][624];
-    SLM_STATIC_SMEM unsigned tw[624];
-    const int t = threadIdx.x;                       // 256 threads
-    int cur = 0;
-    for (int i = t; i < 624; i += 256) mt[0][i] = state_in[i];
+    const int t = threadIdx.x;
+    for (int i = t; i < 624; i += kMtThreads) mt[0][i] = state_in[i];
     sync_cta();
+    int cur = 0;
     long long produced = 0;                          // doubles written so far
+    if (pos < 624) {                                 // what is left of the incoming block
+        const long long avail = (624 - pos) / 2;
+        const int take = (int)(n < avail ? n : avail);
+        if (t < take) u[t] = mt_res53(mt[0][pos + 2 * t], mt[0][pos + 2 * t + 1]);
+        produced = take;
+        pos += 2 * take;
+    }
     while (produced < n) {
-        if (pos >= 624) {                            // regenerate: mt[cur] -> mt[cur^1]
-            const unsigned* o = mt[cur];
-            unsigned* w = mt[cur ^ 1];
-            auto twist = [](unsigned a, unsigned b, unsigned c) {
-                const unsigned y = (a & 0x80000000u) | (b & 0x7fffffffu);
-                return c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-            };
-            if (t < 227) w[t] = twist(o[t], o[t + 1], o[t + 397]);
-            sync_cta();
-            if (t < 227) w[227 + t] = twist(o[227 + t], o[228 + t], w[t]);
-            sync_cta();
-            if (t < 169) w[454 + t] = twist(o[454 + t], o[455 + t], w[227 + t]);
-            if (t == 169) w[623] = twist(o[623], w[0], w[396]);
-            sync_cta();
-            cur ^= 1;
-            pos = 0;
-        }
-        for (int i = t; i < 624; i += 256) {
-            unsigned y = mt[cur][i];
-            y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
-            tw[i] = y;
-        }
-        sync_cta();
-        const int avail = (624 - pos) / 2;           // doubles this block can give
+        const unsigned* o = mt[cur];
+        unsigned* w = mt[cur ^ 1];
         const long long want = n - produced;
-        const int take = want < avail ? (int)want : avail;
-        for (int i = t; i < take; i += 256) {
-            const unsigned a = tw[pos + 2 * i] >> 5, b = tw[pos + 2 * i + 1] >> 6;
-            u[produced + i] = ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
+        const int take = want < 312 ? (int)want : 312;
+        if (t < 312) {
+            const unsigned w0 = mt_next_word(o, 2 * t), w1 = mt_next_word(o, 2 * t + 1);
+            w[2 * t] = w0; w[2 * t + 1] = w1;
+            if (t < take) u[produced + t] = mt_res53(w0, w1);
         }
         produced += take;
-        pos += 2 * take;
-        sync_cta();
+        pos = 2 * take;
+        cur ^= 1;
+        sync_cta();                                  // the new block is complete; the old one may be overwritten next trip
     }
-    for (int i = t; i < 624; i += 256) state_out[i] = mt[cur][i];
+    for (int i = t; i < 624; i += kMtThreads) state_out[i] = mt[cur][i];
     if (t == 0) state_out[624] = (unsigned)pos;
 }
 

@@ -47,6 +47,7 @@ struct slm_ctx {
     double *err_curve = nullptr, *lr = nullptr, *norm = nullptr;
     void* lut = nullptr;
     float* lut32 = nullptr;
+    unsigned* mt_buf = nullptr;                           // [624 state in][625 state out] of slm_mt19937_uniform
     int loops_cap = 0, tiles = 0;
     size_t bytes = 0;
     long long launches = 0;
@@ -309,7 +310,18 @@ static int upload_lut(slm_ctx* c, const double* lut) {
     return 0;
 }
 
+// Programmatic dependent launch for the passes of this run?  (env SLM_PDL=0/1 overrides.)
+static void choose_pdl(slm_ctx* c, int batch) {
+#ifndef SLM_EMULATE
+    static const char* force = getenv("SLM_PDL");
+    tl_pdl = force ? force[0] == '1' : (long long)batch * c->H * c->W <= (1ll << 21);
+#else
+    (void)c; (void)batch;
+#endif
+}
+
 static int begin_run(slm_ctx* c, int batch, const double* norm, int max_loops) {
+    choose_pdl(c, batch);
     SLM_TRY(ensure_loops(c, max_loops));
     SLM_CUDA(cudaMemsetAsync(c->stats, 0, (size_t)batch * sizeof(PlaneStats), c->stream));
     if (norm) SLM_CUDA(cudaMemcpyAsync(c->norm, norm, (size_t)batch * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -512,17 +524,13 @@ extern "C" int slm_mt19937_uniform(slm_ctx* c, const uint32_t* state, int pos, d
     if (!c) return fail(SLM_ERR_ARG, "slm_mt19937_uniform: null context");
     SLM_CUDA(cudaSetDevice(c->device));
     if (!state || !u || !state_out || n < 1 || pos < 0 || pos > 624 || (pos & 1)) return fail(SLM_ERR_ARG, "slm_mt19937_uniform: bad argument (pos must be even)");
-    unsigned* dev = nullptr;                         // [624 in][625 out]
-    SLM_CUDA(cudaMalloc((void**)&dev, (624 + 625) * sizeof(unsigned)));
-    cudaError_t e = cudaMemcpyAsync(dev, state, 624 * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) {
-        { LaunchTimer t_(c, K_ELEMENTWISE); SLM_LAUNCH(mt19937_uniform_kernel, dim3(1), dim3(256), 0, c->stream, dev, pos, u, n, dev + 624); }
-        e = cudaGetLastError();
-    }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(state_out, dev + 624, 625 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(dev);
-    if (e != cudaSuccess) return fail(SLM_ERR_CUDA, std::string("slm_mt19937_uniform: ") + cudaGetErrorString(e));
+    if (!c->mt_buf) SLM_TRY(dev_alloc(c, (void**)&c->mt_buf, (624 + 625) * sizeof(unsigned)));
+    unsigned* dev = c->mt_buf;                       // [624 in][625 out]
+    SLM_CUDA(cudaMemcpyAsync(dev, state, 624 * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
+    { LaunchTimer t_(c, K_ELEMENTWISE); SLM_LAUNCH(mt19937_uniform_kernel, dim3(1), dim3(kMtThreads), 0, c->stream, dev, pos, u, n, dev + 624); }
+    SLM_CUDA(cudaGetLastError());
+    SLM_CUDA(cudaMemcpyAsync(state_out, dev + 624, 625 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    SLM_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

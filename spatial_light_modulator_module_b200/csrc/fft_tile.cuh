@@ -220,8 +220,11 @@ template <int RAD, typename R> SLM_DEV void twiddle_powers(cpx<R>* w, cpx<R> w1)
 }
 
 // ---- line FFT ----------------------------------------------------------------------------
+#ifndef SLM_E32_LEN
+#define SLM_E32_LEN 0          // tuning builds: one more line length transformed with 32 points per thread
+#endif
 template <int N> struct FftPlan {
-    static constexpr int E = (N >= 8192) ? 32 : (N >= 256) ? 16 : 8;      // points per thread
+    static constexpr int E = (N >= 8192 || N == SLM_E32_LEN) ? 32 : (N >= 256) ? 16 : 8;      // points per thread
     static constexpr int M = N / E;                    // threads per line
     static constexpr int MID = N / (E * E);            // middle radix (1 = none)
     static constexpr int NP = N + N / E;               // padded line length in shared memory
@@ -247,7 +250,7 @@ template <int N> struct FftPlan {
 struct CtaSync { SLM_DEV void operator()() const { sync_cta(); } };
 template <int THREADS> struct GroupSync {          // THREADS == 0: whole CTA
     int id;
-    SLM_DEV void operator()() const { if (THREADS == 0) sync_cta(); else sync_named(id, THREADS); }
+    SLM_DEV void operator()() const { if (THREADS == 0) sync_cta(); else if (THREADS == 32) sync_warp(); else sync_named(id, THREADS); }
 };
 
 template <typename R, int N, int DIR, int STRIDE, class Sync = CtaSync, bool TW_SHARED = false>

@@ -22,12 +22,12 @@ template <typename R, int L> struct GroupLaunch<R, L, true> {
     static int launch(int mode, const ColGroupArgs& ga, const TileMap& in, const TileMap& out, int ctas, cudaStream_t s) {
         const long long tiles = (long long)ga.c.B * (ga.c.W / GG::TC);
         const dim3 grid((unsigned)(tiles < ctas ? tiles : ctas)), block(GG::THREADS);
-        if (mode == CGM_GS) SLM_LAUNCH((col_group_kernel<R, L, CGM_GS>), grid, block, GG::SMEM, s, ga, in, out);
-        else if (mode == CGM_GD) SLM_LAUNCH((col_group_kernel<R, L, CGM_GD>), grid, block, GG::SMEM, s, ga, in, out);
-        else if (mode == CGM_STATS) SLM_LAUNCH((col_group_kernel<R, L, CGM_STATS>), grid, block, GG::SMEM, s, ga, in, out);
-        else if (mode == CGM_STATS_KEEP) SLM_LAUNCH((col_group_kernel<R, L, CGM_STATS_KEEP>), grid, block, GG::SMEM, s, ga, in, out);
-        else if (mode == CGM_GD_POST) SLM_LAUNCH((col_group_kernel<R, L, CGM_GD_POST>), grid, block, GG::SMEM, s, ga, in, out);
-        else SLM_LAUNCH((col_group_kernel<R, L, CGM_COMPLEX>), grid, block, GG::SMEM, s, ga, in, out);
+        if (mode == CGM_GS) SLM_LAUNCH_PDL((col_group_kernel<R, L, CGM_GS>), grid, block, GG::SMEM, s, ga, in, out);
+        else if (mode == CGM_GD) SLM_LAUNCH_PDL((col_group_kernel<R, L, CGM_GD>), grid, block, GG::SMEM, s, ga, in, out);
+        else if (mode == CGM_STATS) SLM_LAUNCH_PDL((col_group_kernel<R, L, CGM_STATS>), grid, block, GG::SMEM, s, ga, in, out);
+        else if (mode == CGM_STATS_KEEP) SLM_LAUNCH_PDL((col_group_kernel<R, L, CGM_STATS_KEEP>), grid, block, GG::SMEM, s, ga, in, out);
+        else if (mode == CGM_GD_POST) SLM_LAUNCH_PDL((col_group_kernel<R, L, CGM_GD_POST>), grid, block, GG::SMEM, s, ga, in, out);
+        else SLM_LAUNCH_PDL((col_group_kernel<R, L, CGM_COMPLEX>), grid, block, GG::SMEM, s, ga, in, out);
         return 0;
     }
 };
@@ -47,11 +47,11 @@ template <typename R, int L> struct RowLaunch {
     static int row_pass(int alg, const RowArgs& a, cudaStream_t s) {
         const dim3 grid((unsigned)((long long)a.B * a.H / RG::NR)), block(RG::THREADS);
         if (alg == ALG_GS) {
-            if (a.final_pass) SLM_LAUNCH((row_pass_kernel<R, L, ALG_GS, 1>), grid, block, RG::SMEM, s, a);
-            else SLM_LAUNCH((row_pass_kernel<R, L, ALG_GS, 0>), grid, block, RG::SMEM, s, a);
+            if (a.final_pass) SLM_LAUNCH_PDL((row_pass_kernel<R, L, ALG_GS, 1>), grid, block, RG::SMEM, s, a);
+            else SLM_LAUNCH_PDL((row_pass_kernel<R, L, ALG_GS, 0>), grid, block, RG::SMEM, s, a);
         } else {
-            if (a.final_pass) SLM_LAUNCH((row_pass_kernel<R, L, ALG_GD, 1>), grid, block, RG::SMEM, s, a);
-            else SLM_LAUNCH((row_pass_kernel<R, L, ALG_GD, 0>), grid, block, RG::SMEM, s, a);
+            if (a.final_pass) SLM_LAUNCH_PDL((row_pass_kernel<R, L, ALG_GD, 1>), grid, block, RG::SMEM, s, a);
+            else SLM_LAUNCH_PDL((row_pass_kernel<R, L, ALG_GD, 0>), grid, block, RG::SMEM, s, a);
         }
         return check();
     }

@@ -170,6 +170,8 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), (RowGeom<R, W>::MIN_
     const int t = threadIdx.x, rr = t / M, j = t % M;
     const long long grow = (long long)blockIdx.x * G::NR + rr;
     const int b = (int)(grow / a.H), y = (int)(grow % a.H);
+    griddep_launch();                                 // the next pass may begin its prologue while this one drains
+    griddep_wait();                                   // ... and this one starts only when its predecessor's data is complete
     const PlaneStats* st = a.stats + b;
     const int done = ld_cg(&st->done);
     if (!FINAL && done) return;                       // uniform: a CTA never straddles planes

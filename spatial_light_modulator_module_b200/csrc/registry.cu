@@ -3,6 +3,9 @@
 #include "line_list.h"
 
 namespace slm {
+#ifndef SLM_EMULATE
+thread_local bool tl_pdl = false;
+#endif
 #define SLM_DECL(l) extern const LineTable line_table_##l##_0; extern const LineTable line_table_##l##_1;
 SLM_LINE_LENGTHS(SLM_DECL)
 #undef SLM_DECL

@@ -88,6 +88,10 @@ class Engine:
         torch = self._torch
         host = torch.from_numpy(np.ascontiguousarray(array))
         with torch.cuda.stream(self._stream):
+            if host.numel() * host.element_size() >= (1 << 20) and host.is_pinned():
+                dev = host.to(self._dev, non_blocking=True)            # e.g. a hologram returned by to_host(): no staging copy
+                self._stream.synchronize()
+                return dev
             if (1 << 20) <= host.numel() * host.element_size() <= (1 << 30):   # large planes: stage through pinned memory
                 pinned = torch.empty(host.shape, dtype=host.dtype, pin_memory=True)
                 pinned.copy_(host)
@@ -238,20 +242,36 @@ class Engine:
     def python_random_uniform(self, seed, shape):
         """``prod(shape)`` successive ``random.random()`` draws after ``random.seed(seed)`` as a device
         float64 array (MT19937 continued on the device from CPython's own state); the module-level
-        generator is left where the reference's per-pixel loop leaves it (algorithms.py:117-150)."""
+        generator is left where the reference's per-pixel loop leaves it (algorithms.py:117-150).
+
+        The stream is a pure function of (seed, count) -- and the reference's CLI always seeds with 42
+        (generate_hologram.py:370) -- so the last few streams are kept on the device, keyed by the seeded
+        generator state itself; set ``SLM_NO_GUESS_MEMO=1`` to regenerate on every call."""
+        import os
         import random
         random.seed(seed)
         version, words, gauss = random.getstate()
-        state = np.array(words[:624], dtype=np.uint32)
         pos = int(words[624])
         n = int(np.prod(shape))
         if pos & 1:                                    # not reachable right after seed(); keep the host path for it
             return self._mem_upload(hl.python_random_stream(seed, n).reshape(shape))
+        memo = None if os.environ.get("SLM_NO_GUESS_MEMO") else self.__dict__.setdefault("_stream_memo", {})
+        key = (hash(words), n)
+        if memo is not None and key in memo:
+            u, final_words = memo[key]
+            random.setstate((version, final_words, gauss))
+            return u.reshape(tuple(shape))
+        state = np.array(words[:624], dtype=np.uint32)
         u = self._mem_empty(tuple(shape), np.float64)
         out = np.empty(625, dtype=np.uint32)
         self._check(self._lib.slm_mt19937_uniform(self._ctx, state.ctypes.data_as(C.c_void_p), pos, self._mem_ptr(u), n,
                                                   out.ctypes.data_as(C.c_void_p)))
-        random.setstate((version, tuple(int(w) for w in out[:624]) + (int(out[624]),), gauss))
+        final_words = tuple(int(w) for w in out[:624]) + (int(out[624]),)
+        random.setstate((version, final_words, gauss))
+        if memo is not None:
+            while len(memo) >= 4:
+                memo.pop(next(iter(memo)))
+            memo[key] = (u, final_words)
         return u
 
     def phase_phasor(self, phase, inc_amp=None):

@@ -207,11 +207,14 @@ inline Idx thread_idx() {
 #define SLM_RESTRICT __restrict__
 #define SLM_LAUNCH(kernel, grid, block, smem, stream, ...) \
     emu::launch(grid, block, smem, [=]() { kernel(__VA_ARGS__); })
+#define SLM_LAUNCH_PDL SLM_LAUNCH
 
 namespace slm {
 template <typename T> inline T ld_ro(const T* p) { return *p; }
 template <typename T> inline T ld_cg(const T* p) { return *p; }
 template <typename T> inline void st_cg(T* p, T v) { *p = v; }
+inline void griddep_wait() {}
+inline void griddep_launch() {}
 inline void fence_device() {}
 inline void fence_block() {}
 inline unsigned atomic_add_shared(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
@@ -219,8 +222,10 @@ inline unsigned atomic_inc_wrap(unsigned* p, unsigned limit) { unsigned o = *p; 
 inline float shfl_xor(float v, int m) { return emu::shfl_xor(v, m); }
 inline double shfl_xor(double v, int m) { return emu::shfl_xor(v, m); }
 inline unsigned shfl_idx(unsigned v, int src) { return emu::shfl_idx(v, src); }
+inline void sync_warp() { (void)emu::shfl_idx(0u, 0); }
 inline void sync_cta() { emu::sync_cta(); }
 inline void sync_named(int id, int nthreads) { emu::sync_named(id, nthreads); }
+
 // compiled with -ffp-contract=off, so plain operators are single IEEE operations
 inline double mul_rn(double a, double b) { return a * b; }
 inline double add_rn(double a, double b) { return a + b; }
