@@ -79,9 +79,9 @@ template <> struct GreyWord<8> { using type = uint2; };
 template <> struct GreyWord<4> { using type = unsigned; };
 template <> struct GreyWord<2> { using type = unsigned short; };
 template <> struct GreyWord<1> { using type = unsigned char; };
-template <int TC, int H, int NT> SLM_DEV void copy_grey_tile(const uint8_t* src, size_t pitch, uint8_t* dst, int lane) {
+template <int TC, int H, int NT, int CHMAX = 16> SLM_DEV void copy_grey_tile(const uint8_t* src, size_t pitch, uint8_t* dst, int lane) {
     using Wd = typename GreyWord<TC>::type;
-    constexpr int ROWS = (H + NT - 1) / NT, CH = ROWS < 16 ? ROWS : 16;
+    constexpr int ROWS = (H + NT - 1) / NT, CH = ROWS < CHMAX ? ROWS : CHMAX;
 #pragma unroll 1
     for (int r0 = 0; r0 < ROWS; r0 += CH) {
         Wd w[CH];
@@ -147,7 +147,7 @@ col_group_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const S
     // on the field, the per-plane state and the partial sums of that pass are read
     griddep_wait();
     sync_cta();
-    auto rests = [&](int b) { return MODE != CGM_COMPLEX && ld_cg(&a.stats[b].done) != 0; };
+    auto rests = [&](int b) { return MODE != CGM_COMPLEX && !ga.all_planes && ld_cg(&a.stats[b].done) != 0; };
 
     constexpr bool HAS_STATS = MODE != CGM_COMPLEX;
     constexpr int FIELDS = MODE == CGM_GS ? F_ALL : (IS_GD ? F_A : F_MX);
@@ -267,7 +267,7 @@ col_group_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const S
             pi.done = 0;
             if (MODE != CGM_COMPLEX) {
                 const PlaneStats* ps = a.stats + bb;
-                pi.done = ld_cg(&ps->done);
+                pi.done = ga.all_planes ? 0 : ld_cg(&ps->done);
                 if (MODE == CGM_GS || IS_GD) { pi.scale = ld_cg(&ps->scale); pi.imax = ld_cg(&ps->imax); pi.norm = ld_ro(a.norm + bb); }
             }
         }

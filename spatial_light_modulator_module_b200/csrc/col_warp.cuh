@@ -1,0 +1,392 @@
+// Warp-per-column persistent Fourier-plane kernel (sm_100a) for 1024-point fp32 columns.
+//
+// Why a second column kernel: the group kernel (col_groups.cuh) keeps 16 points per thread, so a column is
+// shared by two warps that meet at four named barriers per transform, and one CTA of 16 compute warps
+// (96 registers) is all an SM holds -- ncu shows it latency bound (issue slots ~30 % busy).  Here
+//   * ONE WARP owns a column: 1024 = 32 x 32, 32 points per lane, one lane<->register transpose per
+//     transform through shared memory, no barrier inside a transform (only __syncwarp);
+//   * the transpose is done IN PLACE in the tile buffer: the two warps of a column pair split the pair's
+//     16-byte chunk of the 64B-swizzled tile image by rows (512 rows each), which makes every exchange
+//     access a conflict-free 64-bit access (a single column alone only reaches half of the banks); the two
+//     warps meet twice per tile (after reading the tile into registers, before writing the results back);
+//   * no exchange buffer is needed, so THREE 64 KB tile buffers fit and TWO tiles are transformed
+//     concurrently by two groups of eight warps, out of phase, while the third buffer is in flight
+//     (TMA store of a finished tile, TMA load of the next one);
+//   * a service warp sequences the tiles (descriptor + per-plane scalars in shared memory, TMA, staging of
+//     the 8-bit target rows), a second one publishes the tiles' partial sums and closes a plane's iteration.
+// Arithmetic, reductions and loop control are those of col_groups.cuh (same modes, same results).
+#pragma once
+#include "col_groups.cuh"
+
+namespace slm {
+
+template <typename R, int H> struct ColWarpGeom {
+    static constexpr int E = 32, M = 32;                          // points per lane, lanes per column
+    static constexpr int TC = 8;                                  // columns per tile (64-byte rows)
+    static constexpr int GROUPS = 2, NBUF = 3;
+    static constexpr int GROUP_THREADS = TC * M;                  // 256: eight warps, one per column
+    static constexpr int COMPUTE = GROUPS * GROUP_THREADS;        // 512
+    static constexpr int THREADS = COMPUTE + 128;                 // + service warpgroup: sequencer, 2 staging helpers, publisher
+    static constexpr int COPIERS = 96;                            // sequencer warp + helpers stage the 8-bit target rows
+    static constexpr int ROWB = TC * (int)sizeof(cpx<R>);
+    static constexpr bool OK = sizeof(R) == 4 && H == 1024;
+    static constexpr size_t TILE = (size_t)H * ROWB;              // 64 KB
+    static constexpr size_t GREY = (size_t)H * TC;                // 8 KB
+    // [tile x3][grey x3][lut][red 3 x 8][desc x3][barriers]
+    static constexpr size_t OFF_GREY = NBUF * TILE;
+    static constexpr size_t OFF_LUT = OFF_GREY + NBUF * GREY;
+    static constexpr size_t OFF_RED = OFF_LUT + 256 * sizeof(R);
+    static constexpr size_t OFF_DESC = OFF_RED + NBUF * TC * sizeof(Partial);
+    static constexpr size_t OFF_ORDER = OFF_DESC + NBUF * 32;     // staging order of the sequencer to its helpers
+    static constexpr size_t OFF_BAR = OFF_ORDER + 32;
+    static constexpr size_t SMEM = OFF_BAR + 3 * NBUF * 32;
+    static_assert(!OK || SMEM <= 232448, "shared memory budget");
+};
+
+// What the sequencer tells the other warps about the tile in a buffer.
+struct TileDesc { long long g; double scale, imax, norm; };      // g < 0: no more tiles
+struct StageOrder { long long g; int s; };                       // g == -2: helpers leave
+
+// f(b): byte offset (inside the 1 KB that 16 rows x one 16-byte chunk span) of element b of a 32-element
+// run, laid out as 16-byte units on consecutive rows of the 64B-swizzled image.  XOR-linear in b.
+SLM_HOSTDEV constexpr unsigned xch_f(unsigned b) { return ((b >> 1) << 6) | (((b >> 2) & 3u) << 4) | ((b & 1u) << 3); }
+
+// v[r] *= w1^r, r = 1..31, powers formed in blocks of four so few of them are live at a time.
+template <typename R> SLM_DEV void twiddle_run32(cpx<R>* v, cpx<R> w1) {
+    const cpx<R> w2 = cmul(w1, w1), w3 = cmul(w2, w1), w4 = cmul(w2, w2);
+    v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3); v[4] = cmul(v[4], w4);
+    cpx<R> W = w4;
+#pragma unroll
+    for (int a = 1; a < 8; ++a) {
+        if (a > 1) { W = cmul(W, w4); v[4 * a] = cmul(v[4 * a], W); }
+        v[4 * a + 1] = cmul(v[4 * a + 1], cmul(W, w1));
+        v[4 * a + 2] = cmul(v[4 * a + 2], cmul(W, w2));
+        v[4 * a + 3] = cmul(v[4 * a + 3], cmul(W, w3));
+    }
+}
+
+// Exchange accesses: address = (lane base ^ X) + OFF with X, OFF compile-time.  The XOR is issued inside the asm
+// statement so the 64 addresses of a transform are formed where they are used (one LOP3 each); left to the
+// optimiser they are computed once per tile, kept across the two transforms and spilled to local memory.
+#if defined(__CUDA_ARCH__) && !defined(SLM_EMULATE)
+using XchBase = unsigned;                                        // shared-window address
+SLM_DEV XchBase xch_base(unsigned char* buf, unsigned off) { return smem_addr(buf) + off; }
+template <unsigned X, unsigned OFF> SLM_DEV void xch_store(XchBase base, cpx<float> v) {
+    asm volatile("{\n.reg .u32 a;\nxor.b32 a, %0, %1;\nst.shared.v2.f32 [a+%2], {%3, %4};\n}"
+                 ::"r"(base), "n"(X), "n"(OFF), "f"(v.x), "f"(v.y) : "memory");
+}
+template <unsigned X, unsigned OFF> SLM_DEV cpx<float> xch_load(XchBase base) {
+    cpx<float> v;
+    asm volatile("{\n.reg .u32 a;\nxor.b32 a, %2, %3;\nld.shared.v2.f32 {%0, %1}, [a+%4];\n}"
+                 : "=f"(v.x), "=f"(v.y) : "r"(base), "n"(X), "n"(OFF) : "memory");
+    return v;
+}
+#else
+struct XchBase { unsigned char* buf; unsigned off; };
+inline XchBase xch_base(unsigned char* buf, unsigned off) { return XchBase{buf, off}; }
+template <unsigned X, unsigned OFF, typename R> inline void xch_store(XchBase b, cpx<R> v) { *reinterpret_cast<cpx<R>*>(b.buf + ((b.off ^ X) + OFF)) = v; }
+template <unsigned X, unsigned OFF> inline cpx<float> xch_load(XchBase b) { return *reinterpret_cast<const cpx<float>*>(b.buf + ((b.off ^ X) + OFF)); }
+#endif
+template <int R0, int N> struct XchRun {
+    template <typename R> static SLM_DEV void store(XchBase b, const cpx<R>* v) {
+        xch_store<xch_f((unsigned)R0), 0u>(b, v[R0]);
+        if constexpr (R0 + 1 < N) XchRun<R0 + 1, N>::store(b, v);
+    }
+    template <typename R> static SLM_DEV void load(XchBase b, cpx<R>* v) {
+        v[R0] = xch_load<xch_f((unsigned)R0), 1024u * R0>(b);
+        if constexpr (R0 + 1 < N) XchRun<R0 + 1, N>::load(b, v);
+    }
+};
+
+// One 1024-point transform held by a warp: v[r] = x[lane + 32 r] on entry, X[lane + 32 r] on exit.
+// xw / xr: this lane's write / read base inside the warp's exchange region of the tile buffer (1 KB aligned).
+template <int DIR, typename R>
+SLM_DEV void warp_fft1024(cpx<R>* v, unsigned char* buf, unsigned xw, unsigned xr, cpx<R> w1) {
+    dft_small<32, DIR>(v);                                       // over n2 = r: Y[n1 = lane][k2 = r]
+    sync_warp();                                                 // earlier reads of the region are complete
+    XchRun<0, 32>::store(xch_base(buf, xw), v);                  // element (lane, r) -> slot 32 lane + (r ^ lane)
+    sync_warp();
+    XchRun<0, 32>::load(xch_base(buf, xr), v);                   // slot 32 r + (lane ^ r) = element (r, lane)
+    if (DIR > 0) w1.y = -w1.y;
+    opaque(w1);                                                  // (or the 31 powers are hoisted out of the tile loop and spilled)
+    twiddle_run32(v, w1);                                        // Y[n1 = r][k2 = lane] * W^(r * lane)
+    dft_small<32, DIR>(v);                                       // over n1 = r: X[lane + 32 r]
+}
+
+template <typename R, int H, int MODE>
+SLM_GLOBAL void SLM_LAUNCH_BOUNDS((ColWarpGeom<R, H>::THREADS), 1)
+col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SLM_GRID_CONSTANT TileMap tm_out) {
+    using G = ColWarpGeom<R, H>;
+    constexpr int TC = G::TC, ROWB = G::ROWB, NBUF = G::NBUF;
+    constexpr bool HAS_T = MODE == CGM_GS || MODE == CGM_GD || MODE == CGM_GD_POST;
+    constexpr bool HAS_OUT = MODE != CGM_STATS;
+    constexpr bool IS_GD = MODE == CGM_GD || MODE == CGM_GD_POST;
+    constexpr bool IS_STATS = MODE == CGM_STATS || MODE == CGM_STATS_KEEP;
+    constexpr bool HAS_STATS = MODE != CGM_COMPLEX;
+    constexpr int FIELDS = MODE == CGM_GS ? F_ALL : (IS_GD ? F_A : F_MX);
+    const ColArgs& a = ga.c;
+    SLM_DYN_SMEM(raw);
+    R* const lut_s = reinterpret_cast<R*>(raw + G::OFF_LUT);
+    Partial* const red = reinterpret_cast<Partial*>(raw + G::OFF_RED);                 // [NBUF][TC]
+    TileDesc* const desc = reinterpret_cast<TileDesc*>(raw + G::OFF_DESC);             // [NBUF]
+    TileBarrier* const full = reinterpret_cast<TileBarrier*>(raw + G::OFF_BAR);        // [NBUF] tile (and grey rows) landed
+    TileBarrier* const done = reinterpret_cast<TileBarrier*>(raw + G::OFF_BAR + NBUF * 32);     // [NBUF] group is through the tile
+    TileBarrier* const taken = reinterpret_cast<TileBarrier*>(raw + G::OFF_BAR + 2 * NBUF * 32); // [NBUF] publisher has the tile's sums
+    auto tile_buf = [&](int s) { return raw + (size_t)s * G::TILE; };
+    auto grey_buf = [&](int s) { return raw + G::OFF_GREY + (size_t)s * G::GREY; };
+    auto bar = [](TileBarrier* base, int s) { return reinterpret_cast<TileBarrier*>(reinterpret_cast<unsigned char*>(base) + s * 32); };
+
+    const int t = threadIdx.x;
+    const int tiles = a.W / TC;
+    const long long total = (long long)a.B * tiles;
+    const bool use_t8 = HAS_T && a.T8 != nullptr;
+    griddep_launch();
+    if (t == 0) {
+        for (int s = 0; s < NBUF; ++s) {
+            mbar_init(bar(full, s), use_t8 ? 2u : 1u);
+            mbar_init(bar(done, s), (unsigned)G::GROUP_THREADS);
+            mbar_init(bar(taken, s), 1u);
+        }
+        mbar_fence_init();
+    }
+    if (use_t8) {
+        const R* lut = static_cast<const R*>(a.lut);
+        for (int i = t; i < 256; i += G::THREADS) lut_s[i] = ld_ro(lut + i);
+    }
+    griddep_wait();
+    sync_cta();
+
+    // Register budget: 640 threads launch with 96 registers each; the service warpgroup gives most of its share
+    // back and the four compute warpgroups take it (32 points per lane need ~110 registers).
+    if (t >= G::COMPUTE) reg_dealloc<64>(); else reg_alloc<104>();
+    if (t >= G::COMPUTE + 96) {
+        // ================= publisher warp =================
+        if (!HAS_STATS) return;
+        const int lane = t - G::COMPUTE - 96;
+        const double hw = (double)H * (double)a.W;
+        for (unsigned k = 0;; ++k) {
+            const int s = (int)(k % NBUF);
+            const unsigned par = (k / NBUF) & 1u;
+            mbar_wait(bar(full, s), par);
+            const TileDesc d = desc[s];
+            if (d.g < 0) break;
+            const int b = (int)(d.g / tiles), tile = (int)(d.g % tiles);
+            mbar_wait(bar(done, s), par);                    // the group's sums of this tile are in shared memory
+            Partial q; q.mx = 0; q.a = 0; q.b = 0; q.c = 0;
+            if (lane < TC) q = red[s * TC + lane];
+            q = warp_reduce<FIELDS>(q);                      // (also: every lane holds its copy before the slot is released)
+            if (lane == 0) mbar_arrive(bar(taken, s));
+            PlaneStats* st = a.stats + b;
+            Partial* plane_partials = a.partial + (size_t)b * tiles;
+            unsigned ticket = 0;
+            if (lane == 0) ticket = publish_partial(q, plane_partials, tile, tiles, a.counter + b);
+            Partial tot;
+            if (collect_if_last<FIELDS>(ticket, lane, plane_partials, tiles, tot) && lane == 0) {
+                if (IS_STATS) {
+                    st->imax = tot.mx; st->scale = d.norm / tot.mx;
+                } else {
+                    double err;
+                    if (MODE == CGM_GS) {
+                        const double sN = d.norm / tot.mx;               // algorithms.py:37
+                        const double s0u = (double)(R)d.scale;           // the scale the tiles actually used
+                        const double dl = (s0u != 0.0) ? sN / s0u - 1.0 : 0.0;
+                        err = (tot.a + 2.0 * dl * tot.b + dl * dl * tot.c) / hw;   // == sum((s*I - T)^2)/HW, :38,:162
+                        st->imax = tot.mx; st->scale = sN;
+                    } else {
+                        err = tot.a / hw;                                // algorithms.py:92
+                    }
+                    const int it = st->iters;
+                    a.err_curve[(size_t)b * a.max_loops + it] = err;
+                    st->err = err; st->iters = it + 1;
+                    st->done = !(err > a.tolerance);                     // loop condition, algorithms.py:29,83
+                }
+            }
+        }
+        return;
+    }
+
+    StageOrder* const order = reinterpret_cast<StageOrder*>(raw + G::OFF_ORDER);
+    auto stage_rows = [&](long long g, int s, int who) {     // the tile's 8-bit target rows -> grey_buf(s), by the 96 copiers
+        const int b = (int)(g / tiles), tile = (int)(g % tiles);
+        copy_grey_tile<TC, H, G::COPIERS>(a.T8 + (size_t)b * H * a.W + (size_t)tile * TC, (size_t)a.W, grey_buf(s), who);
+    };
+    if (t >= G::COMPUTE + 32) {
+        // ================= staging helpers: follow the sequencer's orders =================
+        if (!use_t8) return;
+        for (;;) {
+            sync_named(15, G::COPIERS);
+            const long long g = order->g;
+            const int s = order->s;
+            if (g < 0) break;
+            stage_rows(g, s, t - G::COMPUTE);
+            sync_named(14, G::COPIERS);
+        }
+        return;
+    }
+    if (t >= G::COMPUTE) {
+        // ================= sequencer warp: tile order, TMA, target staging =================
+        const int lane = t - G::COMPUTE;
+        // A candidate tile and its plane's scalars; the loads are issued here and looked at later (resolve).
+        struct Peek { long long g; int done; double scale, imax, norm; };
+        auto peek = [&](long long g) {
+            Peek p; p.g = g; p.done = 0; p.scale = 0; p.imax = 0; p.norm = 0;
+            if (g < total && MODE != CGM_COMPLEX) {
+                const int b = (int)(g / tiles);
+                const PlaneStats* ps = a.stats + b;
+                p.done = ga.all_planes ? 0 : ld_cg(&ps->done); p.scale = ld_cg(&ps->scale); p.imax = ld_cg(&ps->imax); p.norm = ld_ro(a.norm + b);
+            }
+            return p;
+        };
+        // -> descriptor of the first tile at or after the candidate whose plane is still iterating (g = -1: none)
+        auto resolve = [&](Peek p) {
+            while (p.g < total && p.done) p = peek(p.g + gridDim.x);      // finished planes rest (tolerance > 0 only)
+            TileDesc d; d.g = p.g < total ? p.g : -1; d.scale = p.scale; d.imax = p.imax; d.norm = p.norm;
+            return d;
+        };
+        auto stage_grey = [&](int s, const TileDesc& d) {
+            if (!use_t8 || d.g < 0) return;
+            if (lane == 0) { order->g = d.g; order->s = s; }
+            sync_named(15, G::COPIERS);
+            stage_rows(d.g, s, lane);
+            sync_named(14, G::COPIERS);
+        };
+        // the buffer is free (its last tile stored and drained, its sums and descriptor taken): hand it over
+        auto post = [&](int s, const TileDesc& d) {
+            if (lane != 0) return;
+            desc[s] = d;
+            if (d.g < 0) {                                   // stop marker: complete the phase without data
+                mbar_arrive(bar(full, s));
+                if (use_t8) mbar_arrive(bar(full, s));
+                return;
+            }
+            const int b = (int)(d.g / tiles), tile = (int)(d.g % tiles);
+            tile_load(tm_in, tile_buf(s), bar(full, s), (long long)b * H, H, (long long)tile * ROWB, ROWB, (int)sizeof(R));
+            if (use_t8) mbar_arrive(bar(full, s));           // the grey rows were staged (and warp-synchronised) before
+        };
+        TileDesc cur = resolve(peek(blockIdx.x));
+        unsigned k = 0;                                      // next item (tile or stop marker) to issue
+        int stops = 0;                                       // stop markers issued: one per group ends the kernel
+        while (k < (unsigned)NBUF && stops < G::GROUPS) {
+            const int s = (int)(k % NBUF);
+            stage_grey(s, cur);
+            sync_warp();
+            post(s, cur);
+            ++k;
+            if (cur.g < 0) ++stops; else cur = resolve(peek(cur.g + gridDim.x));
+        }
+        // retire tile kd (store it), then reuse its buffer for item kd + NBUF
+        for (unsigned kd = 0; kd < k - (unsigned)stops; ++kd) {              // k - stops = tiles issued so far
+            const int s = (int)(kd % NBUF);
+            const unsigned par = (kd / NBUF) & 1u;
+            mbar_wait(bar(done, s), par);
+            if (HAS_OUT && lane == 0) {
+                const TileDesc d = desc[s];
+                const int b = (int)(d.g / tiles), tile = (int)(d.g % tiles);
+                tile_store(tm_out, tile_buf(s), (long long)b * H, H, (long long)tile * ROWB, ROWB, (int)sizeof(R));
+                tile_store_commit();
+            }
+            if (stops < G::GROUPS) {
+                const Peek ahead = peek(cur.g < 0 ? total : cur.g + gridDim.x);   // in flight during the staging below
+                stage_grey(s, cur);                                       // the group is through this slot's grey rows
+                if (HAS_STATS) mbar_wait(bar(taken, s), par);            // the publisher has this slot's descriptor and sums
+                if (lane == 0) tile_store_wait_read();                   // the store has drained the buffer
+                sync_warp();
+                post(s, cur);
+                ++k;
+                if (cur.g < 0) ++stops; else cur = resolve(ahead);
+            }
+        }
+        if (use_t8) { if (lane == 0) order->g = -2; sync_named(15, G::COPIERS); }     // dismiss the helpers
+        if (lane == 0) tile_store_wait_all();
+        return;
+    }
+
+    // ================= compute warps: one column each =================
+    const int grp = t / G::GROUP_THREADS;
+    const int c = (t % G::GROUP_THREADS) / 32, lane = t % 32;
+    const int pair = c >> 1, half = c & 1;
+    const int pair_bar = 1 + grp * (TC / 2) + pair;                  // named barrier of the column pair (64 threads)
+    // byte offset of (row lane + 32 r, column c) in the swizzled tile image = my + 2048 r
+    const unsigned my = (unsigned)lane * 64u + (((unsigned)c * 8u) ^ ((((unsigned)lane >> 1) & 3u) << 4));
+    // exchange region of this warp: rows [512 half, 512 half + 512) of the pair's 16-byte chunk
+    const unsigned xw = 32768u * half + 1024u * lane + (xch_f((unsigned)lane) ^ ((unsigned)pair << 4));
+    const unsigned xr = 32768u * half + (xch_f((unsigned)lane) ^ ((unsigned)pair << 4));
+    const cpx<R> w1 = ld_const(static_cast<const cpx<R>*>(a.tw) + lane);       // exp(-2 pi i lane / 1024)
+    const unsigned zero = (unsigned)a.B >> 31;
+    cpx<R> v[32];
+    for (unsigned k = (unsigned)grp;; k += G::GROUPS) {
+        const int s = (int)(k % NBUF);
+        const unsigned par = (k / NBUF) & 1u;
+        unsigned char* const buf = tile_buf(s);
+        mbar_wait(bar(full, s), par);
+        const TileDesc d = desc[s];
+        if (d.g < 0) break;
+        const int b = (int)(d.g / tiles), tile = (int)(d.g % tiles);
+#pragma unroll
+        for (int r = 0; r < 32; ++r) v[r] = *reinterpret_cast<const cpx<R>*>(buf + my + 2048u * r);
+        sync_named(pair_bar, 64);                            // the partner holds its column too: the pair's chunk is free
+        if (MODE == CGM_COMPLEX && ga.mode_inverse) warp_fft1024<+1>(v, buf, xw, xr, w1);
+        else if (MODE != CGM_GD_POST) warp_fft1024<-1>(v, buf, xw, xr, w1);
+
+        // ---- pointwise step and per-thread sums (see col_group_kernel) ----
+        R mx = 0, sa = 0, sb = 0, sc = 0;
+        if (MODE == CGM_GS || IS_GD) {
+            const R s0r = (R)d.scale;
+            const R gdk = (R)(d.norm / d.imax);
+            const uint8_t* gsrc = grey_buf(s) + (size_t)lane * TC + c;
+            const size_t goff = (size_t)b * H * a.W + (size_t)lane * a.W + tile * TC + c;
+#pragma unroll
+            for (int r0 = 0; r0 < 32; r0 += 8) {
+                R tv[8], aux[8];
+                if (use_t8) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { const int gl = gsrc[(size_t)(r0 + i) * 32 * TC]; tv[i] = (R)gl; aux[i] = lut_s[gl]; }
+                } else {
+                    const R* T = static_cast<const R*>(a.Treal) + goff;
+                    const R* Q = static_cast<const R*>(a.plane2) + goff;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { tv[i] = ld_ro(T + (size_t)(r0 + i) * 32 * a.W); aux[i] = ld_ro(Q + (size_t)(r0 + i) * 32 * a.W); }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = r0 + i;
+                    const R m2 = cnorm2(v[r]);
+                    if (MODE == CGM_GS) {                                 // algorithms.py:33,36-38
+                        const R u = s0r * m2, dd = u - tv[i];
+                        mx = fmax(mx, m2); sa += dd * dd; sb += dd * u; sc += u * u;
+                        v[r] = (m2 == (R)0) ? mk<R>(copysign(aux[i], v[r].x), (R)0) : cscale(v[r], aux[i] * rsqrt_fast(m2));
+                    } else {                                              // algorithms.py:85-88,92
+                        const R I = m2 * gdk;
+                        const R dd = I - tv[i];
+                        sa += dd * dd;
+                        v[r] = cscale(cscale(v[r], aux[i]), dd);
+                    }
+                }
+            }
+        } else if (IS_STATS) {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) mx = fmax(mx, cnorm2(v[r]));
+        } else {
+            const R sc_out = (R)ga.scale;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) v[r] = cscale(v[r], sc_out);
+        }
+        if (HAS_STATS) {                                     // this column's sums -> shared memory, for the publisher
+            Partial p; p.mx = (double)mx; p.a = (double)sa; p.b = (double)sb; p.c = (double)sc;
+            p = warp_reduce<FIELDS>(p);
+            if (lane == 0) red[s * TC + c] = p;             // (the sequencer reissued this slot only after its sums were taken)
+        }
+        // (+ zero: a run-time 0 the assembler cannot see through, so the exchange addresses of the second transform
+        //  are formed afresh instead of being kept -- in local memory -- from the first one)
+        if (MODE == CGM_GS || IS_GD) warp_fft1024<+1>(v, buf, xw + zero, xr + zero, w1);
+        if (HAS_OUT) {
+            sync_named(pair_bar, 64);                        // the partner is through its exchange: its rows of my column are free
+#pragma unroll
+            for (int r = 0; r < 32; ++r) *reinterpret_cast<cpx<R>*>(buf + my + 2048u * r) = v[r];
+            fence_async_smem();
+        }
+        mbar_arrive(bar(done, s));
+    }
+}
+
+}  // namespace slm

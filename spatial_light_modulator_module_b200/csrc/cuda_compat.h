@@ -56,6 +56,9 @@ SLM_DEV double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v
 SLM_DEV unsigned shfl_idx(unsigned v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 SLM_DEV void sync_cta() { __syncthreads(); }
 SLM_DEV void sync_warp() { __syncwarp(); }
+// warpgroup-wide register reallocation (all four warps of an aligned warpgroup execute the same one)
+template <int N> SLM_DEV void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> SLM_DEV void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 // named barrier `id` (1..15) over `nthreads` threads (whole warps) of the CTA
 SLM_DEV void sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 // IEEE operations that must not be contracted into FMAs (bit parity with numpy)

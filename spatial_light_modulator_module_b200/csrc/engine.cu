@@ -184,10 +184,11 @@ extern "C" int slm_trace_read(unsigned long long* out) {
 }
 #endif
 // Launch one mode of the warp-specialised column kernel over X (in) -> map_out.
-static int launch_group(slm_ctx* c, int mode, int batch, const ColArgs* loop, const TileMap* map_out, int inverse, double scale) {
+static int launch_group(slm_ctx* c, int mode, int batch, const ColArgs* loop, const TileMap* map_out, int inverse, double scale,
+                        int all_planes = 0) {
     ColGroupArgs ga{};
     if (loop) ga.c = *loop;
-    ga.mode_inverse = inverse; ga.scale = scale;
+    ga.mode_inverse = inverse; ga.scale = scale; ga.all_planes = all_planes;
 #ifdef SLM_TRACE
     if (mode == g_trace_mode) { ga.trace = g_trace; g_trace_mode = -1; }      // trace the next launch of that mode only
 #endif
@@ -431,7 +432,16 @@ extern "C" int slm_gs_run(slm_ctx* c, int batch, const uint8_t* T8, const void* 
     }
     ra.final_pass = 1;
     SLM_TIMED(K_ROW_PASS, c->row->row_pass(ALG_GS, ra, c->stream));
-    if (expected_out) { SLM_TIMED(K_COL_PLAIN, c->col->col_plain(stats_args(c, batch, OUT_INTENSITY_GS, expected_out), c->stream)); }
+    if (expected_out) {
+        PlainColArgs ia = stats_args(c, batch, OUT_INTENSITY_GS, expected_out);
+        if (c->use_groups) {
+            // C = fft2(B) of the last iteration once more, by the SAME kernel arithmetic that took its max, kept in X;
+            // the intensity pass then only scales |C|^2 (max(expected_outcome) == norm like the reference's, :36-37)
+            SLM_TRY(launch_group(c, CGM_STATS_KEEP, batch, nullptr, &c->map_x, 0, 1.0, 1));
+            ia.skip_fft = 1;
+        }
+        SLM_TIMED(K_COL_PLAIN, c->col->col_plain(ia, c->stream));
+    }
     return 0;
 }
 
@@ -665,8 +675,10 @@ extern "C" int slm_expected_outcome(slm_ctx* c, int batch, const double* hologra
     PlainRowArgs ra{};
     ra.B = batch; ra.H = c->H; ra.input = IN_PHASE; ra.inverse = 0; ra.in = hologram; ra.out = c->X; ra.tw = c->tw_row;
     SLM_TIMED(K_ROW_PLAIN, c->row->row_plain(ra, c->stream));
-    SLM_TRY(run_stats(c, batch));
-    SLM_TIMED(K_COL_PLAIN, c->col->col_plain(stats_args(c, batch, OUT_INTENSITY_PREVIEW, out), c->stream));
+    PlainColArgs ia = stats_args(c, batch, OUT_INTENSITY_PREVIEW, out);
+    if (c->use_groups) { SLM_TRY(launch_group(c, CGM_STATS_KEEP, batch, nullptr, &c->map_x, 0, 1.0, 1)); ia.skip_fft = 1; }   // see slm_gs_run
+    else SLM_TRY(run_stats(c, batch));
+    SLM_TIMED(K_COL_PLAIN, c->col->col_plain(ia, c->stream));
     return 0;
 }
 

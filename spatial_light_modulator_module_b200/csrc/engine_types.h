@@ -77,6 +77,7 @@ enum ColGroupMode {
 };
 struct ColGroupArgs {
     int mode_inverse;        // CGM_COMPLEX: transform direction
+    int all_planes;          // 1: also planes whose loop has ended (the transform kept for the final intensity pass)
     double scale;            // CGM_COMPLEX: output scale
     unsigned long long* trace;   // -DSLM_TRACE builds: [ctas][64 tiles][16 events] globaltimer stamps, else null
     ColArgs c;               // loop arguments; B, W, stats, partial, counter, norm, tw are used by every mode

@@ -71,6 +71,17 @@ SLM_DEV cpx<float> pk_fma(cpx<float> a, cpx<float> b, cpx<float> c) {
 }
 #endif
 
+// Hide a value's provenance from the optimiser (keeps per-thread constants from being expanded into tables of
+// loop-invariant products that then live in local memory).
+#if defined(__CUDA_ARCH__) && !defined(SLM_EMULATE)
+SLM_DEV void opaque(cpx<float>& a) { asm volatile("" : "+f"(a.x), "+f"(a.y)); }
+SLM_DEV void opaque(cpx<double>& a) { asm volatile("" : "+d"(a.x), "+d"(a.y)); }
+SLM_DEV void opaque(unsigned& a) { asm volatile("" : "+r"(a)); }
+#else
+template <typename R> SLM_DEV void opaque(cpx<R>&) {}
+SLM_DEV void opaque(unsigned&) {}
+#endif
+
 template <typename R> SLM_DEV cpx<R> cadd(cpx<R> a, cpx<R> b) { return pk_add(a, b); }
 template <typename R> SLM_DEV cpx<R> csub(cpx<R> a, cpx<R> b) { return pk_add(a, mk<R>(-b.x, -b.y)); }
 // a * w = a.x*(w.x, w.y) + a.y*(-w.y, w.x)

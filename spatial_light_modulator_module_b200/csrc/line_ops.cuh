@@ -1,6 +1,7 @@
 // Host-side launchers of the pass kernels for one (line length, precision).
 #pragma once
 #include "col_groups.cuh"
+#include "col_warp.cuh"
 #include "passes.cuh"
 
 namespace slm {
@@ -9,9 +10,42 @@ template <typename R, int L, bool OK = ColGroupGeom<R, L>::OK> struct GroupLaunc
     static void prepare() {}
     static int launch(int, const ColGroupArgs&, const TileMap&, const TileMap&, int, cudaStream_t) { return -1; }
 };
+// Which persistent column kernel serves (R, L): the warp-per-column kernel where it is built (col_warp.cuh),
+// else the column-group kernel.  SLM_COL_KERNEL=group selects the latter at run time (A/B measurements).
+template <typename R, int L, bool WARP = ColWarpGeom<R, L>::OK> struct ColWarpLaunch {
+    static void prepare() {}
+    static bool launch(int, const ColGroupArgs&, const TileMap&, const TileMap&, int, cudaStream_t) { return false; }
+};
+template <typename R, int L> struct ColWarpLaunch<R, L, true> {
+    using WG = ColWarpGeom<R, L>;
+    template <int MODE> static void attr() {
+        cudaFuncSetAttribute(col_warp_kernel<R, L, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG::SMEM);
+    }
+    static void prepare() {
+        attr<CGM_GS>(); attr<CGM_GD>(); attr<CGM_STATS>(); attr<CGM_COMPLEX>(); attr<CGM_STATS_KEEP>(); attr<CGM_GD_POST>();
+    }
+    static bool enabled() {
+        static const bool on = !(getenv("SLM_COL_KERNEL") && getenv("SLM_COL_KERNEL")[0] == 'g');
+        return on;
+    }
+    static bool launch(int mode, const ColGroupArgs& ga, const TileMap& in, const TileMap& out, int ctas, cudaStream_t s) {
+        if (!enabled()) return false;
+        const long long tiles = (long long)ga.c.B * (ga.c.W / WG::TC);
+        const dim3 grid((unsigned)(tiles < ctas ? tiles : ctas)), block(WG::THREADS);
+        if (mode == CGM_GS) SLM_LAUNCH_PDL((col_warp_kernel<R, L, CGM_GS>), grid, block, WG::SMEM, s, ga, in, out);
+        else if (mode == CGM_GD) SLM_LAUNCH_PDL((col_warp_kernel<R, L, CGM_GD>), grid, block, WG::SMEM, s, ga, in, out);
+        else if (mode == CGM_STATS) SLM_LAUNCH_PDL((col_warp_kernel<R, L, CGM_STATS>), grid, block, WG::SMEM, s, ga, in, out);
+        else if (mode == CGM_STATS_KEEP) SLM_LAUNCH_PDL((col_warp_kernel<R, L, CGM_STATS_KEEP>), grid, block, WG::SMEM, s, ga, in, out);
+        else if (mode == CGM_GD_POST) SLM_LAUNCH_PDL((col_warp_kernel<R, L, CGM_GD_POST>), grid, block, WG::SMEM, s, ga, in, out);
+        else SLM_LAUNCH_PDL((col_warp_kernel<R, L, CGM_COMPLEX>), grid, block, WG::SMEM, s, ga, in, out);
+        return true;
+    }
+};
+
 template <typename R, int L> struct GroupLaunch<R, L, true> {
     using GG = ColGroupGeom<R, L>;
     static void prepare() {
+        ColWarpLaunch<R, L>::prepare();
         cudaFuncSetAttribute(col_group_kernel<R, L, CGM_GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GG::SMEM);
         cudaFuncSetAttribute(col_group_kernel<R, L, CGM_GD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GG::SMEM);
         cudaFuncSetAttribute(col_group_kernel<R, L, CGM_STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GG::SMEM);
@@ -20,6 +54,9 @@ template <typename R, int L> struct GroupLaunch<R, L, true> {
         cudaFuncSetAttribute(col_group_kernel<R, L, CGM_GD_POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GG::SMEM);
     }
     static int launch(int mode, const ColGroupArgs& ga, const TileMap& in, const TileMap& out, int ctas, cudaStream_t s) {
+        static_assert(!ColWarpGeom<R, L>::OK || (ColWarpGeom<R, L>::TC == GG::TC && ColWarpGeom<R, L>::ROWB == GG::ROWB),
+                      "both column kernels must share the tile maps and the per-tile partial sums");
+        if (ColWarpLaunch<R, L>::launch(mode, ga, in, out, ctas, s)) return 0;
         const long long tiles = (long long)ga.c.B * (ga.c.W / GG::TC);
         const dim3 grid((unsigned)(tiles < ctas ? tiles : ctas)), block(GG::THREADS);
         if (mode == CGM_GS) SLM_LAUNCH_PDL((col_group_kernel<R, L, CGM_GS>), grid, block, GG::SMEM, s, ga, in, out);

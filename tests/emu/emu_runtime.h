@@ -223,6 +223,8 @@ inline float shfl_xor(float v, int m) { return emu::shfl_xor(v, m); }
 inline double shfl_xor(double v, int m) { return emu::shfl_xor(v, m); }
 inline unsigned shfl_idx(unsigned v, int src) { return emu::shfl_idx(v, src); }
 inline void sync_warp() { (void)emu::shfl_idx(0u, 0); }
+template <int N> inline void reg_alloc() {}
+template <int N> inline void reg_dealloc() {}
 inline void sync_cta() { emu::sync_cta(); }
 inline void sync_named(int id, int nthreads) { emu::sync_named(id, nthreads); }
 

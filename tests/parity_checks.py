@@ -139,6 +139,26 @@ def check_gd_golden(make_engine, golden, name, precision):
     eng.close()
 
 
+def check_gd_vs_oracle(make_engine, shape, precision, kind="noise", loops=4, batch=1):
+    """Free-running GD against the oracle's restatement at an arbitrary plane shape (the golden fixtures only
+    hold a few shapes); with ``batch`` > 1 the same target is run in every plane of a batch."""
+    tol = TOL[precision]
+    t = targets(shape)[kind]
+    eng = make_engine(shape, precision, batch)
+    x0 = hl.host_initial_guess("random", t.shape, 42)
+    during, _ = hl.learning_rate_schedule(0.005, 0, loops)
+    tb = np.stack([t] * batch)
+    res, _ = eng.gd(tb, np.stack([x0] * batch), during, loops)
+    ref_h, ref_e, ref_errs, _ = P.gd_run(t, loops)
+    for b in range(batch):
+        e = res.errors[b]
+        assert len(e) == loops
+        assert np.max(np.abs(e - np.array(ref_errs)) / np.abs(ref_errs)) < tol["gd_curve"]
+        assert np.mean(circ(eng.to_host(res.hologram)[b], ref_h) < tol["gd_phase"]) >= 0.999
+        assert np.abs(eng.to_host(res.expected)[b] - ref_e).max() <= tol["gd_inten"] * ref_e.max()
+    eng.close()
+
+
 def check_gs_tolerance_and_batch(make_engine, precision):
     """Loop condition per plane (algorithms.py:29): planes of one batch stop independently, and a
     batched run equals the single-plane runs."""

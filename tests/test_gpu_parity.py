@@ -42,7 +42,7 @@ def test_native_library_is_the_compute_path():
     eng = make_engine((128, 128), "fp32", 1)
     n0 = eng.launch_count()
     eng.gs(synthetic.noise_target((128, 128)), 3)
-    assert eng.launch_count() - n0 == 2 + 1 + 1 + 3 + 2 + 1 + 1   # setup(2), row, max pre-pass, 3 col, 2 row, final row, intensity
+    assert eng.launch_count() - n0 == 2 + 1 + 1 + 3 + 2 + 1 + 2   # setup(2), row, max pre-pass, 3 col, 2 row, final row, intensity (transform kept + scaling)
     eng.close()
 
 
