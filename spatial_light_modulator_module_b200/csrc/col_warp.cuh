@@ -27,7 +27,7 @@ template <typename R, int H> struct ColWarpGeom {
     static constexpr int GROUP_THREADS = TC * M;                  // 256: eight warps, one per column
     static constexpr int COMPUTE = GROUPS * GROUP_THREADS;        // 512
     static constexpr int THREADS = COMPUTE + 128;                 // + service warpgroup: sequencer, 2 staging helpers, publisher
-    static constexpr int COPIERS = 96;                            // sequencer warp + helpers stage the 8-bit target rows
+    static constexpr int COPIERS = 64;                            // two helper warps stage the 8-bit target rows
     static constexpr int ROWB = TC * (int)sizeof(cpx<R>);
     static constexpr bool OK = sizeof(R) == 4 && H == 1024;
     static constexpr size_t TILE = (size_t)H * ROWB;              // 64 KB
@@ -37,15 +37,14 @@ template <typename R, int H> struct ColWarpGeom {
     static constexpr size_t OFF_LUT = OFF_GREY + NBUF * GREY;
     static constexpr size_t OFF_RED = OFF_LUT + 256 * sizeof(R);
     static constexpr size_t OFF_DESC = OFF_RED + NBUF * TC * sizeof(Partial);
-    static constexpr size_t OFF_ORDER = OFF_DESC + NBUF * 32;     // staging order of the sequencer to its helpers
-    static constexpr size_t OFF_BAR = OFF_ORDER + 32;
-    static constexpr size_t SMEM = OFF_BAR + 3 * NBUF * 32;
+    static constexpr size_t OFF_ORDER = OFF_DESC + NBUF * 32;     // [NBUF] staging orders of the sequencer to its helpers
+    static constexpr size_t OFF_BAR = OFF_ORDER + NBUF * 8;
+    static constexpr size_t SMEM = OFF_BAR + 4 * NBUF * 32;
     static_assert(!OK || SMEM <= 232448, "shared memory budget");
 };
 
 // What the sequencer tells the other warps about the tile in a buffer.
 struct TileDesc { long long g; double scale, imax, norm; };      // g < 0: no more tiles
-struct StageOrder { long long g; int s; };                       // g == -2: helpers leave
 
 // f(b): byte offset (inside the 1 KB that 16 rows x one 16-byte chunk span) of element b of a 32-element
 // run, laid out as 16-byte units on consecutive rows of the 64B-swizzled image.  XOR-linear in b.
@@ -132,6 +131,7 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
     TileBarrier* const full = reinterpret_cast<TileBarrier*>(raw + G::OFF_BAR);        // [NBUF] tile (and grey rows) landed
     TileBarrier* const done = reinterpret_cast<TileBarrier*>(raw + G::OFF_BAR + NBUF * 32);     // [NBUF] group is through the tile
     TileBarrier* const taken = reinterpret_cast<TileBarrier*>(raw + G::OFF_BAR + 2 * NBUF * 32); // [NBUF] publisher has the tile's sums
+    TileBarrier* const ordered = reinterpret_cast<TileBarrier*>(raw + G::OFF_BAR + 3 * NBUF * 32); // [NBUF] a staging order is posted
     auto tile_buf = [&](int s) { return raw + (size_t)s * G::TILE; };
     auto grey_buf = [&](int s) { return raw + G::OFF_GREY + (size_t)s * G::GREY; };
     auto bar = [](TileBarrier* base, int s) { return reinterpret_cast<TileBarrier*>(reinterpret_cast<unsigned char*>(base) + s * 32); };
@@ -146,6 +146,7 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
             mbar_init(bar(full, s), use_t8 ? 2u : 1u);
             mbar_init(bar(done, s), (unsigned)G::GROUP_THREADS);
             mbar_init(bar(taken, s), 1u);
+            mbar_init(bar(ordered, s), 1u);
         }
         mbar_fence_init();
     }
@@ -205,21 +206,23 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
         return;
     }
 
-    StageOrder* const order = reinterpret_cast<StageOrder*>(raw + G::OFF_ORDER);
-    auto stage_rows = [&](long long g, int s, int who) {     // the tile's 8-bit target rows -> grey_buf(s), by the 96 copiers
-        const int b = (int)(g / tiles), tile = (int)(g % tiles);
-        copy_grey_tile<TC, H, G::COPIERS>(a.T8 + (size_t)b * H * a.W + (size_t)tile * TC, (size_t)a.W, grey_buf(s), who);
-    };
+    long long* const order = reinterpret_cast<long long*>(raw + G::OFF_ORDER);       // [NBUF] tile whose target rows slot s wants
     if (t >= G::COMPUTE + 32) {
-        // ================= staging helpers: follow the sequencer's orders =================
+        // ================= staging helpers: the 8-bit target rows of every posted tile -> its grey buffer =================
+        // (off the sequencer's path: a tile's rows are requested as soon as its slot's previous tile is done,
+        //  and land while that tile's store drains and the new tile's TMA load is in flight)
         if (!use_t8) return;
-        for (;;) {
+        const int who = t - G::COMPUTE - 32;
+        int stops = 0;
+        for (unsigned k = 0; stops < G::GROUPS; ++k) {
+            const int s = (int)(k % NBUF);
+            mbar_wait(bar(ordered, s), (k / NBUF) & 1u);
+            const long long g = order[s];
+            if (g < 0) { ++stops; continue; }
+            const int b = (int)(g / tiles), tile = (int)(g % tiles);
+            copy_grey_tile<TC, H, G::COPIERS>(a.T8 + (size_t)b * H * a.W + (size_t)tile * TC, (size_t)a.W, grey_buf(s), who);
             sync_named(15, G::COPIERS);
-            const long long g = order->g;
-            const int s = order->s;
-            if (g < 0) break;
-            stage_rows(g, s, t - G::COMPUTE);
-            sync_named(14, G::COPIERS);
+            if (who == 0) mbar_arrive(bar(full, s));
         }
         return;
     }
@@ -243,12 +246,11 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
             TileDesc d; d.g = p.g < total ? p.g : -1; d.scale = p.scale; d.imax = p.imax; d.norm = p.norm;
             return d;
         };
+        // tell the helpers which tile's target rows slot s needs next (its grey buffer is free: the slot's tile is done)
         auto stage_grey = [&](int s, const TileDesc& d) {
-            if (!use_t8 || d.g < 0) return;
-            if (lane == 0) { order->g = d.g; order->s = s; }
-            sync_named(15, G::COPIERS);
-            stage_rows(d.g, s, lane);
-            sync_named(14, G::COPIERS);
+            if (!use_t8 || lane != 0) return;
+            order[s] = d.g;
+            mbar_arrive(bar(ordered, s));
         };
         // the buffer is free (its last tile stored and drained, its sums and descriptor taken): hand it over
         auto post = [&](int s, const TileDesc& d) {
@@ -256,12 +258,11 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
             desc[s] = d;
             if (d.g < 0) {                                   // stop marker: complete the phase without data
                 mbar_arrive(bar(full, s));
-                if (use_t8) mbar_arrive(bar(full, s));
+                if (use_t8) mbar_arrive(bar(full, s));       // (the helpers do not arrive for a stop marker)
                 return;
             }
             const int b = (int)(d.g / tiles), tile = (int)(d.g % tiles);
             tile_load(tm_in, tile_buf(s), bar(full, s), (long long)b * H, H, (long long)tile * ROWB, ROWB, (int)sizeof(R));
-            if (use_t8) mbar_arrive(bar(full, s));           // the grey rows were staged (and warp-synchronised) before
         };
         TileDesc cur = resolve(peek(blockIdx.x));
         unsigned k = 0;                                      // next item (tile or stop marker) to issue
@@ -296,7 +297,6 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
                 if (cur.g < 0) ++stops; else cur = resolve(ahead);
             }
         }
-        if (use_t8) { if (lane == 0) order->g = -2; sync_named(15, G::COPIERS); }     // dismiss the helpers
         if (lane == 0) tile_store_wait_all();
         return;
     }
