@@ -243,12 +243,16 @@ def run_b200(a):
     barrier()
     wall0 = time.time()
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
+    import gc
+    gc.collect()
+    gc.disable()          # a cyclic-GC pass of the interpreter in the middle of a step stalls the launch queue (seen: one 2x step per run)
     e0.record()
     for i in range(a.steps):
         q = step()
         marks[i].record()
     e1.record()
     barrier()
+    gc.enable()
     wall1 = time.time()
     ms = e0.elapsed_time(e1)
     step_ms = [round(([e0] + marks)[i].elapsed_time(marks[i]), 3) for i in range(a.steps)]

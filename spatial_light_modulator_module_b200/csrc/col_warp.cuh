@@ -1,10 +1,12 @@
-// Warp-per-column persistent Fourier-plane kernel (sm_100a) for 1024-point fp32 columns.
+// Warp-per-column persistent Fourier-plane kernel (sm_100a) for fp32 columns of 1024 and 768 points
+// (768 = the SLM height of the reference, constants.py:6).
 //
 // Why a second column kernel: the group kernel (col_groups.cuh) keeps 16 points per thread, so a column is
 // shared by two warps that meet at four named barriers per transform, and one CTA of 16 compute warps
 // (96 registers) is all an SM holds -- ncu shows it latency bound (issue slots ~30 % busy).  Here
 //   * ONE WARP owns a column: 1024 = 32 x 32, 32 points per lane, one lane<->register transpose per
-//     transform through shared memory, no barrier inside a transform (only __syncwarp);
+//     transform through shared memory, no barrier inside a transform (only __syncwarp); 768 = 32 lanes x 24
+//     points on the SLM-plane side <-> 24 lanes x 32 points on the Fourier-plane side;
 //   * the transpose is done IN PLACE in the tile buffer: the two warps of a column pair split the pair's
 //     16-byte chunk of the 64B-swizzled tile image by rows (512 rows each), which makes every exchange
 //     access a conflict-free 64-bit access (a single column alone only reaches half of the banks); the two
@@ -21,7 +23,9 @@
 namespace slm {
 
 template <typename R, int H> struct ColWarpGeom {
-    static constexpr int E = 32, M = 32;                          // points per lane, lanes per column
+    static constexpr int M = 32;                                  // lanes per column
+    static constexpr int RA = H / 32;                             // "side A" (tile order): lane j holds rows j + 32 p, p < RA
+                                                                  // "side B" (after a forward transform): lane j < RA holds rows j + RA k, k < 32
     static constexpr int TC = 8;                                  // columns per tile (64-byte rows)
     static constexpr int GROUPS = 2, NBUF = 3;
     static constexpr int GROUP_THREADS = TC * M;                  // 256: eight warps, one per column
@@ -29,7 +33,7 @@ template <typename R, int H> struct ColWarpGeom {
     static constexpr int THREADS = COMPUTE + 128;                 // + service warpgroup: sequencer, 2 staging helpers, publisher
     static constexpr int COPIERS = 64;                            // two helper warps stage the 8-bit target rows
     static constexpr int ROWB = TC * (int)sizeof(cpx<R>);
-    static constexpr bool OK = sizeof(R) == 4 && H == 1024;
+    static constexpr bool OK = sizeof(R) == 4 && (H == 1024 || H == 768);
     static constexpr size_t TILE = (size_t)H * ROWB;              // 64 KB
     static constexpr size_t GREY = (size_t)H * TC;                // 8 KB
     // [tile x3][grey x3][lut][red 3 x 8][desc x3][barriers]
@@ -50,22 +54,63 @@ struct TileDesc { long long g; double scale, imax, norm; };      // g < 0: no mo
 // run, laid out as 16-byte units on consecutive rows of the 64B-swizzled image.  XOR-linear in b.
 SLM_HOSTDEV constexpr unsigned xch_f(unsigned b) { return ((b >> 1) << 6) | (((b >> 2) & 3u) << 4) | ((b & 1u) << 3); }
 
-// v[r] *= w1^r, r = 1..31, powers formed in blocks of four so few of them are live at a time.
-template <typename R> SLM_DEV void twiddle_run32(cpx<R>* v, cpx<R> w1) {
-    const cpx<R> w2 = cmul(w1, w1), w3 = cmul(w2, w1), w4 = cmul(w2, w2);
-    v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3); v[4] = cmul(v[4], w4);
-    cpx<R> W = w4;
-#pragma unroll
-    for (int a = 1; a < 8; ++a) {
-        if (a > 1) { W = cmul(W, w4); v[4 * a] = cmul(v[4 * a], W); }
-        v[4 * a + 1] = cmul(v[4 * a + 1], cmul(W, w1));
-        v[4 * a + 2] = cmul(v[4 * a + 2], cmul(W, w2));
-        v[4 * a + 3] = cmul(v[4 * a + 3], cmul(W, w3));
+// ---- 24-point DFT on registers: natural order in, position 8 k1 + k2 holds X[k1 + 3 k2] on exit -------------
+// multiply by exp(DIR * 2 pi i * M / 24)
+template <int DIR, int M, typename R> SLM_DEV cpx<R> mul_w24(cpx<R> a) {
+    constexpr int m = ((M % 24) + 24) % 24;
+    if constexpr (m % 3 == 0) return mul_w16<DIR, 2 * (m / 3)>(a);          // multiples of 45 degrees
+    else {
+        constexpr double C24[24] = {1.0, 0.96592582628906828675, 0.86602540378443864676, 0.70710678118654752440, 0.5,
+                                    0.25881904510252076235, 0.0, -0.25881904510252076235, -0.5, -0.70710678118654752440,
+                                    -0.86602540378443864676, -0.96592582628906828675, -1.0, -0.96592582628906828675,
+                                    -0.86602540378443864676, -0.70710678118654752440, -0.5, -0.25881904510252076235, 0.0,
+                                    0.25881904510252076235, 0.5, 0.70710678118654752440, 0.86602540378443864676,
+                                    0.96592582628906828675};
+        constexpr double sn = C24[(m + 18) % 24];                            // sin(x) = cos(x - pi/2)
+        return cmul(a, mk<R>((R)C24[m], (R)(DIR < 0 ? -sn : sn)));
     }
+}
+template <int DIR, int N2, typename R> struct Dft24Twiddle {                // position 8 k1 + n2 *= W24^(n2 k1), k1 = 1, 2
+    static SLM_DEV void run(cpx<R>* v) {
+        v[8 + N2] = mul_w24<DIR, N2>(v[8 + N2]);
+        v[16 + N2] = mul_w24<DIR, 2 * N2>(v[16 + N2]);
+        if constexpr (N2 + 1 < 8) Dft24Twiddle<DIR, N2 + 1, R>::run(v);
+    }
+};
+template <int DIR, typename R> SLM_DEV void dft24(cpx<R>* v) {
+    // n = 8 n1 + n2, k = k1 + 3 k2:  X[k1 + 3 k2] = sum_n2 W8^(n2 k2) W24^(n2 k1) sum_n1 W3^(n1 k1) x[8 n1 + n2]
+#pragma unroll
+    for (int n2 = 0; n2 < 8; ++n2) dft3<DIR>(v[n2], v[8 + n2], v[16 + n2]);
+    Dft24Twiddle<DIR, 1, R>::run(v);
+    dft8<DIR>(v); dft8<DIR>(v + 8); dft8<DIR>(v + 16);
+}
+
+// Side-A register transform of a column of H = 32 RA points and the index its position p holds afterwards.
+template <int RA> SLM_HOSTDEV constexpr int side_a_index(int p) { return RA == 32 ? p : (p / 8 + 3 * (p % 8)); }
+template <int RA> SLM_HOSTDEV constexpr int side_a_position(int q) { return RA == 32 ? q : (8 * (q % 3) + q / 3); }
+template <int RA, int DIR, typename R> SLM_DEV void dft_side_a(cpx<R>* v) {
+    if constexpr (RA == 32) dft_small<32, DIR>(v); else dft24<DIR>(v);
+}
+
+// v[pos(q)] *= w1^q, q = 1..RA-1 (pos = side_a_position when PERMUTED, else identity); the powers are formed in
+// blocks of four so few of them are live at a time.
+template <int RA, bool PERMUTED, int Q, typename R> struct TwiddleRun {
+    static SLM_DEV void run(cpx<R>* v, const cpx<R>* w, cpx<R> W) {      // w[1..3] = w1^1..3, w[4] = w1^4, W = w1^(4 floor(Q/4))
+        constexpr int pos = PERMUTED ? side_a_position<RA>(Q) : Q;
+        if constexpr (Q % 4 == 0) { if constexpr (Q > 4) W = cmul(W, w[4]); v[pos] = cmul(v[pos], W); }
+        else if constexpr (Q < 4) v[pos] = cmul(v[pos], w[Q]);
+        else v[pos] = cmul(v[pos], cmul(W, w[Q % 4]));
+        if constexpr (Q + 1 < RA) TwiddleRun<RA, PERMUTED, Q + 1, R>::run(v, w, W);
+    }
+};
+template <int RA, bool PERMUTED, typename R> SLM_DEV void twiddle_run(cpx<R>* v, cpx<R> w1) {
+    cpx<R> w[5];
+    w[1] = w1; w[2] = cmul(w1, w1); w[3] = cmul(w[2], w1); w[4] = cmul(w[2], w[2]);
+    TwiddleRun<RA, PERMUTED, 1, R>::run(v, w, w[4]);
 }
 
 // Exchange accesses: address = (lane base ^ X) + OFF with X, OFF compile-time.  The XOR is issued inside the asm
-// statement so the 64 addresses of a transform are formed where they are used (one LOP3 each); left to the
+// statement so the addresses of a transform are formed where they are used (one LOP3 each); left to the
 // optimiser they are computed once per tile, kept across the two transforms and spilled to local memory.
 #if defined(__CUDA_ARCH__) && !defined(SLM_EMULATE)
 using XchBase = unsigned;                                        // shared-window address
@@ -86,30 +131,56 @@ inline XchBase xch_base(unsigned char* buf, unsigned off) { return XchBase{buf, 
 template <unsigned X, unsigned OFF, typename R> inline void xch_store(XchBase b, cpx<R> v) { *reinterpret_cast<cpx<R>*>(b.buf + ((b.off ^ X) + OFF)) = v; }
 template <unsigned X, unsigned OFF> inline cpx<float> xch_load(XchBase b) { return *reinterpret_cast<const cpx<float>*>(b.buf + ((b.off ^ X) + OFF)); }
 #endif
-template <int R0, int N> struct XchRun {
-    template <typename R> static SLM_DEV void store(XchBase b, const cpx<R>* v) {
-        xch_store<xch_f((unsigned)R0), 0u>(b, v[R0]);
-        if constexpr (R0 + 1 < N) XchRun<R0 + 1, N>::store(b, v);
+// The warp's exchange region holds a [32][32] array of slots (fewer rows or columns used for RA = 24); slot
+// (i, j) lives at element 32 i + (j ^ i), which makes a warp's access conflict free whether its lanes run over
+// i (LANE-major: address = lane base ^ f(j)) or over j (STEP-major: address = (lane base ^ f(i)) + 1024 i).
+template <int P, int N, int RA, bool PERMUTED> struct XchRun {
+    static constexpr unsigned C = (unsigned)(PERMUTED ? side_a_index<RA>(P) : P);        // the index position P holds
+    template <typename R> static SLM_DEV void store_step_major(XchBase b, const cpx<R>* v) {
+        xch_store<xch_f(C), 1024u * C>(b, v[P]);
+        if constexpr (P + 1 < N) XchRun<P + 1, N, RA, PERMUTED>::store_step_major(b, v);
     }
-    template <typename R> static SLM_DEV void load(XchBase b, cpx<R>* v) {
-        v[R0] = xch_load<xch_f((unsigned)R0), 1024u * R0>(b);
-        if constexpr (R0 + 1 < N) XchRun<R0 + 1, N>::load(b, v);
+    template <typename R> static SLM_DEV void store_lane_major(XchBase b, const cpx<R>* v) {
+        xch_store<xch_f(C), 0u>(b, v[P]);
+        if constexpr (P + 1 < N) XchRun<P + 1, N, RA, PERMUTED>::store_lane_major(b, v);
+    }
+    template <typename R> static SLM_DEV void load_step_major(XchBase b, cpx<R>* v) {
+        v[P] = xch_load<xch_f(C), 1024u * C>(b);
+        if constexpr (P + 1 < N) XchRun<P + 1, N, RA, PERMUTED>::load_step_major(b, v);
+    }
+    template <typename R> static SLM_DEV void load_lane_major(XchBase b, cpx<R>* v) {
+        v[P] = xch_load<xch_f(C), 0u>(b);
+        if constexpr (P + 1 < N) XchRun<P + 1, N, RA, PERMUTED>::load_lane_major(b, v);
     }
 };
 
-// One 1024-point transform held by a warp: v[r] = x[lane + 32 r] on entry, X[lane + 32 r] on exit.
-// xw / xr: this lane's write / read base inside the warp's exchange region of the tile buffer (1 KB aligned).
-template <int DIR, typename R>
-SLM_DEV void warp_fft1024(cpx<R>* v, unsigned char* buf, unsigned xw, unsigned xr, cpx<R> w1) {
-    dft_small<32, DIR>(v);                                       // over n2 = r: Y[n1 = lane][k2 = r]
+// Forward transform of a column of H = 32 RA points held by a warp.
+//   in : side A, v[p] = x[lane + 32 p], p < RA
+//   out: side B, v[k] = X[lane + RA k], k < 32, in lanes < RA
+// lm / sm: this lane's LANE-major / STEP-major base inside the warp's exchange region (1 KB aligned region).
+template <int RA, typename R>
+SLM_DEV void warp_fft_forward(cpx<R>* v, unsigned char* buf, unsigned lm, unsigned sm, cpx<R> w1) {
+    dft_side_a<RA, -1>(v);                                       // over n2 = p: Y[n1 = lane][k2 = idx(p)]
+    opaque(w1);                                                  // (or the powers are hoisted out of the tile loop and spilled)
+    twiddle_run<RA, true>(v, w1);                                // * W_H^(lane k2)
     sync_warp();                                                 // earlier reads of the region are complete
-    XchRun<0, 32>::store(xch_base(buf, xw), v);                  // element (lane, r) -> slot 32 lane + (r ^ lane)
+    XchRun<0, RA, RA, true>::store_step_major(xch_base(buf, sm), v);     // slot (k2, lane)
     sync_warp();
-    XchRun<0, 32>::load(xch_base(buf, xr), v);                   // slot 32 r + (lane ^ r) = element (r, lane)
-    if (DIR > 0) w1.y = -w1.y;
-    opaque(w1);                                                  // (or the 31 powers are hoisted out of the tile loop and spilled)
-    twiddle_run32(v, w1);                                        // Y[n1 = r][k2 = lane] * W^(r * lane)
-    dft_small<32, DIR>(v);                                       // over n1 = r: X[lane + 32 r]
+    XchRun<0, 32, RA, false>::load_lane_major(xch_base(buf, lm), v);     // slot (lane, r) = Y[n1 = r][k2 = lane]
+    dft_small<32, -1>(v);                                        // over n1 = r: X[lane + RA k1]
+}
+// Inverse transform (unnormalised): side B in, side A out with position p holding y[lane + 32 idx(p)].
+template <int RA, typename R>
+SLM_DEV void warp_fft_inverse(cpx<R>* v, unsigned char* buf, unsigned lm, unsigned sm, cpx<R> w1, bool active) {
+    dft_small<32, +1>(v);                                        // over n2' = k: Z[n1' = lane][k2' = k]
+    sync_warp();
+    if (active) XchRun<0, 32, RA, false>::store_lane_major(xch_base(buf, lm), v);        // slot (lane, k2'), lanes < RA
+    sync_warp();
+    XchRun<0, RA, RA, false>::load_step_major(xch_base(buf, sm), v);     // slot (r, lane) = Z[n1' = r][k2' = lane]
+    w1.y = -w1.y;
+    opaque(w1);
+    twiddle_run<RA, false>(v, w1);                               // * conj(W_H)^(r lane)
+    dft_side_a<RA, +1>(v);                                       // over n1' = r: y[lane + 32 k1'], k1' = idx(p)
 }
 
 template <typename R, int H, int MODE>
@@ -302,17 +373,25 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
     }
 
     // ================= compute warps: one column each =================
+    constexpr int RA = G::RA;
     const int grp = t / G::GROUP_THREADS;
     const int c = (t % G::GROUP_THREADS) / 32, lane = t % 32;
     const int pair = c >> 1, half = c & 1;
+    const bool active = RA == 32 || lane < RA;                      // side B lives in the first RA lanes
     const int pair_bar = 1 + grp * (TC / 2) + pair;                  // named barrier of the column pair (64 threads)
-    // byte offset of (row lane + 32 r, column c) in the swizzled tile image = my + 2048 r
+    // byte offset of (row, column c) in the swizzled tile image: side A row lane + 32 p -> my + 2048 p;
+    // side B row lane + RA k -> my + 64 RA k (RA is a multiple of 8, so the swizzle term is the lane's in both)
     const unsigned my = (unsigned)lane * 64u + (((unsigned)c * 8u) ^ ((((unsigned)lane >> 1) & 3u) << 4));
-    // exchange region of this warp: rows [512 half, 512 half + 512) of the pair's 16-byte chunk
-    const unsigned xw = 32768u * half + 1024u * lane + (xch_f((unsigned)lane) ^ ((unsigned)pair << 4));
-    const unsigned xr = 32768u * half + (xch_f((unsigned)lane) ^ ((unsigned)pair << 4));
-    const cpx<R> w1 = ld_const(static_cast<const cpx<R>*>(a.tw) + lane);       // exp(-2 pi i lane / 1024)
+    // exchange region of this warp: its half of the rows of the pair's 16-byte chunk
+    const unsigned region = (unsigned)(H / 2) * 64u * half;
+    const unsigned lm = region + 1024u * lane + (xch_f((unsigned)lane) ^ ((unsigned)pair << 4));
+    const unsigned sm = region + (xch_f((unsigned)lane) ^ ((unsigned)pair << 4));
+    const cpx<R> w1 = ld_const(static_cast<const cpx<R>*>(a.tw) + lane);       // exp(-2 pi i lane / H)
+    // (a run-time 0 the assembler cannot see through: the exchange addresses of the second transform are formed
+    //  afresh instead of being kept -- in local memory -- from the first one)
     const unsigned zero = (unsigned)a.B >> 31;
+    constexpr bool IN_B = MODE == CGM_GD_POST;                       // the tile already holds a transformed field
+    constexpr bool OUT_B = MODE == CGM_STATS_KEEP;                   // the transformed field goes back as it is
     cpx<R> v[32];
     for (unsigned k = (unsigned)grp;; k += G::GROUPS) {
         const int s = (int)(k % NBUF);
@@ -322,13 +401,18 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
         const TileDesc d = desc[s];
         if (d.g < 0) break;
         const int b = (int)(d.g / tiles), tile = (int)(d.g % tiles);
+        const bool inverse_only = MODE == CGM_COMPLEX && ga.mode_inverse;
+        if (IN_B || inverse_only) {
 #pragma unroll
-        for (int r = 0; r < 32; ++r) v[r] = *reinterpret_cast<const cpx<R>*>(buf + my + 2048u * r);
+            for (int q = 0; q < 32; ++q) v[q] = *reinterpret_cast<const cpx<R>*>(buf + my + 64u * RA * q);
+        } else {
+#pragma unroll
+            for (int p = 0; p < RA; ++p) v[p] = *reinterpret_cast<const cpx<R>*>(buf + my + 2048u * p);
+        }
         sync_named(pair_bar, 64);                            // the partner holds its column too: the pair's chunk is free
-        if (MODE == CGM_COMPLEX && ga.mode_inverse) warp_fft1024<+1>(v, buf, xw, xr, w1);
-        else if (MODE != CGM_GD_POST) warp_fft1024<-1>(v, buf, xw, xr, w1);
+        if (!IN_B && !inverse_only) warp_fft_forward<RA>(v, buf, lm, sm, w1);
 
-        // ---- pointwise step and per-thread sums (see col_group_kernel) ----
+        // ---- pointwise step and per-thread sums on side B (see col_group_kernel) ----
         R mx = 0, sa = 0, sb = 0, sc = 0;
         if (MODE == CGM_GS || IS_GD) {
             const R s0r = (R)d.scale;
@@ -340,12 +424,15 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
                 R tv[8], aux[8];
                 if (use_t8) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) { const int gl = gsrc[(size_t)(r0 + i) * 32 * TC]; tv[i] = (R)gl; aux[i] = lut_s[gl]; }
+                    for (int i = 0; i < 8; ++i) { const int gl = gsrc[(size_t)(r0 + i) * RA * TC]; tv[i] = (R)gl; aux[i] = lut_s[gl]; }
                 } else {
                     const R* T = static_cast<const R*>(a.Treal) + goff;
                     const R* Q = static_cast<const R*>(a.plane2) + goff;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) { tv[i] = ld_ro(T + (size_t)(r0 + i) * 32 * a.W); aux[i] = ld_ro(Q + (size_t)(r0 + i) * 32 * a.W); }
+                    for (int i = 0; i < 8; ++i) {
+                        tv[i] = active ? ld_ro(T + (size_t)(r0 + i) * RA * a.W) : (R)0;
+                        aux[i] = active ? ld_ro(Q + (size_t)(r0 + i) * RA * a.W) : (R)0;
+                    }
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -372,17 +459,25 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
             for (int r = 0; r < 32; ++r) v[r] = cscale(v[r], sc_out);
         }
         if (HAS_STATS) {                                     // this column's sums -> shared memory, for the publisher
+            if (!active) { mx = 0; sa = 0; sb = 0; sc = 0; }             // lanes outside side B hold no points
             Partial p; p.mx = (double)mx; p.a = (double)sa; p.b = (double)sb; p.c = (double)sc;
             p = warp_reduce<FIELDS>(p);
             if (lane == 0) red[s * TC + c] = p;             // (the sequencer reissued this slot only after its sums were taken)
         }
-        // (+ zero: a run-time 0 the assembler cannot see through, so the exchange addresses of the second transform
-        //  are formed afresh instead of being kept -- in local memory -- from the first one)
-        if (MODE == CGM_GS || IS_GD) warp_fft1024<+1>(v, buf, xw + zero, xr + zero, w1);
+        constexpr bool SECOND = MODE == CGM_GS || IS_GD;
+        if (SECOND) warp_fft_inverse<RA>(v, buf, lm + zero, sm + zero, w1, active);
+        else if (inverse_only) warp_fft_inverse<RA>(v, buf, lm, sm, w1, active);
         if (HAS_OUT) {
             sync_named(pair_bar, 64);                        // the partner is through its exchange: its rows of my column are free
+            if (OUT_B || (MODE == CGM_COMPLEX && !inverse_only)) {
+                if (active) {
 #pragma unroll
-            for (int r = 0; r < 32; ++r) *reinterpret_cast<cpx<R>*>(buf + my + 2048u * r) = v[r];
+                    for (int q = 0; q < 32; ++q) *reinterpret_cast<cpx<R>*>(buf + my + 64u * RA * q) = v[q];
+                }
+            } else {
+#pragma unroll
+                for (int p = 0; p < RA; ++p) *reinterpret_cast<cpx<R>*>(buf + my + 2048u * side_a_index<RA>(p)) = v[p];
+            }
             fence_async_smem();
         }
         mbar_arrive(bar(done, s));

@@ -34,20 +34,22 @@ def test_gs_device_setup(kind, precision):
     pc.check_gs_device_setup(make_engine, (128, 128), precision, kind)
 
 
-# 1024-point fp32 columns run on the warp-per-column kernel (col_warp.cuh): every mode of it, several tiles per
-# CTA (the emulated grid has 3 CTAs), both compute groups, a batch, the stop markers
+# fp32 columns of 1024 and 768 points run on the warp-per-column kernel (col_warp.cuh): every mode of it, several
+# tiles per CTA (the emulated grid has 3 CTAs), both compute groups, a batch, the stop markers
+@pytest.mark.parametrize("rows", [1024, 768])
 @pytest.mark.parametrize("kind", ["noise", "shapes"])
-def test_warp_column_kernel_gs(kind):
-    pc.check_gs_teacher_forced(make_engine, (1024, 64), "fp32", kind, steps=(0, 2))
+def test_warp_column_kernel_gs(kind, rows):
+    pc.check_gs_teacher_forced(make_engine, (rows, 64), "fp32", kind, steps=(0, 2))
 
 
-def test_warp_column_kernel_gs_device_setup():
-    pc.check_gs_device_setup(make_engine, (1024, 64), "fp32", "noise", loops=3)
+@pytest.mark.parametrize("rows", [1024, 768])
+def test_warp_column_kernel_gs_device_setup(rows):
+    pc.check_gs_device_setup(make_engine, (rows, 64), "fp32", "noise", loops=3)
 
 
-@pytest.mark.parametrize("batch", [1, 2])
-def test_warp_column_kernel_gd(batch):
-    pc.check_gd_vs_oracle(make_engine, (1024, 64), "fp32", "noise", loops=3, batch=batch)
+@pytest.mark.parametrize("rows,batch", [(1024, 1), (1024, 2), (768, 2)])
+def test_warp_column_kernel_gd(rows, batch):
+    pc.check_gd_vs_oracle(make_engine, (rows, 64), "fp32", "noise", loops=3, batch=batch)
 
 
 GD_CASES = ["gd_noise_random_128x128", "gd_shapes_fourier_192x256", "gd_traps_unsettle_128x128",
