@@ -42,7 +42,8 @@ template <typename R, int H> struct ColWarpGeom {
     static constexpr size_t OFF_RED = OFF_LUT + 256 * sizeof(R);
     static constexpr size_t OFF_DESC = OFF_RED + NBUF * TC * sizeof(Partial);
     static constexpr size_t OFF_ORDER = OFF_DESC + NBUF * 32;     // [NBUF] staging orders of the sequencer to its helpers
-    static constexpr size_t OFF_BAR = OFF_ORDER + NBUF * 8;
+    static constexpr size_t OFF_FMX = OFF_ORDER + NBUF * 8;       // CGM_GD_FUSED: [NBUF][TC] column maxima, [NBUF] plane max
+    static constexpr size_t OFF_BAR = OFF_FMX + NBUF * (TC + 2) * 4;
     static constexpr size_t SMEM = OFF_BAR + 4 * NBUF * 32;
     static_assert(!OK || SMEM <= 232448, "shared memory budget");
 };
@@ -188,9 +189,10 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((ColWarpGeom<R, H>::THREADS), 1)
 col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SLM_GRID_CONSTANT TileMap tm_out) {
     using G = ColWarpGeom<R, H>;
     constexpr int TC = G::TC, ROWB = G::ROWB, NBUF = G::NBUF;
-    constexpr bool HAS_T = MODE == CGM_GS || MODE == CGM_GD || MODE == CGM_GD_POST;
+    constexpr bool FUSED = MODE == CGM_GD_FUSED;
+    constexpr bool HAS_T = MODE == CGM_GS || MODE == CGM_GD || MODE == CGM_GD_POST || FUSED;
     constexpr bool HAS_OUT = MODE != CGM_STATS;
-    constexpr bool IS_GD = MODE == CGM_GD || MODE == CGM_GD_POST;
+    constexpr bool IS_GD = MODE == CGM_GD || MODE == CGM_GD_POST || FUSED;
     constexpr bool IS_STATS = MODE == CGM_STATS || MODE == CGM_STATS_KEEP;
     constexpr bool HAS_STATS = MODE != CGM_COMPLEX;
     constexpr int FIELDS = MODE == CGM_GS ? F_ALL : (IS_GD ? F_A : F_MX);
@@ -266,6 +268,11 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
                         st->imax = tot.mx; st->scale = sN;
                     } else {
                         err = tot.a / hw;                                // algorithms.py:92
+                        if (FUSED) {                                     // every tile of the plane has used the max: record and re-arm
+                            const double pm = (double)__uint_as_float(ld_cg(a.fused_max + b));
+                            st->imax = pm; st->scale = d.norm / pm;
+                            a.fused_max[b] = 0u; a.fused_count[b] = 0u;
+                        }
                     }
                     const int it = st->iters;
                     a.err_curve[(size_t)b * a.max_loops + it] = err;
@@ -412,11 +419,36 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
         sync_named(pair_bar, 64);                            // the partner holds its column too: the pair's chunk is free
         if (!IN_B && !inverse_only) warp_fft_forward<RA>(v, buf, lm, sm, w1);
 
+        // ---- CGM_GD_FUSED: max |F|^2 of the whole plane (algorithms.py:86), across the CTAs holding its tiles ----
+        double plane_max = d.imax;
+        if (FUSED) {
+            R m = 0;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) m = fmax(m, cnorm2(v[r]));
+            if (!active) m = 0;
+#pragma unroll
+            for (int sh = 16; sh >= 1; sh >>= 1) m = fmax(m, shfl_xor(m, sh));
+            float* const fmx = reinterpret_cast<float*>(raw + G::OFF_FMX) + s * (TC + 2);
+            if (lane == 0) fmx[c] = m;
+            sync_named(9 + grp, G::GROUP_THREADS);
+            if (c == 0 && lane == 0) {
+                float mm = fmx[0];
+#pragma unroll
+                for (int i = 1; i < TC; ++i) mm = fmax(mm, fmx[i]);
+                atomic_max_u32(a.fused_max + b, __float_as_uint(mm));       // |F|^2 >= 0: ordered like its bit pattern
+                fence_device();
+                atomic_add_u32(a.fused_count + b, 1u);
+                while (ld_acquire(a.fused_count + b) < (unsigned)tiles) {}   // the plane's other tiles are in flight on other SMs
+                fmx[TC] = __uint_as_float(ld_cg(a.fused_max + b));
+            }
+            sync_named(9 + grp, G::GROUP_THREADS);
+            plane_max = (double)fmx[TC];
+        }
         // ---- pointwise step and per-thread sums on side B (see col_group_kernel) ----
         R mx = 0, sa = 0, sb = 0, sc = 0;
         if (MODE == CGM_GS || IS_GD) {
             const R s0r = (R)d.scale;
-            const R gdk = (R)(d.norm / d.imax);
+            const R gdk = (R)(d.norm / plane_max);
             const uint8_t* gsrc = grey_buf(s) + (size_t)lane * TC + c;
             const size_t goff = (size_t)b * H * a.W + (size_t)lane * a.W + tile * TC + c;
 #pragma unroll

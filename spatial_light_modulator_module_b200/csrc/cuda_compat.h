@@ -51,6 +51,9 @@ SLM_DEV void fence_device() { __threadfence(); }
 SLM_DEV void fence_block() { __threadfence_block(); }
 SLM_DEV unsigned atomic_add_shared(unsigned* p, unsigned v) { return atomicAdd(p, v); }
 SLM_DEV unsigned atomic_inc_wrap(unsigned* p, unsigned limit) { return atomicInc(p, limit); }
+SLM_DEV unsigned atomic_max_u32(unsigned* p, unsigned v) { return atomicMax(p, v); }
+SLM_DEV unsigned atomic_add_u32(unsigned* p, unsigned v) { return atomicAdd(p, v); }
+SLM_DEV unsigned ld_acquire(const unsigned* p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 SLM_DEV float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 SLM_DEV double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 SLM_DEV unsigned shfl_idx(unsigned v, int src) { return __shfl_sync(0xffffffffu, v, src); }

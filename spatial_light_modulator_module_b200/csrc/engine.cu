@@ -44,6 +44,8 @@ struct slm_ctx {
     PlaneStats* stats = nullptr;
     Partial* partial = nullptr;
     unsigned* counter = nullptr;
+    unsigned* fused = nullptr;                            // [2][max_batch]: plane max bits, tile count of CGM_GD_FUSED
+    int fused_ctas = 0;                                   // grid of the fused GD column pass (0: two passes)
     double *err_curve = nullptr, *lr = nullptr, *norm = nullptr;
     void* lut = nullptr;
     float* lut32 = nullptr;
@@ -165,6 +167,17 @@ static int setup_groups(slm_ctx* c) {
     c->persist_ctas = sms > 0 ? sms : 1;
 #endif
     c->use_groups = true;
+#ifndef SLM_EMULATE
+    // One fused Fourier-plane pass per GD iteration needs every tile of a plane on an SM at the same time: grid = a
+    // whole number of planes' tiles, all CTAs resident (one per SM).  Worth it when that grid fills most of the device.
+    // (The host emulation runs one CTA at a time and keeps the two-pass form.)
+    const char* ck = getenv("SLM_COL_KERNEL");
+    const int tiles = c->W / c->col->cols_per_cta;
+    if (c->col->group_fused && !(ck && ck[0] == 'g') && !getenv("SLM_NO_FUSED_GD") && tiles <= c->persist_ctas) {
+        const int grid = tiles * (c->persist_ctas / tiles);
+        if (5 * grid >= 4 * c->persist_ctas) c->fused_ctas = grid;
+    }
+#endif
     return 0;
 }
 
@@ -194,8 +207,10 @@ static int launch_group(slm_ctx* c, int mode, int batch, const ColArgs* loop, co
 #endif
     ga.c.B = batch; ga.c.W = c->W; ga.c.stats = c->stats; ga.c.partial = c->partial; ga.c.counter = c->counter;
     ga.c.norm = c->norm; ga.c.tw = c->tw_col;
+    ga.c.fused_max = c->fused; ga.c.fused_count = c->fused + c->max_batch;
+    const int ctas = mode == CGM_GD_FUSED ? c->fused_ctas : c->persist_ctas;
     const int kind = (mode == CGM_STATS || mode == CGM_STATS_KEEP) ? K_COL_STATS : (mode == CGM_COMPLEX ? K_COL_PLAIN : K_COL_PASS);
-    SLM_TIMED(kind, c->col->col_group(mode, ga, &c->map_x, map_out ? map_out : &c->map_x, c->persist_ctas, c->stream));
+    SLM_TIMED(kind, c->col->col_group(mode, ga, &c->map_x, map_out ? map_out : &c->map_x, ctas, c->stream));
     return 0;
 }
 
@@ -250,6 +265,7 @@ extern "C" int slm_ctx_create(slm_ctx** out, int device, int H, int W, int max_b
     A((void**)&c->stats, (size_t)max_batch * sizeof(PlaneStats));
     A((void**)&c->partial, (size_t)max_batch * tmax * sizeof(Partial));
     A((void**)&c->counter, (size_t)max_batch * sizeof(unsigned));
+    A((void**)&c->fused, 2 * (size_t)max_batch * sizeof(unsigned));
     A((void**)&c->norm, (size_t)max_batch * sizeof(double));
     A(&c->lut, 256 * real_size(precision));
     A((void**)&c->lut32, 256 * sizeof(float));
@@ -260,6 +276,7 @@ extern "C" int slm_ctx_create(slm_ctx** out, int device, int H, int W, int max_b
     if (!rc) rc = ensure_loops(c, 256);
     if (!rc) rc = setup_groups(c);
     if (!rc && cudaMemset(c->counter, 0, (size_t)max_batch * sizeof(unsigned)) != cudaSuccess) rc = fail(SLM_ERR_CUDA, "cudaMemset(counter)");
+    if (!rc && cudaMemset(c->fused, 0, 2 * (size_t)max_batch * sizeof(unsigned)) != cudaSuccess) rc = fail(SLM_ERR_CUDA, "cudaMemset(fused)");
     if (!rc && cudaMemset(c->stats, 0, (size_t)max_batch * sizeof(PlaneStats)) != cudaSuccess) rc = fail(SLM_ERR_CUDA, "cudaMemset(stats)");
     if (rc) { std::string keep = g_err; slm_ctx_destroy(c); g_err = keep; return rc; }
     *out = c;
@@ -325,6 +342,7 @@ static int begin_run(slm_ctx* c, int batch, const double* norm, int max_loops) {
     choose_pdl(c, batch);
     SLM_TRY(ensure_loops(c, max_loops));
     SLM_CUDA(cudaMemsetAsync(c->stats, 0, (size_t)batch * sizeof(PlaneStats), c->stream));
+    if (c->fused) SLM_CUDA(cudaMemsetAsync(c->fused, 0, 2 * (size_t)c->max_batch * sizeof(unsigned), c->stream));
     if (norm) SLM_CUDA(cudaMemcpyAsync(c->norm, norm, (size_t)batch * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     return 0;
 }
@@ -469,8 +487,16 @@ extern "C" int slm_gd_run(slm_ctx* c, int batch, const uint8_t* T8, const void* 
     ca.err_curve = c->err_curve; ca.max_loops = max_loops; ca.tolerance = tolerance;
     ca.inv_hw = ra.inv_hw; ca.tw = c->tw_col;
     ra.source = ROW_FROM_Y;
+    // The fused pass saves a launch and a trip of the field through L2/HBM per iteration, but its CTAs wait for each
+    // other once per plane and it leaves the SMs beyond a whole number of planes idle: measured faster for a few
+    // planes (latency bound: 2.9 vs 3.3 ms per 100-iteration hologram), slower for a large batch (47.9 vs 46.4 ms).
+    const bool fused = c->use_groups && c->fused_ctas && (long long)batch * (c->W / c->col->cols_per_cta) <= 4LL * c->persist_ctas;
     for (int k = 0; k < max_loops; ++k) {
-        if (c->use_groups) {
+        if (fused) {
+            // one Fourier-plane pass: the tiles of a plane agree on amax(output_unnormed) (algorithms.py:86) between
+            // their forward transforms and the gradient step
+            SLM_TRY(launch_group(c, CGM_GD_FUSED, batch, &ca, &c->map_y, 0, 1.0));
+        } else if (c->use_groups) {
             // med_output = fft2(...) is finished in place in X while its max is taken (algorithms.py:84-86),
             // so the gradient pass starts from the transformed field
             SLM_TRY(launch_group(c, CGM_STATS_KEEP, batch, nullptr, &c->map_x, 0, 1.0));
@@ -485,7 +511,9 @@ extern "C" int slm_gd_run(slm_ctx* c, int batch, const uint8_t* T8, const void* 
     SLM_TIMED(K_ROW_PASS, c->row->row_pass(ALG_GD, ra, c->stream));
     if (expected_out) {
         PlainColArgs ia = stats_args(c, batch, OUT_INTENSITY_GD, expected_out);
-        ia.skip_fft = c->use_groups ? 1 : 0;       // X already holds med_output
+        // two-pass form: X already holds med_output; fused form: transform X once more (same kernel arithmetic), kept
+        if (fused) SLM_TRY(launch_group(c, CGM_STATS_KEEP, batch, nullptr, &c->map_x, 0, 1.0, 1));
+        ia.skip_fft = c->use_groups ? 1 : 0;
         SLM_TIMED(K_COL_PLAIN, c->col->col_plain(ia, c->stream));
     }
     return 0;

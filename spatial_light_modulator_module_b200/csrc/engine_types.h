@@ -64,6 +64,8 @@ struct ColArgs {
     double tolerance;
     double inv_hw;
     const void* tw;          // complex<R> [H] column twiddles
+    unsigned* fused_max;     // CGM_GD_FUSED: [B] bit pattern of the running max |F|^2 of the plane (0 between launches)
+    unsigned* fused_count;   // CGM_GD_FUSED: [B] tiles of the plane that have contributed (0 between launches)
 };
 
 // ---- warp-specialised persistent column kernel (col_groups.cuh) ---------------------------------------
@@ -74,6 +76,9 @@ enum ColGroupMode {
     CGM_COMPLEX = 3,  // plain transform, complex out  (== col_plain_kernel OUT_COMPLEX)
     CGM_STATS_KEEP = 4,  // CGM_STATS that also writes the transformed field back (GD: F = fft2(b) kept in X)
     CGM_GD_POST = 5,     // CGM_GD on an already transformed field: no forward transform
+    CGM_GD_FUSED = 6,    // CGM_GD that takes the plane's max ITSELF: every tile of a plane is in flight at once (grid = a
+                         // multiple of the tiles per plane, all CTAs resident), tiles meet at a per-plane counter between
+                         // the forward transform and the pointwise step (warp-per-column kernel only)
 };
 struct ColGroupArgs {
     int mode_inverse;        // CGM_COMPLEX: transform direction
@@ -149,6 +154,7 @@ struct LineTable {
     int (*col_plain)(const PlainColArgs&, cudaStream_t);
     // warp-specialised persistent column kernel (col_groups.cuh); group_ok == 0: not built for this length
     int group_ok, group_row_bytes;
+    int group_fused;         // CGM_GD_FUSED is available (col_warp.cuh serves this length and precision)
     int (*col_group)(int mode, const ColGroupArgs&, const void* map_in, const void* map_out, int ctas, cudaStream_t);
     int (*row_fourier)(const RowFourierArgs&, cudaStream_t);     // fp32/fp64 GS Fourier-plane step on rows
     int rows_only;                                               // long lines (>= 8192): no column kernels

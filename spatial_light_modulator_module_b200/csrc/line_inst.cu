@@ -32,7 +32,7 @@ const LineTable SLM_TABLE_NAME(SLM_LINE_L, SLM_LINE_PREC) = {
     Rows::RG::NR, Rows::RG::THREADS, Rows::RG::SMEM,
     Cols::CG::TC, Cols::CG::THREADS, Cols::CG::SMEM,
     &prepare_, &row_pass_, &row_plain_, &col_pass_, &col_plain_,
-    Cols::GG::OK ? 1 : 0, Cols::GG::ROWB, &col_group_,
+    Cols::GG::OK ? 1 : 0, Cols::GG::ROWB, (Cols::GG::OK && ColWarpGeom<LineReal, SLM_LINE_L>::OK) ? 1 : 0, &col_group_,
     &row_fourier_, 0,
 };
 #else
@@ -43,7 +43,7 @@ const LineTable SLM_TABLE_NAME(SLM_LINE_L, SLM_LINE_PREC) = {
     Rows::RG::NR, Rows::RG::THREADS, Rows::RG::SMEM,
     0, 0, 0,
     &prepare_, &row_pass_, &row_plain_, nullptr, nullptr,
-    0, 0, nullptr,
+    0, 0, 0, nullptr,
     &row_fourier_, 1,
 };
 #endif

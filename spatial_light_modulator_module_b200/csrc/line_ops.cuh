@@ -15,6 +15,7 @@ template <typename R, int L, bool OK = ColGroupGeom<R, L>::OK> struct GroupLaunc
 template <typename R, int L, bool WARP = ColWarpGeom<R, L>::OK> struct ColWarpLaunch {
     static void prepare() {}
     static bool launch(int, const ColGroupArgs&, const TileMap&, const TileMap&, int, cudaStream_t) { return false; }
+    static bool enabled() { return false; }
 };
 template <typename R, int L> struct ColWarpLaunch<R, L, true> {
     using WG = ColWarpGeom<R, L>;
@@ -22,7 +23,7 @@ template <typename R, int L> struct ColWarpLaunch<R, L, true> {
         cudaFuncSetAttribute(col_warp_kernel<R, L, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG::SMEM);
     }
     static void prepare() {
-        attr<CGM_GS>(); attr<CGM_GD>(); attr<CGM_STATS>(); attr<CGM_COMPLEX>(); attr<CGM_STATS_KEEP>(); attr<CGM_GD_POST>();
+        attr<CGM_GS>(); attr<CGM_GD_FUSED>(); attr<CGM_STATS>(); attr<CGM_COMPLEX>(); attr<CGM_STATS_KEEP>(); attr<CGM_GD_POST>();
     }
     static bool enabled() {
         static const bool on = !(getenv("SLM_COL_KERNEL") && getenv("SLM_COL_KERNEL")[0] == 'g');
@@ -33,7 +34,8 @@ template <typename R, int L> struct ColWarpLaunch<R, L, true> {
         const long long tiles = (long long)ga.c.B * (ga.c.W / WG::TC);
         const dim3 grid((unsigned)(tiles < ctas ? tiles : ctas)), block(WG::THREADS);
         if (mode == CGM_GS) SLM_LAUNCH_PDL((col_warp_kernel<R, L, CGM_GS>), grid, block, WG::SMEM, s, ga, in, out);
-        else if (mode == CGM_GD) SLM_LAUNCH_PDL((col_warp_kernel<R, L, CGM_GD>), grid, block, WG::SMEM, s, ga, in, out);
+        else if (mode == CGM_GD_FUSED) SLM_LAUNCH_PDL((col_warp_kernel<R, L, CGM_GD_FUSED>), grid, block, WG::SMEM, s, ga, in, out);
+        else if (mode == CGM_GD) return false;              // (unused by the engine: the column-group kernel keeps it)
         else if (mode == CGM_STATS) SLM_LAUNCH_PDL((col_warp_kernel<R, L, CGM_STATS>), grid, block, WG::SMEM, s, ga, in, out);
         else if (mode == CGM_STATS_KEEP) SLM_LAUNCH_PDL((col_warp_kernel<R, L, CGM_STATS_KEEP>), grid, block, WG::SMEM, s, ga, in, out);
         else if (mode == CGM_GD_POST) SLM_LAUNCH_PDL((col_warp_kernel<R, L, CGM_GD_POST>), grid, block, WG::SMEM, s, ga, in, out);
@@ -57,6 +59,7 @@ template <typename R, int L> struct GroupLaunch<R, L, true> {
         static_assert(!ColWarpGeom<R, L>::OK || (ColWarpGeom<R, L>::TC == GG::TC && ColWarpGeom<R, L>::ROWB == GG::ROWB),
                       "both column kernels must share the tile maps and the per-tile partial sums");
         if (ColWarpLaunch<R, L>::launch(mode, ga, in, out, ctas, s)) return 0;
+        if (mode == CGM_GD_FUSED) return -1;                 // only the warp-per-column kernel has it
         const long long tiles = (long long)ga.c.B * (ga.c.W / GG::TC);
         const dim3 grid((unsigned)(tiles < ctas ? tiles : ctas)), block(GG::THREADS);
         if (mode == CGM_GS) SLM_LAUNCH_PDL((col_group_kernel<R, L, CGM_GS>), grid, block, GG::SMEM, s, ga, in, out);

@@ -219,6 +219,13 @@ inline void fence_device() {}
 inline void fence_block() {}
 inline unsigned atomic_add_shared(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 inline unsigned atomic_inc_wrap(unsigned* p, unsigned limit) { unsigned o = *p; *p = (o >= limit) ? 0 : o + 1; return o; }
+inline unsigned atomic_max_u32(unsigned* p, unsigned v) { unsigned o = *p; if (v > o) *p = v; return o; }
+inline unsigned atomic_add_u32(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
+inline unsigned ld_acquire(const unsigned* p) { return *p; }
+}  // namespace slm
+inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+namespace slm {
 inline float shfl_xor(float v, int m) { return emu::shfl_xor(v, m); }
 inline double shfl_xor(double v, int m) { return emu::shfl_xor(v, m); }
 inline unsigned shfl_idx(unsigned v, int src) { return emu::shfl_idx(v, src); }

@@ -125,6 +125,38 @@ def test_gd_full_size_curve_fp32(golden):
     assert np.abs(exp[sub] - g["expected_sub"]).max() < 1e-3 * g["expected_sub"].max()   # north star: 1e-3
 
 
+@pytest.mark.parametrize("shape", [(1024, 1024), (768, 1024), (1024, 512)])
+def test_gd_fused_fourier_pass_vs_oracle(shape):
+    """fp32 columns of 1024 / 768 points: the warp-per-column kernel, GD with the plane max taken inside ONE
+    Fourier-plane pass (every tile of a plane in flight at once) -- against the oracle, in a batch."""
+    pc.check_gd_vs_oracle(make_engine, shape, "fp32", "noise", loops=5, batch=3)
+
+
+def test_gd_fused_equals_two_pass():
+    """The fused pass and the two-pass form (max pass that keeps the transform + gradient pass) run the same
+    arithmetic: identical curves and holograms.  The two-pass library instance lives in a child process."""
+    import subprocess, sys, os, tempfile
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "from spatial_light_modulator_module_b200.engine import Engine\n"
+        "from spatial_light_modulator_module_b200 import synthetic, host_logic as hl\n"
+        "shape=(1024,1024); eng=Engine(shape,'fp32',2)\n"
+        "t=np.stack([synthetic.noise_target(shape,seed=i) for i in range(2)])\n"
+        "x0=np.stack([hl.host_initial_guess('random',shape,42)]*2)\n"
+        "during,_=hl.learning_rate_schedule(0.005,0,6)\n"
+        "r,_=eng.gd(t,x0,during,6)\n"
+        "np.savez(sys.argv[1], e=np.array(r.errors), h=eng.to_host(r.hologram), x=eng.to_host(r.expected))\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, env in (("fused", {}), ("two_pass", {"SLM_NO_FUSED_GD": "1"})):
+            path = os.path.join(tmp, name + ".npz")
+            subprocess.run([sys.executable, "-c", code, path], check=True, env={**os.environ, **env}, timeout=600)
+            out[name] = dict(np.load(path))
+    for k in ("e", "h", "x"):
+        np.testing.assert_array_equal(out["fused"][k], out["two_pass"][k])
+
+
 def test_gs_traps_full_size_from_reference_phasor(golden):
     """Trap movie frame (768x1024, 50 iterations): free-running from the reference's first phasor."""
     g = golden("gs_traps_768x1024_curves")
