@@ -128,9 +128,11 @@ class ClockSampler:
             nv, h = self.nv, self.h
             while not self._stop:
                 try:
-                    self.samples.append((time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
-                                         nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM),
-                                         nv.nvmlDeviceGetCurrentClocksEventReasons(h), nv.nvmlDeviceGetPowerUsage(h) / 1000.0))
+                    t_s = time.time()
+                    row = (t_s, nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
+                           nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM),
+                           nv.nvmlDeviceGetCurrentClocksEventReasons(h), nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                    self.samples.append(row + (time.time() - t_s,))
                 except Exception as exc:
                     self.err = str(exc)
                     return
@@ -147,7 +149,8 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "no samples"]}
         reasons = sorted(k for k, bit in self.THROTTLE.items() if any(r[3] & bit for r in rows))
         return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": float(max(r[2] for r in rows)),
-                "reasons": reasons, "samples": len(rows), "power_w_max": max(r[4] for r in rows), "source": "nvml"}
+                "reasons": reasons, "samples": len(rows), "power_w_max": max(r[4] for r in rows), "source": "nvml",
+                "sample_ms_max": round(1e3 * max(r[5] for r in rows), 2)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -233,26 +236,26 @@ def run_b200(a):
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("SLM_BENCH_NO_SAMPLER"):
         sampler.start()
+    # Warm-up steps keep their result alive exactly like the timed ones (`q = step()`): the previous frame is still
+    # referenced while the next one is allocated, so the caching allocator needs TWO output blocks -- left to the
+    # timed region, the second one cost a cudaMalloc (2-70 ms) in its second step.
+    q = None
     for _ in range(max(a.warmup, 3)):
-        step()
+        q = step()
     barrier()
     n0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     wall0 = time.time()
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
-    import gc
-    gc.collect()
-    gc.disable()          # a cyclic-GC pass of the interpreter in the middle of a step stalls the launch queue (seen: one 2x step per run)
     e0.record()
     for i in range(a.steps):
         q = step()
         marks[i].record()
     e1.record()
     barrier()
-    gc.enable()
     wall1 = time.time()
     ms = e0.elapsed_time(e1)
     step_ms = [round(([e0] + marks)[i].elapsed_time(marks[i]), 3) for i in range(a.steps)]
@@ -364,6 +367,7 @@ def run_b200(a):
         ns.learning_rate = 0.005
         return display_holograms.hologram_to_grey(holo, host_mask, 256), errs
     e2e_once(host_targets[-1])
+    e2e_once(host_targets[-1])             # (second warm-up: the engine page-locks a host array it is handed twice -- the mask)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for i in range(a.e2e_steps):

@@ -67,7 +67,7 @@ def gerchberg_saxton(demanded_output, args):
     else:
         res = eng.gs(target, int(args.max_loops), float(args.tolerance), inc_amp=inc)
         errors = [np.float64(e) for e in res.errors[0]]
-        hologram, expected = eng.to_host(res.hologram)[0], eng.to_host(res.expected)[0]
+        hologram, expected = (a[0] for a in eng.to_host_many([res.hologram, res.expected]))
     _progress(len(errors), args.max_loops)
     if args.print_info:
         print()
@@ -95,7 +95,7 @@ def gradient_descent(demanded_output, args):
         res, _x = eng.gd(target, x0, during, int(args.max_loops), float(args.tolerance),
                          white_attention=args.white_attention, inc_amp=inc)
         errors = [np.float64(e) for e in res.errors[0]]
-        hologram, expected = eng.to_host(res.hologram)[0], eng.to_host(res.expected)[0]
+        hologram, expected = (a[0] for a in eng.to_host_many([res.hologram, res.expected]))
     args.learning_rate = after[len(errors)]
     _progress(len(errors), args.max_loops)
     if args.print_info:

@@ -86,13 +86,17 @@ class Engine:
 
     def _mem_upload(self, array: np.ndarray):
         torch = self._torch
-        host = torch.from_numpy(np.ascontiguousarray(array))
+        array = np.ascontiguousarray(array)
+        host = torch.from_numpy(array)
+        nbytes = host.numel() * host.element_size()
         with torch.cuda.stream(self._stream):
-            if host.numel() * host.element_size() >= (1 << 20) and host.is_pinned():
-                dev = host.to(self._dev, non_blocking=True)            # e.g. a hologram returned by to_host(): no staging copy
+            if nbytes >= (1 << 20) and (host.is_pinned() or _page_lock_if_reused(torch, array)):
+                # page-locked already (a result of to_host(), or a caller's array seen before, e.g. the one
+                # wavefront-correction mask every frame is added to): DMA straight from it, no staging copy
+                dev = host.to(self._dev, non_blocking=True)
                 self._stream.synchronize()
                 return dev
-            if (1 << 20) <= host.numel() * host.element_size() <= (1 << 30):   # large planes: stage through pinned memory
+            if (1 << 20) <= nbytes <= (1 << 30):                     # large planes: stage through pinned memory
                 pinned = torch.empty(host.shape, dtype=host.dtype, pin_memory=True)
                 pinned.copy_(host)
                 dev = pinned.to(self._dev, non_blocking=True)
@@ -117,6 +121,19 @@ class Engine:
             host.copy_(buf, non_blocking=True)
         self._stream.synchronize()
         return host.numpy()
+
+    def _mem_download_many(self, bufs):
+        """Several device buffers -> host arrays with one synchronisation."""
+        torch = self._torch
+        small = [b for b in bufs if not ((1 << 20) <= b.numel() * b.element_size() <= (1 << 30))]
+        if small:
+            return [self._mem_download(b) for b in bufs]
+        with torch.cuda.stream(self._stream):
+            hosts = [torch.empty(b.shape, dtype=b.dtype, pin_memory=True) for b in bufs]
+            for h, b in zip(hosts, bufs):
+                h.copy_(b, non_blocking=True)
+        self._stream.synchronize()
+        return [h.numpy() for h in hosts]
 
     def _mem_np_dtype(self, buf):
         return np.dtype(str(buf.dtype).replace("torch.", ""))
@@ -376,6 +393,9 @@ class Engine:
     def to_host(self, buf) -> Optional[np.ndarray]:
         return None if buf is None else self._mem_download(buf)
 
+    def to_host_many(self, bufs):
+        return self._mem_download_many(list(bufs))
+
     KINDS = ("row_pass", "col_pass", "col_stats", "row_plain", "col_plain", "elementwise")
 
     def profile(self, enable: bool) -> None:
@@ -405,6 +425,49 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+
+# Host arrays a caller passes again and again (same memory) are page-locked in place on their second use, so later
+# uploads skip the staging copy.  The registration ends when the array that owns the memory is collected.
+_SEEN_ONCE = {}
+_LOCKED = {}
+_LOCK_BUDGET = 1 << 30
+
+
+def _page_lock_if_reused(torch, array: np.ndarray) -> bool:
+    import weakref
+    owner = array
+    while isinstance(getattr(owner, "base", None), np.ndarray):
+        owner = owner.base
+    if not isinstance(owner, np.ndarray) or owner.base is not None or not owner.flags.owndata:
+        return False                                    # memory owned by something we cannot watch
+    key = (array.ctypes.data, array.nbytes)
+    if key in _LOCKED:
+        return True
+    if _SEEN_ONCE.pop(key, None) != id(owner):
+        if len(_SEEN_ONCE) > 64:
+            _SEEN_ONCE.clear()
+        _SEEN_ONCE[key] = id(owner)
+        return False
+    if sum(n for _, n in _LOCKED) + array.nbytes > _LOCK_BUDGET:
+        return False
+    rt = torch.cuda.cudart()
+    try:
+        res = rt.cudaHostRegister(array.ctypes.data, array.nbytes, 0)
+        if int(getattr(res, "value", res)) != 0:
+            return False
+    except Exception:
+        return False
+    _LOCKED[key] = True
+
+    def release(k=key, ptr=array.ctypes.data):
+        if _LOCKED.pop(k, None):
+            try:
+                rt.cudaHostUnregister(ptr)
+            except Exception:
+                pass
+    weakref.finalize(owner, release)
+    return True
 
 
 def _numel(buf) -> int:

@@ -58,6 +58,9 @@ class EmuEngine(Engine):
     def _mem_download(self, buf):
         return np.asarray(buf).copy()
 
+    def _mem_download_many(self, bufs):
+        return [self._mem_download(b) for b in bufs]
+
     def _mem_np_dtype(self, buf):
         return buf.dtype
 
