@@ -186,7 +186,7 @@ def run_reference(a):
     value = sample_loops * a.steps / total
     sample = (f"each step = 1 hologram x {sample_loops} iterations of the numpy restatement (oracle/numpy_port.py) "
               f"incl. setup, scipy.fft workers={cores}")
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": "GS/GD iterations/sec at 1024^2", "value": value, "unit": "iterations/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -400,7 +400,7 @@ def run_b200(a):
         "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof,
         "iteration_roofline": iteration_roofline, "kernels": kernels, "single_hologram": single, "movie_config3_sample": movie, "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -445,7 +445,7 @@ def run_slab(a):
         c = 8 if a.precision == "fp32" else 16
         it_bytes = (8 * c + 4) * n * n
         per_it = ms * 1e-3 / (a.steps * loops)
-        print(json.dumps({
+        emit(({
             "metric": f"GS iterations/sec on one {n}^2 plane (slab-decomposed)", "value": 1.0 / per_it, "unit": "iterations/s",
             "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 1), "ms_per_step": ms / a.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32" if a.precision == "fp32" else "f64", "data": "synthetic",
@@ -461,8 +461,19 @@ def run_slab(a):
         dist.destroy_process_group()
 
 
+def emit(line: dict) -> None:
+    """The ONE JSON line of this run, on the process's real stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
 if __name__ == "__main__":
     args = parse()
+    # libraries (NCCL's version banner, ...) write to file descriptor 1: keep it for the JSON line alone
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "slab":
