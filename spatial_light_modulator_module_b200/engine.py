@@ -396,6 +396,60 @@ class Engine:
     def to_host_many(self, bufs):
         return self._mem_download_many(list(bufs))
 
+    def to_host_into(self, buf, out: np.ndarray):
+        """Start copying a device buffer into the host array ``out`` (same shape and dtype) while the engine's
+        stream goes on with other work; returns a handle whose ``join()`` waits for the copy."""
+        return self._mem_download_into(buf, out)
+
+    def _mem_download_into(self, buf, out):
+        import threading
+        torch = self._torch
+        if not out.flags.c_contiguous or out.dtype != self._mem_np_dtype(buf) or tuple(out.shape) != tuple(buf.shape):
+            raise ValueError("to_host_into: destination must be a C-contiguous array of the buffer's shape and dtype")
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(self._dev)
+        side = self._copy_stream
+        ready = torch.cuda.Event()
+        ready.record(self._stream)                       # everything that produced `buf`
+        buf.record_stream(side)
+
+        dst = torch.from_numpy(out)
+        if dst.is_pinned():                              # page-locked destination (host_empty): a plain asynchronous DMA
+            with torch.cuda.stream(side):
+                side.wait_event(ready)
+                dst.copy_(buf, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(side)
+
+            class Copy:
+                def join(self_inner):
+                    done.synchronize()
+            return Copy()
+
+        def work():
+            with torch.cuda.device(self._dev), torch.cuda.stream(side):
+                side.wait_event(ready)
+                dst.copy_(buf)                           # device -> host array directly (the driver stages pageable memory)
+                side.synchronize()
+        th = threading.Thread(target=work, daemon=True)
+        th.start()
+        return th
+
+    def host_empty(self, shape, dtype) -> np.ndarray:
+        """Host array for results that are read back with :meth:`to_host_into`: page-locked (from PyTorch's caching
+        host allocator, so repeated calls neither pin nor page-fault again) up to ``SLM_PINNED_RESULT_BYTES``
+        (default 2 GiB), ordinary memory beyond."""
+        return self._mem_host_empty(shape, dtype)
+
+    def _mem_host_empty(self, shape, dtype):
+        import os
+        torch = self._torch
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        if nbytes == 0 or nbytes > int(os.environ.get("SLM_PINNED_RESULT_BYTES", 2 << 30)):
+            return np.empty(shape, dtype=dtype)
+        tdt = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32, np.dtype(np.uint8): torch.uint8}[np.dtype(dtype)]
+        return torch.empty(tuple(shape), dtype=tdt, pin_memory=True).numpy()
+
     KINDS = ("row_pass", "col_pass", "col_stats", "row_plain", "col_plain", "elementwise")
 
     def profile(self, enable: bool) -> None:

@@ -49,16 +49,22 @@ def sequence_holograms(frames, max_loops: int, tolerance: float = 0.0, precision
         eng = get_engine(shape, precision, batch)
     else:
         eng = engine_factory(shape, precision, batch)
-    holos = np.empty((n_local,) + shape, dtype=np.float64)
-    exps = np.empty((n_local,) + shape, dtype=np.float64) if want_expected else None
+    holos = eng.host_empty((n_local,) + shape, np.float64)
+    exps = eng.host_empty((n_local,) + shape, np.float64) if want_expected else None
     errors: List[np.ndarray] = []
+    # the read-back of one batch (float64: 8 bytes per pixel and frame) runs beside the iterations of the next one
+    pending = []
     for s in range(0, n_local, batch):
         e = min(s + batch, n_local)
         res = eng.gs(frames[lo + s:lo + e], max_loops, tolerance, want_expected=want_expected)
-        holos[s:e] = eng.to_host(res.hologram)
+        for job in pending:
+            job.join()
+        pending = [eng.to_host_into(res.hologram, holos[s:e])]
         if want_expected:
-            exps[s:e] = eng.to_host(res.expected)
+            pending.append(eng.to_host_into(res.expected, exps[s:e]))
         errors.extend(res.errors)
+    for job in pending:
+        job.join()
     if dist and world > 1 and gather:
         holos, exps, errors = _gather_to_root(dist, frames.shape[0], shape, holos, exps, errors, max_loops)
         if rank == 0:

@@ -58,6 +58,17 @@ class EmuEngine(Engine):
     def _mem_download(self, buf):
         return np.asarray(buf).copy()
 
+    def _mem_host_empty(self, shape, dtype):
+        return np.empty(shape, dtype=dtype)
+
+    def _mem_download_into(self, buf, out):
+        np.copyto(out, np.asarray(buf))
+
+        class Done:
+            def join(self):
+                pass
+        return Done()
+
     def _mem_download_many(self, bufs):
         return [self._mem_download(b) for b in bufs]
 
