@@ -388,7 +388,7 @@ def run_b200(a):
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / a.e2e_steps
     csz = 8 if a.precision == "fp32" else 16
-    h2d = npx * (1 + (csz if a.alg == "gd" else 0)) + npx * 8 + npx * 8     # target, x0, hologram + mask for the quantiser
+    h2d = npx * 1 + npx * 8 + npx * 8     # target; hologram + mask for the quantiser (the GD initial guess is drawn on the device)
     d2h = npx * 8 * 2 + a.loops * 8 + npx                                    # hologram, expected, error curve, grey frame
     e2e = {"value": a.loops / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "ms_per_hologram": 1e3 * e2e_s, "holograms_per_s": 1 / e2e_s,

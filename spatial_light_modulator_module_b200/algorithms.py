@@ -81,7 +81,7 @@ def gradient_descent(demanded_output, args):
     target = np.asarray(demanded_output)
     inc = _illumination(args, target.shape)
     eng = _engine(target.shape, args)
-    inc_amp = np.ones(target.shape) if inc is None else inc
+    inc_amp = np.float64(1.0) if inc is None else inc        # (uniform illumination: make_initial_guess takes a scalar too)
     x0 = make_initial_guess(args.initial_guess, inc_amp, target, args.random_seed, _engine_hint=eng, _device=True)
     if args.print_info:
         print("computing hologram")

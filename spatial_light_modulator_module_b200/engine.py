@@ -90,7 +90,7 @@ class Engine:
         host = torch.from_numpy(array)
         nbytes = host.numel() * host.element_size()
         with torch.cuda.stream(self._stream):
-            if nbytes >= (1 << 20) and (host.is_pinned() or _page_lock_if_reused(torch, array)):
+            if nbytes >= (1 << 20) and (host.is_pinned() or (nbytes >= _LOCK_MIN and _page_lock_if_reused(torch, array))):
                 # page-locked already (a result of to_host(), or a caller's array seen before, e.g. the one
                 # wavefront-correction mask every frame is added to): DMA straight from it, no staging copy
                 dev = host.to(self._dev, non_blocking=True)
@@ -486,6 +486,7 @@ class Engine:
 _SEEN_ONCE = {}
 _LOCKED = {}
 _LOCK_BUDGET = 1 << 30
+_LOCK_MIN = 4 << 20           # cudaHostRegister costs ~2 ms whatever the size: not worth it for small arrays
 
 
 def _page_lock_if_reused(torch, array: np.ndarray) -> bool:

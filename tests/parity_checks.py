@@ -159,10 +159,44 @@ def check_gd_vs_oracle(make_engine, shape, precision, kind="noise", loops=4, bat
     eng.close()
 
 
-def check_gs_tolerance_and_batch(make_engine, precision):
+def check_gd_tolerance_and_batch(make_engine, precision, shape=(128, 128), loops=8):
+    """GD loop condition per plane (algorithms.py:83): the planes of one batch stop independently and every plane
+    equals its single-plane run (error curve, hologram, expected outcome) bit for bit."""
+    tt = targets(shape)
+    order = ["noise", "shapes", "traps"]
+    eng = make_engine(shape, precision, 3)
+    x0 = hl.host_initial_guess("random", shape, 42)
+    during, _ = hl.learning_rate_schedule(0.005, 0, loops)
+    singles = {}
+    for k in order:
+        r, _ = eng.gd(tt[k], x0.copy(), during, loops)
+        singles[k] = (r.errors[0], eng.to_host(r.hologram)[0], eng.to_host(r.expected)[0])
+    e_mid = singles["shapes"][0]
+    tol = float(0.5 * (e_mid[loops // 2 - 1] + e_mid[loops // 2]))      # GD errors fall monotonically here: "shapes" stops midway
+    res, _ = eng.gd(np.stack([tt[k] for k in order]), np.stack([x0] * 3), during, loops, tol)
+    holo, exp = eng.to_host(res.hologram), eng.to_host(res.expected)
+    stops = []
+    for i, k in enumerate(order):
+        ref_err = singles[k][0]
+        below = ~(ref_err > tol)
+        stop = int(np.argmax(below)) + 1 if np.any(below) else loops
+        stops.append(stop)
+        assert len(res.errors[i]) == stop == res.iterations[i]
+        np.testing.assert_array_equal(res.errors[i], ref_err[:stop])
+        if stop == loops:
+            np.testing.assert_array_equal(holo[i], singles[k][1])
+            np.testing.assert_array_equal(exp[i], singles[k][2])
+        else:                                            # equals a run of exactly `stop` iterations
+            r2, _ = eng.gd(tt[k], x0.copy(), during[:stop], stop)
+            np.testing.assert_array_equal(eng.to_host(r2.hologram)[0], holo[i])
+            np.testing.assert_array_equal(eng.to_host(r2.expected)[0], exp[i])
+    assert min(stops) < loops
+    eng.close()
+
+
+def check_gs_tolerance_and_batch(make_engine, precision, shape=(128, 128)):
     """Loop condition per plane (algorithms.py:29): planes of one batch stop independently, and a
     batched run equals the single-plane runs."""
-    shape = (128, 128)
     tt = targets(shape)
     st = {k: P.gs_setup(v) for k, v in tt.items()}
     B0 = {k: P.gs_first_phasor(s) for k, s in st.items()}

@@ -52,6 +52,16 @@ def test_warp_column_kernel_gd(rows, batch):
     pc.check_gd_vs_oracle(make_engine, (rows, 64), "fp32", "noise", loops=3, batch=batch)
 
 
+def test_warp_column_kernel_tolerance_and_batch():
+    pc.check_gs_tolerance_and_batch(make_engine, "fp32", shape=(1024, 64))
+    pc.check_gd_tolerance_and_batch(make_engine, "fp32", shape=(768, 64), loops=6)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_gd_tolerance_and_batch(precision):
+    pc.check_gd_tolerance_and_batch(make_engine, precision)
+
+
 GD_CASES = ["gd_noise_random_128x128", "gd_shapes_fourier_192x256", "gd_traps_unsettle_128x128",
             "gd_noise_wa2int_128x128", "gd_noise_wa05_128x128", "gd_shapes_old_128x128",
             "gd_shapes_unnormed_128x128", "gd_shapes_zeros_128x128", "gd_shapes_ones_128x128",

@@ -81,6 +81,18 @@ def test_gs_tolerance_and_batch(precision):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_gd_tolerance_and_batch(precision):
+    pc.check_gd_tolerance_and_batch(make_engine, precision)
+
+
+@pytest.mark.parametrize("shape", [(1024, 128), (768, 1024), (1024, 1024)])
+def test_warp_column_kernel_tolerance_and_batch(shape):
+    """Planes that stop early inside a batch, on the warp-per-column kernel (GS) and its fused GD pass."""
+    pc.check_gs_tolerance_and_batch(make_engine, "fp32", shape=shape)
+    pc.check_gd_tolerance_and_batch(make_engine, "fp32", shape=shape, loops=6)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
 def test_gs_real_valued_targets(golden, precision):
     pc.check_gs_real_targets(make_engine, golden, precision)
 
