@@ -184,6 +184,57 @@ SLM_DEV void warp_fft_inverse(cpx<R>* v, unsigned char* buf, unsigned lm, unsign
     dft_side_a<RA, +1>(v);                                       // over n1' = r: y[lane + 32 k1'], k1' = idx(p)
 }
 
+// Close a plane's Fourier-plane pass from the total of its tiles' sums (one thread): max and scale, error,
+// iteration count, loop condition.  s0 / norm: the plane's scale and norm as the tiles used them.
+template <typename R, int H, int MODE>
+SLM_DEV void close_plane(const ColArgs& a, int b, const Partial& tot, double s0, double norm) {
+    constexpr bool IS_STATS = MODE == CGM_STATS || MODE == CGM_STATS_KEEP;
+    PlaneStats* st = a.stats + b;
+    const double hw = (double)H * (double)a.W;
+    if (IS_STATS) {
+        st->imax = tot.mx; st->scale = norm / tot.mx;
+        return;
+    }
+    double err;
+    if (MODE == CGM_GS) {
+        const double sN = norm / tot.mx;                 // algorithms.py:37
+        const double s0u = (double)(R)s0;                // the scale the tiles actually used
+        const double dl = (s0u != 0.0) ? sN / s0u - 1.0 : 0.0;
+        err = (tot.a + 2.0 * dl * tot.b + dl * dl * tot.c) / hw;   // == sum((s*I - T)^2)/HW, :38,:162
+        st->imax = tot.mx; st->scale = sN;
+    } else {
+        err = tot.a / hw;                                // algorithms.py:92
+        if (MODE == CGM_GD_FUSED) {                      // every tile of the plane has used the max: record and re-arm
+            const double pm = (double)__uint_as_float(ld_cg(a.fused_max + b));
+            st->imax = pm; st->scale = norm / pm;
+            a.fused_max[b] = 0u; a.fused_count[b] = 0u;
+        }
+    }
+    const int it = st->iters;
+    a.err_curve[(size_t)b * a.max_loops + it] = err;
+    st->err = err; st->iters = it + 1;
+    st->done = !(err > a.tolerance);                     // loop condition, algorithms.py:29,83
+}
+
+// The planes' closing as a kernel of its own (ColGroupArgs::defer_close): one warp per plane sums the tiles'
+// partial sums in the order collect_if_last uses, so both forms give the same bits.
+template <typename R, int H, int MODE>
+SLM_GLOBAL void SLM_LAUNCH_BOUNDS(32, 1) close_planes_kernel(ColGroupArgs ga) {
+    constexpr bool IS_GD = MODE == CGM_GD || MODE == CGM_GD_POST || MODE == CGM_GD_FUSED;
+    constexpr int FIELDS = MODE == CGM_GS ? F_ALL : (IS_GD ? F_A : F_MX);
+    const ColArgs& a = ga.c;
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const int tiles = a.W / ColWarpGeom<R, H>::TC;
+    griddep_wait();
+    PlaneStats* st = a.stats + b;
+    if (!ga.all_planes && ld_cg(&st->done) != 0) return;         // the pass skipped this plane
+    const Partial* plane_partials = a.partial + (size_t)b * tiles;
+    Partial q; q.mx = 0; q.a = 0; q.b = 0; q.c = 0;
+    for (int i = lane; i < tiles; i += 32) q = combine<FIELDS>(q, ld_partial(plane_partials + i));
+    const Partial tot = warp_reduce<FIELDS>(q);
+    if (lane == 0) close_plane<R, H, MODE>(a, b, tot, ld_cg(&st->scale), ld_ro(a.norm + b));
+}
+
 template <typename R, int H, int MODE>
 SLM_GLOBAL void SLM_LAUNCH_BOUNDS((ColWarpGeom<R, H>::THREADS), 1)
 col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SLM_GRID_CONSTANT TileMap tm_out) {
@@ -250,36 +301,16 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
             if (lane < TC) q = red[s * TC + lane];
             q = warp_reduce<FIELDS>(q);                      // (also: every lane holds its copy before the slot is released)
             if (lane == 0) mbar_arrive(bar(taken, s));
-            PlaneStats* st = a.stats + b;
             Partial* plane_partials = a.partial + (size_t)b * tiles;
+            if (ga.defer_close) {                            // the closing kernel behind this launch sums the tiles
+                if (lane == 0) plane_partials[tile] = q;
+                continue;
+            }
             unsigned ticket = 0;
             if (lane == 0) ticket = publish_partial(q, plane_partials, tile, tiles, a.counter + b);
             Partial tot;
-            if (collect_if_last<FIELDS>(ticket, lane, plane_partials, tiles, tot) && lane == 0) {
-                if (IS_STATS) {
-                    st->imax = tot.mx; st->scale = d.norm / tot.mx;
-                } else {
-                    double err;
-                    if (MODE == CGM_GS) {
-                        const double sN = d.norm / tot.mx;               // algorithms.py:37
-                        const double s0u = (double)(R)d.scale;           // the scale the tiles actually used
-                        const double dl = (s0u != 0.0) ? sN / s0u - 1.0 : 0.0;
-                        err = (tot.a + 2.0 * dl * tot.b + dl * dl * tot.c) / hw;   // == sum((s*I - T)^2)/HW, :38,:162
-                        st->imax = tot.mx; st->scale = sN;
-                    } else {
-                        err = tot.a / hw;                                // algorithms.py:92
-                        if (FUSED) {                                     // every tile of the plane has used the max: record and re-arm
-                            const double pm = (double)__uint_as_float(ld_cg(a.fused_max + b));
-                            st->imax = pm; st->scale = d.norm / pm;
-                            a.fused_max[b] = 0u; a.fused_count[b] = 0u;
-                        }
-                    }
-                    const int it = st->iters;
-                    a.err_curve[(size_t)b * a.max_loops + it] = err;
-                    st->err = err; st->iters = it + 1;
-                    st->done = !(err > a.tolerance);                     // loop condition, algorithms.py:29,83
-                }
-            }
+            if (collect_if_last<FIELDS>(ticket, lane, plane_partials, tiles, tot) && lane == 0)
+                close_plane<R, H, MODE>(a, b, tot, d.scale, d.norm);
         }
         return;
     }
@@ -443,6 +474,8 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
             }
             sync_named(9 + grp, G::GROUP_THREADS);
             plane_max = (double)fmx[TC];
+#pragma unroll
+            for (int r = 0; r < 32; ++r) opaque(v[r]);       // (or the 32 |F|^2 above are kept -- spilled -- for the step below)
         }
         // ---- pointwise step and per-thread sums on side B (see col_group_kernel) ----
         R mx = 0, sa = 0, sb = 0, sc = 0;

@@ -202,6 +202,10 @@ static int launch_group(slm_ctx* c, int mode, int batch, const ColArgs* loop, co
     ColGroupArgs ga{};
     if (loop) ga.c = *loop;
     ga.mode_inverse = inverse; ga.scale = scale; ga.all_planes = all_planes;
+    // large batches: the planes are closed by a kernel behind the pass (see ColGroupArgs::defer_close); a few planes
+    // keep the in-kernel closing, which costs no extra launch
+    ga.defer_close = (mode != CGM_COMPLEX && mode != CGM_GD_FUSED && !getenv("SLM_NO_DEFER_CLOSE") &&
+                      (long long)batch * (c->W / c->col->cols_per_cta) > 4LL * c->persist_ctas) ? 1 : 0;
 #ifdef SLM_TRACE
     if (mode == g_trace_mode) { ga.trace = g_trace; g_trace_mode = -1; }      // trace the next launch of that mode only
 #endif

@@ -83,6 +83,9 @@ enum ColGroupMode {
 struct ColGroupArgs {
     int mode_inverse;        // CGM_COMPLEX: transform direction
     int all_planes;          // 1: also planes whose loop has ended (the transform kept for the final intensity pass)
+    int defer_close;         // 1: the pass only stores its tiles' partial sums; a one-warp-per-plane kernel launched behind it
+                             // closes the planes' iteration (warp-per-column kernel, large batches: keeps fences and atomics
+                             // out of the tile pipeline)
     double scale;            // CGM_COMPLEX: output scale
     unsigned long long* trace;   // -DSLM_TRACE builds: [ctas][64 tiles][16 events] globaltimer stamps, else null
     ColArgs c;               // loop arguments; B, W, stats, partial, counter, norm, tw are used by every mode

@@ -29,17 +29,24 @@ template <typename R, int L> struct ColWarpLaunch<R, L, true> {
         static const bool on = !(getenv("SLM_COL_KERNEL") && getenv("SLM_COL_KERNEL")[0] == 'g');
         return on;
     }
+    template <int MODE> static void run(int mode, const ColGroupArgs& ga, const TileMap& in, const TileMap& out, dim3 grid, dim3 block,
+                                        cudaStream_t s) {
+        if (mode != MODE) return;
+        SLM_LAUNCH_PDL((col_warp_kernel<R, L, MODE>), grid, block, WG::SMEM, s, ga, in, out);
+        if (MODE != CGM_COMPLEX && ga.defer_close)
+            SLM_LAUNCH((close_planes_kernel<R, L, MODE>), dim3((unsigned)ga.c.B), dim3(32), 0, s, ga);
+    }
     static bool launch(int mode, const ColGroupArgs& ga, const TileMap& in, const TileMap& out, int ctas, cudaStream_t s) {
         if (!enabled()) return false;
         const long long tiles = (long long)ga.c.B * (ga.c.W / WG::TC);
         const dim3 grid((unsigned)(tiles < ctas ? tiles : ctas)), block(WG::THREADS);
-        if (mode == CGM_GS) SLM_LAUNCH_PDL((col_warp_kernel<R, L, CGM_GS>), grid, block, WG::SMEM, s, ga, in, out);
-        else if (mode == CGM_GD_FUSED) SLM_LAUNCH_PDL((col_warp_kernel<R, L, CGM_GD_FUSED>), grid, block, WG::SMEM, s, ga, in, out);
-        else if (mode == CGM_GD) return false;              // (unused by the engine: the column-group kernel keeps it)
-        else if (mode == CGM_STATS) SLM_LAUNCH_PDL((col_warp_kernel<R, L, CGM_STATS>), grid, block, WG::SMEM, s, ga, in, out);
-        else if (mode == CGM_STATS_KEEP) SLM_LAUNCH_PDL((col_warp_kernel<R, L, CGM_STATS_KEEP>), grid, block, WG::SMEM, s, ga, in, out);
-        else if (mode == CGM_GD_POST) SLM_LAUNCH_PDL((col_warp_kernel<R, L, CGM_GD_POST>), grid, block, WG::SMEM, s, ga, in, out);
-        else SLM_LAUNCH_PDL((col_warp_kernel<R, L, CGM_COMPLEX>), grid, block, WG::SMEM, s, ga, in, out);
+        run<CGM_GS>(mode, ga, in, out, grid, block, s);
+        run<CGM_GD_FUSED>(mode, ga, in, out, grid, block, s);
+        run<CGM_STATS>(mode, ga, in, out, grid, block, s);
+        run<CGM_STATS_KEEP>(mode, ga, in, out, grid, block, s);
+        run<CGM_GD_POST>(mode, ga, in, out, grid, block, s);
+        run<CGM_COMPLEX>(mode, ga, in, out, grid, block, s);
+        if (mode == CGM_GD) return false;                    // (unused by the engine: the column-group kernel keeps it)
         return true;
     }
 };
