@@ -34,7 +34,7 @@ SLM_DEV void trace_stamp(unsigned long long* buf, bool who, unsigned k, int ev) 
 constexpr int lines_per_group(int m) { return m % 32 == 0 ? 1 : (m % 16 == 0 ? 2 : (m % 8 == 0 ? 4 : 8)); }
 
 template <typename R, int H> struct ColGroupGeom {
-    using P = FftPlan<H>;
+    using P = ColPlan<H>;
     using CG = ColGeom<R, H>;
     static constexpr int E = P::E, M = P::M, TC = CG::TC;
     static constexpr int COMPUTE = TC * M;                        // compute threads
@@ -52,8 +52,6 @@ template <typename R, int H> struct ColGroupGeom {
     static constexpr int LPG = PAIRED ? 2 : lines_per_group(M);
     static constexpr int GROUPS = TC / LPG;
     static constexpr int GROUP_THREADS = LPG * M;
-    static constexpr bool OK = (ROWB == 64 || ROWB == 32) && COMPUTE % 32 == 0 && TC % LPG == 0 && GROUPS <= 14 &&
-                               H % 32 == 0 && NW <= 32;
     static constexpr size_t TILE = (size_t)H * ROWB;
     static constexpr size_t XCH = (size_t)TC * P::NP * sizeof(cpx<R>);
     static constexpr size_t GREY = (size_t)H * TC;
@@ -69,6 +67,8 @@ template <typename R, int H> struct ColGroupGeom {
     static constexpr size_t TW_BYTES = (size_t)H * sizeof(cpx<R>);
     static constexpr bool TW_SHARED = OFF_TW + TW_BYTES <= 232448; // 227 KB of shared memory per CTA
     static constexpr size_t SMEM = OFF_TW + (TW_SHARED ? TW_BYTES : 0);
+    static constexpr bool OK = (ROWB == 64 || ROWB == 32) && COMPUTE % 32 == 0 && TC % LPG == 0 && GROUPS <= 14 &&
+                               H % 32 == 0 && NW <= 32 && OFF_TW <= 232448;    // (two tile buffers + exchange must fit)
     using Sync = GroupSync<GROUP_THREADS>;
 };
 
@@ -102,7 +102,7 @@ template <typename R, int H, int MODE>
 SLM_GLOBAL void SLM_LAUNCH_BOUNDS((ColGroupGeom<R, H>::THREADS), 1)
 col_group_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SLM_GRID_CONSTANT TileMap tm_out) {
     using G = ColGroupGeom<R, H>;
-    using P = FftPlan<H>;
+    using P = ColPlan<H>;
     constexpr int E = G::E, M = G::M, TC = G::TC, ROWB = G::ROWB, CS = (int)sizeof(cpx<R>);
     constexpr bool HAS_T = MODE == CGM_GS || MODE == CGM_GD || MODE == CGM_GD_POST;
     constexpr bool HAS_OUT = MODE != CGM_STATS;
@@ -169,6 +169,11 @@ col_group_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const S
             shfl_idx(0u, 0);                                 // all lanes hold their copy before the slot is released
             if (lane == 0) mbar_arrive(pubfree + s);
             Partial* plane_partials = a.partial + (size_t)b * tiles;
+            if (ga.defer_close) {                            // the closing kernel behind this launch sums the tiles (col_warp.cuh)
+                if (lane == 0) plane_partials[tile] = q;
+                ++k;
+                continue;
+            }
             unsigned ticket = 0;
             if (lane == 0) ticket = publish_partial(q, plane_partials, tile, tiles, a.counter + b);
             Partial tot;
@@ -296,8 +301,8 @@ col_group_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const S
 #pragma unroll
             for (int r = 0; r < E; ++r) { tv[r] = ld_ro(T + (size_t)r * M * a.W); aux[r] = ld_ro(Q + (size_t)r * M * a.W); }
         }
-        if (MODE == CGM_COMPLEX && ga.mode_inverse) line_fft<R, H, +1, 1, Sy, G::TW_SHARED>(v, line, j, tw, sync);
-        else if (MODE != CGM_GD_POST) line_fft<R, H, -1, 1, Sy, G::TW_SHARED>(v, line, j, tw, sync);
+        if (MODE == CGM_COMPLEX && ga.mode_inverse) line_fft<R, H, +1, 1, Sy, G::TW_SHARED, column_points(H)>(v, line, j, tw, sync);
+        else if (MODE != CGM_GD_POST) line_fft<R, H, -1, 1, Sy, G::TW_SHARED, column_points(H)>(v, line, j, tw, sync);
 
         SLM_STAMP(t == 0, k, 2);
         // ---- pointwise step and per-thread sums ----
@@ -362,7 +367,7 @@ col_group_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const S
         }
 
         SLM_STAMP(t == 0, k, 4);
-        if (MODE == CGM_GS || IS_GD) line_fft<R, H, +1, 1, Sy, G::TW_SHARED>(v, line, j, tw, sync);
+        if (MODE == CGM_GS || IS_GD) line_fft<R, H, +1, 1, Sy, G::TW_SHARED, column_points(H)>(v, line, j, tw, sync);
         SLM_STAMP(t == 0, k, 5);
         if (HAS_OUT) {
 #pragma unroll

@@ -219,12 +219,11 @@ SLM_DEV void close_plane(const ColArgs& a, int b, const Partial& tot, double s0,
 // The planes' closing as a kernel of its own (ColGroupArgs::defer_close): one warp per plane sums the tiles'
 // partial sums in the order collect_if_last uses, so both forms give the same bits.
 template <typename R, int H, int MODE>
-SLM_GLOBAL void SLM_LAUNCH_BOUNDS(32, 1) close_planes_kernel(ColGroupArgs ga) {
+SLM_GLOBAL void SLM_LAUNCH_BOUNDS(32, 1) close_planes_kernel(ColGroupArgs ga, int tiles) {
     constexpr bool IS_GD = MODE == CGM_GD || MODE == CGM_GD_POST || MODE == CGM_GD_FUSED;
     constexpr int FIELDS = MODE == CGM_GS ? F_ALL : (IS_GD ? F_A : F_MX);
     const ColArgs& a = ga.c;
     const int b = blockIdx.x, lane = threadIdx.x;
-    const int tiles = a.W / ColWarpGeom<R, H>::TC;
     griddep_wait();
     PlaneStats* st = a.stats + b;
     if (!ga.all_planes && ld_cg(&st->done) != 0) return;         // the pass skipped this plane

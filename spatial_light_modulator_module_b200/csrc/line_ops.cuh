@@ -34,7 +34,7 @@ template <typename R, int L> struct ColWarpLaunch<R, L, true> {
         if (mode != MODE) return;
         SLM_LAUNCH_PDL((col_warp_kernel<R, L, MODE>), grid, block, WG::SMEM, s, ga, in, out);
         if (MODE != CGM_COMPLEX && ga.defer_close)
-            SLM_LAUNCH((close_planes_kernel<R, L, MODE>), dim3((unsigned)ga.c.B), dim3(32), 0, s, ga);
+            SLM_LAUNCH((close_planes_kernel<R, L, MODE>), dim3((unsigned)ga.c.B), dim3(32), 0, s, ga, ga.c.W / WG::TC);
     }
     static bool launch(int mode, const ColGroupArgs& ga, const TileMap& in, const TileMap& out, int ctas, cudaStream_t s) {
         if (!enabled()) return false;
@@ -62,6 +62,13 @@ template <typename R, int L> struct GroupLaunch<R, L, true> {
         cudaFuncSetAttribute(col_group_kernel<R, L, CGM_STATS_KEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GG::SMEM);
         cudaFuncSetAttribute(col_group_kernel<R, L, CGM_GD_POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GG::SMEM);
     }
+    template <int MODE> static void run(int mode, const ColGroupArgs& ga, const TileMap& in, const TileMap& out, dim3 grid, dim3 block,
+                                        cudaStream_t s) {
+        if (mode != MODE) return;
+        SLM_LAUNCH_PDL((col_group_kernel<R, L, MODE>), grid, block, GG::SMEM, s, ga, in, out);
+        if (MODE != CGM_COMPLEX && ga.defer_close)
+            SLM_LAUNCH((close_planes_kernel<R, L, MODE>), dim3((unsigned)ga.c.B), dim3(32), 0, s, ga, ga.c.W / GG::TC);
+    }
     static int launch(int mode, const ColGroupArgs& ga, const TileMap& in, const TileMap& out, int ctas, cudaStream_t s) {
         static_assert(!ColWarpGeom<R, L>::OK || (ColWarpGeom<R, L>::TC == GG::TC && ColWarpGeom<R, L>::ROWB == GG::ROWB),
                       "both column kernels must share the tile maps and the per-tile partial sums");
@@ -69,12 +76,12 @@ template <typename R, int L> struct GroupLaunch<R, L, true> {
         if (mode == CGM_GD_FUSED) return -1;                 // only the warp-per-column kernel has it
         const long long tiles = (long long)ga.c.B * (ga.c.W / GG::TC);
         const dim3 grid((unsigned)(tiles < ctas ? tiles : ctas)), block(GG::THREADS);
-        if (mode == CGM_GS) SLM_LAUNCH_PDL((col_group_kernel<R, L, CGM_GS>), grid, block, GG::SMEM, s, ga, in, out);
-        else if (mode == CGM_GD) SLM_LAUNCH_PDL((col_group_kernel<R, L, CGM_GD>), grid, block, GG::SMEM, s, ga, in, out);
-        else if (mode == CGM_STATS) SLM_LAUNCH_PDL((col_group_kernel<R, L, CGM_STATS>), grid, block, GG::SMEM, s, ga, in, out);
-        else if (mode == CGM_STATS_KEEP) SLM_LAUNCH_PDL((col_group_kernel<R, L, CGM_STATS_KEEP>), grid, block, GG::SMEM, s, ga, in, out);
-        else if (mode == CGM_GD_POST) SLM_LAUNCH_PDL((col_group_kernel<R, L, CGM_GD_POST>), grid, block, GG::SMEM, s, ga, in, out);
-        else SLM_LAUNCH_PDL((col_group_kernel<R, L, CGM_COMPLEX>), grid, block, GG::SMEM, s, ga, in, out);
+        run<CGM_GS>(mode, ga, in, out, grid, block, s);
+        run<CGM_GD>(mode, ga, in, out, grid, block, s);
+        run<CGM_STATS>(mode, ga, in, out, grid, block, s);
+        run<CGM_STATS_KEEP>(mode, ga, in, out, grid, block, s);
+        run<CGM_GD_POST>(mode, ga, in, out, grid, block, s);
+        run<CGM_COMPLEX>(mode, ga, in, out, grid, block, s);
         return 0;
     }
 };

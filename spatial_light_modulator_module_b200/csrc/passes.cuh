@@ -158,7 +158,7 @@ template <typename R, int L> struct RowGeom {
     using Sync = GroupSync<GROUP_THREADS>;
 };
 template <typename R, int L> struct ColGeom {
-    using P = FftPlan<L>;
+    using P = ColPlan<L>;
     static constexpr int M = P::M;
 #ifndef SLM_TCMAX_F32
 #define SLM_TCMAX_F32 8
@@ -284,7 +284,7 @@ template <typename R, int H, int ALG>
 SLM_DEV void col_pass_tile(const ColArgs& a, int b, int tile, int tiles, cpx<R>* v, cpx<R>* line, const R* lut_s,
                            int t, int c, int j) {
     using G = ColGeom<R, H>;
-    using P = FftPlan<H>;
+    using P = ColPlan<H>;
     constexpr int E = P::E, M = P::M, TC = G::TC;
     PlaneStats* st = a.stats + b;
     const size_t W = a.W;
@@ -303,7 +303,7 @@ SLM_DEV void col_pass_tile(const ColArgs& a, int b, int tile, int tiles, cpx<R>*
 #pragma unroll
         for (int r = 0; r < E; ++r) { tv[r] = ld_ro(T + (size_t)r * M * W); aux[r] = ld_ro(Q + (size_t)r * M * W); }
     }
-    line_fft<R, H, -1, TC>(v, line, j, tw);                   // C = fft2(B)  /  med_output
+    line_fft<R, H, -1, TC, CtaSync, false, column_points(H)>(v, line, j, tw);                   // C = fft2(B)  /  med_output
     if (a.T8) {
 #pragma unroll
         for (int r = 0; r < E; ++r) { tv[r] = (R)grey[r]; aux[r] = lut_s[grey[r]]; }
@@ -339,7 +339,7 @@ SLM_DEV void col_pass_tile(const ColArgs& a, int b, int tile, int tiles, cpx<R>*
     unsigned ticket = 0;
     if (t == 0) ticket = publish_partial(p, plane_partials, tile, tiles, a.counter + b);
 
-    line_fft<R, H, +1, TC>(v, line, j, tw);
+    line_fft<R, H, +1, TC, CtaSync, false, column_points(H)>(v, line, j, tw);
     cpx<R>* Y = static_cast<cpx<R>*>(a.Y) + off;
 #pragma unroll
     for (int r = 0; r < E; ++r) st_plane(Y + (size_t)r * M * W, v[r]);
@@ -370,15 +370,15 @@ SLM_DEV void col_pass_tile(const ColArgs& a, int b, int tile, int tiles, cpx<R>*
 template <typename R, int H>
 SLM_DEV void col_plain_tile(const PlainColArgs& a, int b, int tile, int tiles, cpx<R>* v, cpx<R>* line, int t, int c, int j) {
     using G = ColGeom<R, H>;
-    using P = FftPlan<H>;
+    using P = ColPlan<H>;
     constexpr int E = P::E, M = P::M, TC = G::TC;
     PlaneStats* st = a.stats ? a.stats + b : nullptr;
     const size_t W = a.W;
     const size_t off = (size_t)b * H * W + (size_t)j * W + tile * TC + c;
     const cpx<R>* tw = static_cast<const cpx<R>*>(a.tw);
     if (!a.skip_fft) {
-        if (a.inverse) line_fft<R, H, +1, TC>(v, line, j, tw);
-        else line_fft<R, H, -1, TC>(v, line, j, tw);
+        if (a.inverse) line_fft<R, H, +1, TC, CtaSync, false, column_points(H)>(v, line, j, tw);
+        else line_fft<R, H, -1, TC, CtaSync, false, column_points(H)>(v, line, j, tw);
     }
 
     if (a.output == OUT_COMPLEX) {
@@ -421,7 +421,7 @@ SLM_DEV void col_plain_tile(const PlainColArgs& a, int b, int tile, int tiles, c
 template <typename R, int H, class Skip, class Body>
 SLM_DEV void col_tiles(const void* in, int W, unsigned char* raw, Skip skip, Body body) {
     using G = ColGeom<R, H>;
-    using P = FftPlan<H>;
+    using P = ColPlan<H>;
     constexpr int E = P::E, M = P::M, TC = G::TC;
     const int tiles = W / TC;
     const int t = threadIdx.x, c = t % TC, j = t / TC;
