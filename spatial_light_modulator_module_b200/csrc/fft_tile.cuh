@@ -238,7 +238,10 @@ SLM_HOSTDEV constexpr int default_points(int N) { return (N >= 8192 || N == SLM_
 // Column transforms of 4096 points keep 32 points per thread: 128 threads per column let a CTA hold FOUR columns
 // (32-byte row segments, whole sectors) instead of two; measured 0.48 -> 0.36 ms per Fourier-plane pass (2 x 4096^2).
 // The row kernels stay at 16 (the GD row pass holds x beside the field and would spill).
-SLM_HOSTDEV constexpr int column_points(int N) { return N == 4096 ? 32 : default_points(N); }
+#ifndef SLM_COL_E32_LEN
+#define SLM_COL_E32_LEN 0      // tuning builds: one more COLUMN length with 32 points per thread
+#endif
+SLM_HOSTDEV constexpr int column_points(int N) { return (N == 4096 || N == SLM_COL_E32_LEN) ? 32 : default_points(N); }
 template <int N, int EP = default_points(N)> struct FftPlan {
     static constexpr int E = EP;                       // points per thread
     static constexpr int M = N / E;                    // threads per line
