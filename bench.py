@@ -362,8 +362,8 @@ def run_b200(a):
         ghs.sequence_holograms(host_frames, mloops, precision=a.precision, batch=mframes // 2, gather=False)
         torch.cuda.synchronize()
         et = time.perf_counter() - t0
-        movie["e2e"] = {"holograms_per_s": 2 * mframes / et, "frames": 2 * mframes, "batch": mframes // 2,
-                        "h2d_bytes": int(host_frames.nbytes), "d2h_bytes": int(2 * mframes * mshape[0] * mshape[1] * 8),
+        movie["e2e"] = {"holograms_per_s": 2 * mframes / et / world, "frames": 2 * mframes // world, "batch": mframes // 2,
+                        "h2d_bytes": int(host_frames.nbytes) // world, "d2h_bytes": int(2 * mframes * mshape[0] * mshape[1] * 8) // world,
                         "api": "generate_hologram_sequence.sequence_holograms(frames_uint8, 50) -> float64 holograms"}
 
     # ---- end to end through the drop-in API with host buffers ----------------------------------------
@@ -483,6 +483,11 @@ _REAL_STDOUT = 1
 
 if __name__ == "__main__":
     args = parse()
+    # watchdog: a run that takes absurdly long (default 20 min; SLM_BENCH_WATCHDOG=seconds) dumps every thread's stack
+    # to stderr and exits instead of hanging its launcher (one 2-GPU run of this round stalled after NCCL's init and
+    # could not be reproduced in five repeats)
+    import faulthandler
+    faulthandler.dump_traceback_later(float(os.environ.get("SLM_BENCH_WATCHDOG", "1200")), exit=True)
     # libraries (NCCL's version banner, ...) write to file descriptor 1: keep it for the JSON line alone
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)

@@ -215,6 +215,7 @@ static int launch_group(slm_ctx* c, int mode, int batch, const ColArgs* loop, co
     const int ctas = mode == CGM_GD_FUSED ? c->fused_ctas : c->persist_ctas;
     const int kind = (mode == CGM_STATS || mode == CGM_STATS_KEEP) ? K_COL_STATS : (mode == CGM_COMPLEX ? K_COL_PLAIN : K_COL_PASS);
     SLM_TIMED(kind, c->col->col_group(mode, ga, &c->map_x, map_out ? map_out : &c->map_x, ctas, c->stream));
+    if (ga.defer_close) c->launches++;               // the closing kernel behind the pass
     return 0;
 }
 
