@@ -372,6 +372,12 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
             const int b = (int)(d.g / tiles), tile = (int)(d.g % tiles);
             tile_load(tm_in, tile_buf(s), bar(full, s), (long long)b * H, H, (long long)tile * ROWB, ROWB, (int)sizeof(R));
         };
+        // the tile that will be loaded when the next buffer frees: have L2 fetch it now, so that load is an L2 hit
+        auto prefetch = [&](const TileDesc& d) {
+            if (lane != 0 || d.g < 0) return;
+            const int b = (int)(d.g / tiles), tile = (int)(d.g % tiles);
+            tile_prefetch(tm_in, (long long)b * H, H, (long long)tile * ROWB, (int)sizeof(R));
+        };
         TileDesc cur = resolve(peek(blockIdx.x));
         unsigned k = 0;                                      // next item (tile or stop marker) to issue
         int stops = 0;                                       // stop markers issued: one per group ends the kernel
@@ -382,6 +388,7 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
             post(s, cur);
             ++k;
             if (cur.g < 0) ++stops; else cur = resolve(peek(cur.g + gridDim.x));
+            prefetch(cur);
         }
         // retire tile kd (store it), then reuse its buffer for item kd + NBUF
         for (unsigned kd = 0; kd < k - (unsigned)stops; ++kd) {              // k - stops = tiles issued so far
@@ -403,6 +410,7 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
                 post(s, cur);
                 ++k;
                 if (cur.g < 0) ++stops; else cur = resolve(ahead);
+                prefetch(cur);
             }
         }
         if (lane == 0) tile_store_wait_all();

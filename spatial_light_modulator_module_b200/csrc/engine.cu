@@ -495,7 +495,9 @@ extern "C" int slm_gd_run(slm_ctx* c, int batch, const uint8_t* T8, const void* 
     // The fused pass saves a launch and a trip of the field through L2/HBM per iteration, but its CTAs wait for each
     // other once per plane and it leaves the SMs beyond a whole number of planes idle: measured faster for a few
     // planes (latency bound: 2.9 vs 3.3 ms per 100-iteration hologram), slower for a large batch (47.9 vs 46.4 ms).
-    const bool fused = c->use_groups && c->fused_ctas && (long long)batch * (c->W / c->col->cols_per_cta) <= 4LL * c->persist_ctas;
+    static const char* fused_always = getenv("SLM_FUSED_GD_ALWAYS");      // developer switch (A/B measurements)
+    const bool fused = c->use_groups && c->fused_ctas &&
+                       (fused_always || (long long)batch * (c->W / c->col->cols_per_cta) <= 4LL * c->persist_ctas);
     for (int k = 0; k < max_loops; ++k) {
         if (fused) {
             // one Fourier-plane pass: the tiles of a plane agree on amax(output_unnormed) (algorithms.py:86) between

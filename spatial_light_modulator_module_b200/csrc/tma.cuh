@@ -106,6 +106,13 @@ SLM_DEV void tile_load(const TileMap& tm, void* dst, TileBarrier* bar, long long
                      : "memory");
     }
 }
+// Ask L2 for a tile that will be loaded a little later (no shared-memory destination, nothing to wait for).
+SLM_DEV void tile_prefetch(const TileMap& tm, long long row0, int rows, long long col_byte0, int real_bytes) {
+    const unsigned long long desc = reinterpret_cast<unsigned long long>(&tm.map);
+    const int c0 = (int)(col_byte0 / real_bytes);
+    for (int r = 0; r < rows; r += tm.box_rows)
+        asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(desc), "r"(c0), "r"((int)(row0 + r)) : "memory");
+}
 SLM_DEV void tile_store(const TileMap& tm, const void* src, long long row0, int rows, long long col_byte0, int row_bytes, int real_bytes) {
     const unsigned long long desc = reinterpret_cast<unsigned long long>(&tm.map);
     const int c0 = (int)(col_byte0 / real_bytes);
@@ -124,6 +131,7 @@ SLM_DEV void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" 
 #endif
 
 #ifdef SLM_EMULATE
+inline void tile_prefetch(const TileMap&, long long, int, long long, int) {}
 inline void tile_load(const TileMap& tm, void* dst, TileBarrier* bar, long long row0, int rows, long long col_byte0, int row_bytes, int) {
     tile_load(tm, dst, bar, row0, rows, col_byte0, row_bytes);
 }
