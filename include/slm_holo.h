@@ -161,6 +161,13 @@ int slm_quantize(slm_ctx* ctx, const double* phase, const double* mask, double c
 int slm_quantize_grey(slm_ctx* ctx, const uint8_t* grey, const double* mask, double ct2pi, uint8_t* out,
                       long long n, long long plane);
 
+/* ---- host memory ------------------------------------------------------------------------------------------
+ * Page-lock / release a HOST array in place, so that copies from it are plain DMA (the reference hands the same
+ * numpy arrays -- the wavefront-correction mask, display_holograms.py:189-204 -- to every frame).  A range that
+ * cannot be locked (already locked pages, limits) returns SLM_ERR_CUDA and leaves no pending CUDA error. */
+int slm_host_register(void* ptr, size_t bytes);
+int slm_host_unregister(void* ptr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,8 @@ SIGNATURES = {
     "slm_add_mod2pi": (_i, [_vp, _vp, _vp, _vp, _ll, _ll]),
     "slm_quantize": (_i, [_vp, _vp, _vp, _d, _i, _vp, _ll, _ll]),
     "slm_quantize_grey": (_i, [_vp, _vp, _vp, _d, _vp, _ll, _ll]),
+    "slm_host_register": (_i, [_vp, C.c_size_t]),
+    "slm_host_unregister": (_i, [_vp]),
 }
 
 

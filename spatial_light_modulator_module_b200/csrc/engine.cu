@@ -717,6 +717,27 @@ extern "C" int slm_expected_outcome(slm_ctx* c, int batch, const double* hologra
     return 0;
 }
 
+extern "C" int slm_host_register(void* ptr, size_t bytes) {
+    if (!ptr || !bytes) return fail(SLM_ERR_ARG, "slm_host_register: bad argument");
+#ifdef SLM_EMULATE
+    return 0;
+#else
+    const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(SLM_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e)); }
+    return 0;
+#endif
+}
+extern "C" int slm_host_unregister(void* ptr) {
+    if (!ptr) return fail(SLM_ERR_ARG, "slm_host_unregister: bad argument");
+#ifdef SLM_EMULATE
+    return 0;
+#else
+    const cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(SLM_ERR_CUDA, std::string("cudaHostUnregister: ") + cudaGetErrorString(e)); }
+    return 0;
+#endif
+}
+
 #define SLM_EW_PROLOGUE(who)                                              \
     if (!c) return fail(SLM_ERR_ARG, who ": null context");              \
     SLM_CUDA(cudaSetDevice(c->device));

@@ -90,7 +90,7 @@ class Engine:
         host = torch.from_numpy(array)
         nbytes = host.numel() * host.element_size()
         with torch.cuda.stream(self._stream):
-            if nbytes >= (1 << 20) and (host.is_pinned() or (nbytes >= _LOCK_MIN and _page_lock_if_reused(torch, array))):
+            if nbytes >= (1 << 20) and _dma_ready(torch, host, array):
                 # page-locked already (a result of to_host(), or a caller's array seen before, e.g. the one
                 # wavefront-correction mask every frame is added to): DMA straight from it, no staging copy
                 dev = host.to(self._dev, non_blocking=True)
@@ -489,6 +489,19 @@ _LOCK_BUDGET = 1 << 30
 _LOCK_MIN = 4 << 20           # cudaHostRegister costs ~2 ms whatever the size: not worth it for small arrays
 
 
+def _dma_ready(torch, host, array: np.ndarray) -> bool:
+    """May `array` be copied to the device asynchronously, straight from where it lies?  Yes for PyTorch's own pinned
+    memory (results of to_host) and for ranges lying COMPLETELY inside memory this module has page-locked; an array
+    that only begins in a locked range (``is_pinned`` looks at the first byte alone) must take the staged copy."""
+    lo, hi = array.ctypes.data, array.ctypes.data + array.nbytes
+    for (p, n) in _LOCKED:
+        if p <= lo < p + n or p < hi <= p + n:
+            return lo >= p and hi <= p + n
+    if host.is_pinned():
+        return True
+    return array.nbytes >= _LOCK_MIN and _page_lock_if_reused(torch, array)
+
+
 def _page_lock_if_reused(torch, array: np.ndarray) -> bool:
     import weakref
     owner = array
@@ -506,19 +519,15 @@ def _page_lock_if_reused(torch, array: np.ndarray) -> bool:
         return False
     if sum(n for _, n in _LOCKED) + array.nbytes > _LOCK_BUDGET:
         return False
-    rt = torch.cuda.cudart()
-    try:
-        res = rt.cudaHostRegister(array.ctypes.data, array.nbytes, 0)
-        if int(getattr(res, "value", res)) != 0:
-            return False
-    except Exception:
+    lib = _ffi.load()
+    if lib.slm_host_register(C.c_void_p(array.ctypes.data), array.nbytes) != 0:
         return False
     _LOCKED[key] = True
 
     def release(k=key, ptr=array.ctypes.data):
         if _LOCKED.pop(k, None):
             try:
-                rt.cudaHostUnregister(ptr)
+                lib.slm_host_unregister(C.c_void_p(ptr))
             except Exception:
                 pass
     weakref.finalize(owner, release)

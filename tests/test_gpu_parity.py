@@ -414,6 +414,26 @@ def test_slab_gs_8192_invariants():
     eng.close()
 
 
+def test_reused_host_arrays_are_page_locked_safely():
+    """Host arrays handed over a second time are page-locked in place (engine._page_lock_if_reused); overlapping
+    ranges cannot be locked twice -- that must fall back to the staged copy without leaving a CUDA error behind."""
+    from spatial_light_modulator_module_b200 import _ffi as F
+    eng = make_engine((1024, 1024), "fp32", 2)
+    rng = np.random.default_rng(5)
+    base = rng.random((3, 1024, 1024)) * 2 * np.pi
+    mask = rng.random((1024, 1024)) * 2 * np.pi
+    ref = {}
+    for sl in (slice(0, 2), slice(1, 3)):
+        ref[sl.start] = ((base[sl] + mask) % (2 * np.pi) * 256 / (2 * np.pi)).astype(np.uint8)
+    for rep in range(3):                     # 2nd use of [0:2] locks it; [1:3] overlaps it and must still work
+        for sl in (slice(0, 2), slice(1, 3)):
+            out = eng.to_host(eng.quantize(base[sl], mask, 256, F.QUANT_FLOOR))
+            np.testing.assert_array_equal(out, ref[sl.start])
+    base[0, 0, 0] = 1.0                      # the locked array is still ordinary, writable memory
+    assert eng.to_host(eng.quantize(base[0:2], mask, 256, F.QUANT_FLOOR))[0, 0, 0] == np.uint8(((1.0 + mask[0, 0]) % (2 * np.pi)) * 256 / (2 * np.pi))
+    eng.close()
+
+
 def test_device_mt19937_stream():
     pc.check_device_mt19937(make_engine)
 
