@@ -312,6 +312,20 @@ def test_dropin_analytic_and_display(golden, tmp_path):
     np.testing.assert_array_equal(np.array(dh.mask_hologram(str(pp), q["mask"], 200)), q["q2png_200"])
 
 
+def test_sequence_results_pinned_and_pageable_agree(monkeypatch):
+    """The movie driver reads a batch back while the next one iterates: into pooled page-locked arrays (plain DMA)
+    or, beyond SLM_PINNED_RESULT_BYTES, into ordinary memory from a worker thread.  Same bits either way."""
+    from spatial_light_modulator_module_b200 import generate_hologram_sequence as ghs
+    frames = synthetic.movie_frames(7, rescale_parameter=5.0)
+    h1, e1, err1, _ = ghs.sequence_holograms(frames, 5, precision="fp32", batch=3, want_expected=True)
+    monkeypatch.setenv("SLM_PINNED_RESULT_BYTES", "0")
+    h2, e2, err2, _ = ghs.sequence_holograms(frames, 5, precision="fp32", batch=3, want_expected=True)
+    np.testing.assert_array_equal(h1, h2)
+    np.testing.assert_array_equal(e1, e2)
+    for a, b in zip(err1, err2):
+        np.testing.assert_array_equal(a, b)
+
+
 def test_sequence_driver_files(tmp_path, monkeypatch):
     """generate_hologram_sequence: PNG frames in, .npy holograms + preview PNGs out
     (generate_hologram_sequence.py:10-32)."""
