@@ -509,7 +509,12 @@ extern "C" int slm_gd_run(slm_ctx* c, int batch, const uint8_t* T8, const void* 
             SLM_TRY(launch_group(c, CGM_STATS_KEEP, batch, nullptr, &c->map_x, 0, 1.0));
             SLM_TRY(launch_group(c, CGM_GD_POST, batch, &ca, &c->map_y, 0, 1.0));
         } else {
-            SLM_TRY(run_stats(c, batch));                                     // amax(output_unnormed), algorithms.py:86
+            // amax(output_unnormed), algorithms.py:86; the transformed field is kept in X so the gradient pass need not
+            // transform again
+            PlainColArgs sa = stats_args(c, batch, OUT_STATS, c->X);
+            sa.keep = 1;
+            SLM_TIMED(K_COL_STATS, c->col->col_plain(sa, c->stream));
+            ca.skip_forward = 1;
             SLM_TIMED(K_COL_PASS, c->col->col_pass(ALG_GD, ca, c->stream));
         }
         if (k + 1 < max_loops) { SLM_TIMED(K_ROW_PASS, c->row->row_pass(ALG_GD, ra, c->stream)); }
@@ -520,7 +525,7 @@ extern "C" int slm_gd_run(slm_ctx* c, int batch, const uint8_t* T8, const void* 
         PlainColArgs ia = stats_args(c, batch, OUT_INTENSITY_GD, expected_out);
         // two-pass form: X already holds med_output; fused form: transform X once more (same kernel arithmetic), kept
         if (fused) SLM_TRY(launch_group(c, CGM_STATS_KEEP, batch, nullptr, &c->map_x, 0, 1.0, 1));
-        ia.skip_fft = c->use_groups ? 1 : 0;
+        ia.skip_fft = 1;
         SLM_TIMED(K_COL_PLAIN, c->col->col_plain(ia, c->stream));
     }
     return 0;

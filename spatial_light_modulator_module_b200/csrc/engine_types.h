@@ -64,6 +64,7 @@ struct ColArgs {
     double tolerance;
     double inv_hw;
     const void* tw;          // complex<R> [H] column twiddles
+    int skip_forward;        // col_pass_kernel<GD>: X already holds the column-transformed field (max pass with `keep`)
     unsigned* fused_max;     // CGM_GD_FUSED: [B] bit pattern of the running max |F|^2 of the plane (0 between launches)
     unsigned* fused_count;   // CGM_GD_FUSED: [B] tiles of the plane that have contributed (0 between launches)
 };
@@ -121,6 +122,7 @@ struct PlainColArgs {
     int output;              // PlainColOutput
     int inverse;
     int skip_fft;            // intensity outputs: `in` already holds the column-transformed field
+    int keep;                // OUT_STATS: also write the transformed field to `out` (GD: the gradient pass starts from it)
     double scale;            // OUT_COMPLEX: multiply results (1/(HW) for ifft2)
     const void* in;          // complex<R> [B][H][W]
     void* out;               // complex<R> [B][H][W] or double [B][H][W]

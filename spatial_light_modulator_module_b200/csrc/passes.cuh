@@ -303,7 +303,7 @@ SLM_DEV void col_pass_tile(const ColArgs& a, int b, int tile, int tiles, cpx<R>*
 #pragma unroll
         for (int r = 0; r < E; ++r) { tv[r] = ld_ro(T + (size_t)r * M * W); aux[r] = ld_ro(Q + (size_t)r * M * W); }
     }
-    line_fft<R, H, -1, TC, CtaSync, false, column_points(H)>(v, line, j, tw);                   // C = fft2(B)  /  med_output
+    if (!a.skip_forward) line_fft<R, H, -1, TC, CtaSync, false, column_points(H)>(v, line, j, tw);   // C = fft2(B)  /  med_output
     if (a.T8) {
 #pragma unroll
         for (int r = 0; r < E; ++r) { tv[r] = (R)grey[r]; aux[r] = lut_s[grey[r]]; }
@@ -387,6 +387,11 @@ SLM_DEV void col_plain_tile(const PlainColArgs& a, int b, int tile, int tiles, c
 #pragma unroll
         for (int r = 0; r < E; ++r) st_plane(out + (size_t)r * M * W, cscale(v[r], s));
     } else if (a.output == OUT_STATS) {
+        if (a.keep) {                                               // the transformed field goes back (in place)
+            cpx<R>* out = static_cast<cpx<R>*>(a.out) + off;
+#pragma unroll
+            for (int r = 0; r < E; ++r) st_plane(out + (size_t)r * M * W, v[r]);
+        }
         Partial p; p.mx = 0; p.a = 0; p.b = 0; p.c = 0;
         R mx = 0;
 #pragma unroll
@@ -442,6 +447,7 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((ColGeom<R, H>::THREADS), 1) col_pass_kernel(C
         const R* lut = static_cast<const R*>(a.lut);
         for (int i = threadIdx.x; i < 256; i += ColGeom<R, H>::THREADS) lut_s[i] = ld_ro(lut + i);
     }
+    if (a.skip_forward) sync_cta();                             // no forward transform whose barriers would publish the table
     col_tiles<R, H>(a.X, a.W, raw,
         [&](int b) { return ld_cg(&a.stats[b].done) != 0; },
         [&](int b, int tile, int tiles, cpx<R>* v, cpx<R>* line, int t, int c, int j) {
