@@ -476,7 +476,13 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
                 atomic_max_u32(a.fused_max + b, __float_as_uint(mm));       // |F|^2 >= 0: ordered like its bit pattern
                 fence_device();
                 atomic_add_u32(a.fused_count + b, 1u);
-                while (ld_acquire(a.fused_count + b) < (unsigned)tiles) {}   // the plane's other tiles are in flight on other SMs
+                // the plane's other tiles are in flight on other SMs; should they not be (the CTAs of this launch not all
+                // resident: a foreign kernel holding SMs for good), give up after ~2 s with the error flag set instead of
+                // hanging the device
+                const long long t0 = clock_now();
+                while (ld_acquire(a.fused_count + b) < (unsigned)tiles) {
+                    if (clock_now() - t0 > (1ll << 32)) { atomic_max_u32(a.fused_count + (size_t)a.max_planes, 1u); break; }
+                }
                 fmx[TC] = __uint_as_float(ld_cg(a.fused_max + b));
             }
             sync_named(9 + grp, G::GROUP_THREADS);

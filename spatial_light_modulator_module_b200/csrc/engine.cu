@@ -44,7 +44,7 @@ struct slm_ctx {
     PlaneStats* stats = nullptr;
     Partial* partial = nullptr;
     unsigned* counter = nullptr;
-    unsigned* fused = nullptr;                            // [2][max_batch]: plane max bits, tile count of CGM_GD_FUSED
+    unsigned* fused = nullptr;                            // [3][max_batch]: plane max bits, tile count of CGM_GD_FUSED, [0] of the third row: time-out flag
     int fused_ctas = 0;                                   // grid of the fused GD column pass (0: two passes)
     double *err_curve = nullptr, *lr = nullptr, *norm = nullptr;
     void* lut = nullptr;
@@ -211,7 +211,7 @@ static int launch_group(slm_ctx* c, int mode, int batch, const ColArgs* loop, co
 #endif
     ga.c.B = batch; ga.c.W = c->W; ga.c.stats = c->stats; ga.c.partial = c->partial; ga.c.counter = c->counter;
     ga.c.norm = c->norm; ga.c.tw = c->tw_col;
-    ga.c.fused_max = c->fused; ga.c.fused_count = c->fused + c->max_batch;
+    ga.c.fused_max = c->fused; ga.c.fused_count = c->fused + c->max_batch; ga.c.max_planes = c->max_batch;
     const int ctas = mode == CGM_GD_FUSED ? c->fused_ctas : c->persist_ctas;
     const int kind = (mode == CGM_STATS || mode == CGM_STATS_KEEP) ? K_COL_STATS : (mode == CGM_COMPLEX ? K_COL_PLAIN : K_COL_PASS);
     SLM_TIMED(kind, c->col->col_group(mode, ga, &c->map_x, map_out ? map_out : &c->map_x, ctas, c->stream));
@@ -270,7 +270,7 @@ extern "C" int slm_ctx_create(slm_ctx** out, int device, int H, int W, int max_b
     A((void**)&c->stats, (size_t)max_batch * sizeof(PlaneStats));
     A((void**)&c->partial, (size_t)max_batch * tmax * sizeof(Partial));
     A((void**)&c->counter, (size_t)max_batch * sizeof(unsigned));
-    A((void**)&c->fused, 2 * (size_t)max_batch * sizeof(unsigned));
+    A((void**)&c->fused, 3 * (size_t)max_batch * sizeof(unsigned));
     A((void**)&c->norm, (size_t)max_batch * sizeof(double));
     A(&c->lut, 256 * real_size(precision));
     A((void**)&c->lut32, 256 * sizeof(float));
@@ -281,7 +281,7 @@ extern "C" int slm_ctx_create(slm_ctx** out, int device, int H, int W, int max_b
     if (!rc) rc = ensure_loops(c, 256);
     if (!rc) rc = setup_groups(c);
     if (!rc && cudaMemset(c->counter, 0, (size_t)max_batch * sizeof(unsigned)) != cudaSuccess) rc = fail(SLM_ERR_CUDA, "cudaMemset(counter)");
-    if (!rc && cudaMemset(c->fused, 0, 2 * (size_t)max_batch * sizeof(unsigned)) != cudaSuccess) rc = fail(SLM_ERR_CUDA, "cudaMemset(fused)");
+    if (!rc && cudaMemset(c->fused, 0, 3 * (size_t)max_batch * sizeof(unsigned)) != cudaSuccess) rc = fail(SLM_ERR_CUDA, "cudaMemset(fused)");
     if (!rc && cudaMemset(c->stats, 0, (size_t)max_batch * sizeof(PlaneStats)) != cudaSuccess) rc = fail(SLM_ERR_CUDA, "cudaMemset(stats)");
     if (rc) { std::string keep = g_err; slm_ctx_destroy(c); g_err = keep; return rc; }
     *out = c;
@@ -347,7 +347,7 @@ static int begin_run(slm_ctx* c, int batch, const double* norm, int max_loops) {
     choose_pdl(c, batch);
     SLM_TRY(ensure_loops(c, max_loops));
     SLM_CUDA(cudaMemsetAsync(c->stats, 0, (size_t)batch * sizeof(PlaneStats), c->stream));
-    if (c->fused) SLM_CUDA(cudaMemsetAsync(c->fused, 0, 2 * (size_t)c->max_batch * sizeof(unsigned), c->stream));
+    if (c->fused) SLM_CUDA(cudaMemsetAsync(c->fused, 0, 3 * (size_t)c->max_batch * sizeof(unsigned), c->stream));
     if (norm) SLM_CUDA(cudaMemcpyAsync(c->norm, norm, (size_t)batch * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     return 0;
 }
@@ -703,7 +703,11 @@ extern "C" int slm_read_curves(slm_ctx* c, int batch, int max_loops, double* err
     std::vector<PlaneStats> st(batch);
     SLM_CUDA(cudaMemcpyAsync(st.data(), c->stats, (size_t)batch * sizeof(PlaneStats), cudaMemcpyDeviceToHost, c->stream));
     if (err) SLM_CUDA(cudaMemcpyAsync(err, c->err_curve, (size_t)batch * max_loops * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    unsigned timed_out = 0;
+    if (c->fused) SLM_CUDA(cudaMemcpyAsync(&timed_out, c->fused + 2 * (size_t)c->max_batch, sizeof timed_out, cudaMemcpyDeviceToHost, c->stream));
     SLM_CUDA(cudaStreamSynchronize(c->stream));
+    if (timed_out) return fail(SLM_ERR_CUDA, "the fused Fourier-plane pass timed out waiting for the tiles of a plane (its CTAs were not all "
+                                             "resident: is another kernel holding SMs?); set SLM_NO_FUSED_GD=1");
     if (iters) for (int b = 0; b < batch; ++b) iters[b] = st[b].iters;
     return 0;
 }

@@ -67,6 +67,7 @@ struct ColArgs {
     int skip_forward;        // col_pass_kernel<GD>: X already holds the column-transformed field (max pass with `keep`)
     unsigned* fused_max;     // CGM_GD_FUSED: [B] bit pattern of the running max |F|^2 of the plane (0 between launches)
     unsigned* fused_count;   // CGM_GD_FUSED: [B] tiles of the plane that have contributed (0 between launches)
+    int max_planes;          // stride of the two arrays above; fused_count[max_planes] is the pass's time-out flag
 };
 
 // ---- warp-specialised persistent column kernel (col_groups.cuh) ---------------------------------------

@@ -222,6 +222,7 @@ inline unsigned atomic_inc_wrap(unsigned* p, unsigned limit) { unsigned o = *p; 
 inline unsigned atomic_max_u32(unsigned* p, unsigned v) { unsigned o = *p; if (v > o) *p = v; return o; }
 inline unsigned atomic_add_u32(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 inline unsigned ld_acquire(const unsigned* p) { return *p; }
+inline long long clock_now() { return 0; }
 }  // namespace slm
 inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
