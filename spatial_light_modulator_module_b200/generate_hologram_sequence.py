@@ -28,8 +28,9 @@ def _dist():
 
 def sequence_holograms(frames, max_loops: int, tolerance: float = 0.0, precision: str = "fp32",
                        batch: int = 32, want_expected: bool = False, engine_factory: Optional[Callable] = None,
-                       gather: bool = True):
-    """GS holograms of ``frames`` (uint8 [F,H,W]).
+                       gather: bool = True, inc_amp=None):
+    """GS holograms of ``frames`` (uint8 [F,H,W]); ``inc_amp``: illumination amplitude plane [H,W] shared by all
+    frames (algorithms.py:14-19), None = uniform.
 
     Under an initialised process group every rank passes the SAME ``frames`` and computes only its
     block; with ``gather`` the full results are returned on rank 0 (other ranks get their own
@@ -56,7 +57,7 @@ def sequence_holograms(frames, max_loops: int, tolerance: float = 0.0, precision
     pending = []
     for s in range(0, n_local, batch):
         e = min(s + batch, n_local)
-        res = eng.gs(frames[lo + s:lo + e], max_loops, tolerance, want_expected=want_expected)
+        res = eng.gs(frames[lo + s:lo + e], max_loops, tolerance, inc_amp=inc_amp, want_expected=want_expected)
         for job in pending:
             job.join()
         pending = [eng.to_host_into(res.hologram, holos[s:e])]
@@ -118,12 +119,14 @@ def generate_hologram_sequence(args):
     frames = np.stack([np.array(im.open(f"{source_dir_path}/{i}.png")) for i in range(len(files))])
     if frames.dtype != np.uint8 or frames.ndim != 3:
         raise ValueError("trap frames must be single-channel 8-bit images")
+    inc = None
     if getattr(args, "incomming_intensity", "uniform") != "uniform":
-        raise NotImplementedError("non-uniform illumination is supported by gerchberg_saxton(); the batched "
-                                  "sequence driver handles the uniform case")
+        from .algorithms import _illumination
+        inc = _illumination(args, frames.shape[1:])
     holos, exps, errors, (lo, hi) = sequence_holograms(
         frames, int(args.max_loops), float(args.tolerance), getattr(args, "precision", None) or
-        os.environ.get("SLM_PRECISION", "fp32"), int(getattr(args, "batch", 32)), bool(args.preview), gather=False)
+        os.environ.get("SLM_PRECISION", "fp32"), int(getattr(args, "batch", 32)), bool(args.preview), gather=False,
+        inc_amp=inc)
     from .display_holograms import preview_to_grey
     for k in range(hi - lo):
         i = lo + k

@@ -109,3 +109,22 @@ def test_single_trap_and_device_frames(golden):
 
 def test_device_mt19937_stream():
     pc.check_device_mt19937(make_engine)
+
+
+def test_sequence_driver_with_illumination_plane():
+    """The movie driver hands a non-uniform illumination amplitude (algorithms.py:14-19) to every frame."""
+    import numpy as np
+    from spatial_light_modulator_module_b200 import generate_hologram_sequence as ghs, synthetic
+    shape = (128, 128)
+    frames = np.stack([synthetic.noise_target(shape, seed=s) for s in range(3)])
+    yy, xx = np.mgrid[0:shape[0], 0:shape[1]]
+    inc = np.sqrt(np.exp(-((yy - 64.0) ** 2 + (xx - 64.0) ** 2) / 3000.0) * 255).astype(np.float16).astype(np.float64)
+    holos, exps, errors, _ = ghs.sequence_holograms(frames, 4, precision="fp64", batch=2, want_expected=True,
+                                                    engine_factory=make_engine, inc_amp=inc)
+    eng = make_engine(shape, "fp64", 1)
+    for i in range(3):
+        r = eng.gs(frames[i], 4, inc_amp=inc)
+        np.testing.assert_array_equal(holos[i], eng.to_host(r.hologram)[0])
+        np.testing.assert_array_equal(exps[i], eng.to_host(r.expected)[0])
+        np.testing.assert_array_equal(errors[i], r.errors[0])
+    eng.close()
