@@ -28,9 +28,14 @@ def _dist():
 
 def sequence_holograms(frames, max_loops: int, tolerance: float = 0.0, precision: str = "fp32",
                        batch: int = 32, want_expected: bool = False, engine_factory: Optional[Callable] = None,
-                       gather: bool = True, inc_amp=None):
+                       gather: bool = True, inc_amp=None, warm_start: bool = False):
     """GS holograms of ``frames`` (uint8 [F,H,W]); ``inc_amp``: illumination amplitude plane [H,W] shared by all
     frames (algorithms.py:14-19), None = uniform.
+
+    ``warm_start`` (an extension, off by default because it changes the results): every frame of a rank's block
+    starts from the previous frame's hologram (``B = inc * exp(1j * hologram)``) instead of the reference's
+    ``ifft2(sqrt(target))`` setup, which lets a slowly moving trap pattern converge in a few iterations; the frames
+    are then processed one after the other.
 
     Under an initialised process group every rank passes the SAME ``frames`` and computes only its
     block; with ``gather`` the full results are returned on rank 0 (other ranks get their own
@@ -53,6 +58,16 @@ def sequence_holograms(frames, max_loops: int, tolerance: float = 0.0, precision
     holos = eng.host_empty((n_local,) + shape, np.float64)
     exps = eng.host_empty((n_local,) + shape, np.float64) if want_expected else None
     errors: List[np.ndarray] = []
+    if warm_start:
+        phasor = None
+        for s in range(n_local):
+            res = eng.gs(frames[lo + s:lo + s + 1], max_loops, tolerance, inc_amp=inc_amp, phasor0=phasor, want_expected=want_expected)
+            holos[s] = eng.to_host(res.hologram)[0]
+            if want_expected:
+                exps[s] = eng.to_host(res.expected)[0]
+            errors.extend(res.errors)
+            phasor = eng.phase_phasor(res.hologram, inc_amp)
+        n_local = 0                                      # nothing left for the batched loop below
     # the read-back of one batch (float64: 8 bytes per pixel and frame) runs beside the iterations of the next one
     pending = []
     for s in range(0, n_local, batch):

@@ -128,3 +128,23 @@ def test_sequence_driver_with_illumination_plane():
         np.testing.assert_array_equal(exps[i], eng.to_host(r.expected)[0])
         np.testing.assert_array_equal(errors[i], r.errors[0])
     eng.close()
+
+
+def test_sequence_driver_warm_start():
+    """Opt-in warm start: frame n starts from frame n-1's hologram; equals the hand-made chain, and on a slowly
+    moving trap pattern the warm-started frames begin from a far smaller error than cold ones."""
+    import numpy as np
+    from spatial_light_modulator_module_b200 import generate_hologram_sequence as ghs, synthetic
+    frames = synthetic.movie_frames(3, rescale_parameter=0.2)[:, :128, :128].copy()
+    frames[:, 40, 50] = 255
+    holos, _, errors, _ = ghs.sequence_holograms(frames, 5, precision="fp64", engine_factory=make_engine, warm_start=True)
+    eng = make_engine(frames.shape[1:], "fp64", 1)
+    phasor = None
+    for i in range(3):
+        r = eng.gs(frames[i], 5, phasor0=phasor)
+        np.testing.assert_array_equal(holos[i], eng.to_host(r.hologram)[0])
+        np.testing.assert_array_equal(errors[i], r.errors[0])
+        phasor = eng.phase_phasor(r.hologram)
+    cold, _, cold_errors, _ = ghs.sequence_holograms(frames, 5, precision="fp64", engine_factory=make_engine)
+    assert errors[2][0] < cold_errors[2][0]
+    eng.close()
