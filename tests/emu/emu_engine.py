@@ -58,6 +58,10 @@ class EmuEngine(Engine):
     def _mem_download(self, buf):
         return np.asarray(buf).copy()
 
+    def _mem_plane_max(self, dev):
+        a = np.asarray(dev)
+        return a.reshape(a.shape[0], -1).max(axis=1).astype(np.float64)
+
     def _mem_host_empty(self, shape, dtype):
         return np.empty(shape, dtype=dtype)
 
