@@ -437,16 +437,22 @@ def run_slab(a):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0 and not os.environ.get("SLM_BENCH_NO_SAMPLER"):
+        sampler.start()
     for _ in range(max(a.warmup, 1)):
         eng.gs(slab, 2, want_expected=False, on_device=True)
     barrier()
     n0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.time()
     e0.record()
     for _ in range(a.steps):
         holo, _, errs = eng.gs(slab, loops, want_expected=False, on_device=True)
     e1.record()
     barrier()
+    wall1 = time.time()
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     ms = e0.elapsed_time(e1)
     if world > 1:
         tmax = torch.tensor([ms], device=torch.device("cuda", local_rank), dtype=torch.float64)
@@ -465,7 +471,7 @@ def run_slab(a):
             "config": {"workload": f"gerchberg_saxton, one {n}x{n} uint8 noise target, {loops} iterations incl. setup and the final "
                                    f"hologram read-back, rows split over {world} GPU(s), 2 all-to-alls + 1 all-reduce per iteration "
                                    f"(BASELINE.json configs[4])"},
-            "gpu_launches": int(launches), "final_error": float(errs[-1]),
+            "gpu_launches": int(launches), "final_error": float(errs[-1]), "clocks": clocks,
             "iteration_roofline": {"alg_bytes_per_iteration": it_bytes, "achieved": it_bytes / per_it / 1e9 / world, "peak": peak,
                                    "unit": "GB/s per GPU", "frac": it_bytes / per_it / 1e9 / world / peak, "peak_source": peak_src},
         }))
