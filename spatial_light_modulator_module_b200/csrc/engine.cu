@@ -649,6 +649,15 @@ extern "C" int slm_rows_create(slm_ctx** out, int device, int rows, int W, int p
     return 0;
 }
 
+// exchange-layout block width the row kernels can address: a power-of-two number of runs of M = threads-per-line points
+static bool block_width_ok(const slm_ctx* c, int wb) {
+    if (wb == 0) return true;
+    const int m = c->row->row_threads / c->row->rows_per_cta;
+    if (wb < m || wb % m) return false;
+    const int q = wb / m;
+    return (q & (q - 1)) == 0;
+}
+
 extern "C" int slm_rows_fft(slm_ctx* c, const void* in, const uint8_t* in_u8, const double* lut, void* out, int inverse,
                             int block_in, int block_out) {
     if (!c || !out || (!in && !in_u8) || (in_u8 && !lut)) return fail(SLM_ERR_ARG, "slm_rows_fft: bad argument");
@@ -677,6 +686,8 @@ extern "C" int slm_rows_gs_row_pass(slm_ctx* c, const void* in, void* out, const
 extern "C" int slm_rows_gs_fourier_pass(slm_ctx* c, const void* in, void* out, int block_w, const uint8_t* target_u8,
                                         const double* amp_lut, double scale_prev, double* partial, double* intensity) {
     if (!c || !in || !out || !target_u8 || !amp_lut || !partial) return fail(SLM_ERR_ARG, "slm_rows_gs_fourier_pass: bad argument");
+    if (!block_width_ok(c, block_w))
+        return fail(SLM_ERR_SHAPE, "slm_rows_gs_fourier_pass: the exchange block width must be a power-of-two multiple of the line's thread count");
     SLM_CUDA(cudaSetDevice(c->device));
     SLM_TRY(upload_lut(c, amp_lut));
     RowFourierArgs fa{};
