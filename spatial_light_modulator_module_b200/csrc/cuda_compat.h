@@ -20,7 +20,7 @@
 #define SLM_HOSTDEV __host__ __device__
 #define SLM_LAUNCH_BOUNDS(t, b) __launch_bounds__(t, b)
 // dynamic shared memory of the running CTA
-#define SLM_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#define SLM_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]   // (swizzled TMA tiles and the XOR-addressed exchange assume 1 KB)
 #define SLM_STATIC_SMEM __shared__
 #define SLM_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #define SLM_RESTRICT __restrict__
