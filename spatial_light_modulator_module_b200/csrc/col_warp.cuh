@@ -373,8 +373,10 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
             tile_load(tm_in, tile_buf(s), bar(full, s), (long long)b * H, H, (long long)tile * ROWB, ROWB, (int)sizeof(R));
         };
         // the tile that will be loaded when the next buffer frees: have L2 fetch it now, so that load is an L2 hit
+        // (A/B on one box: GS pass +2 %; the light max passes, which run near the memory system's limits, lose 4 %
+        //  to the extra requests and do without)
         auto prefetch = [&](const TileDesc& d) {
-            if (lane != 0 || d.g < 0) return;
+            if (IS_STATS || lane != 0 || d.g < 0) return;
             const int b = (int)(d.g / tiles), tile = (int)(d.g % tiles);
             tile_prefetch(tm_in, (long long)b * H, H, (long long)tile * ROWB, (int)sizeof(R));
         };
