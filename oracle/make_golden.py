@@ -64,9 +64,35 @@ def targets(shape):
             "traps": synthetic.traps_target(shape)}
 
 
+def benched_path_fixtures(alg):
+    """Round 2: the exact configuration bench.py times (config 2 at the metric shape 1024x1024, 100 iterations)
+    and the 8-bit frames of config 2 (mask add + quantise, move_traps.py:135-140 / display_holograms.py:253-266)
+    from the reference's own holograms.  Frames are stored as a 4x4-strided subsample + SHA-256."""
+    from PIL import Image as im
+    sub = (slice(None, None, 16), slice(None, None, 16))
+    sub4 = (slice(None, None, 4), slice(None, None, 4))
+    for shape in ((1024, 1024), (768, 1024)):
+        t = synthetic.noise_target(shape, seed=0)
+        mask = synthetic.random_mask(shape, seed=1)
+        holo, exp, errs = quiet(alg.gradient_descent, t, ns(max_loops=100))
+        q3 = ((holo + mask) % (2 * np.pi) * 256 / (2 * np.pi)).astype(np.uint8)            # move_traps.py:135-140
+        q2 = np.array(im.fromarray((holo + mask) % (2 * np.pi) / (2 * np.pi) * 256).convert("L"))   # display_holograms.py:257-260
+        extra = dict(errors=np.array(errs), hologram_sub=holo[sub], expected_sub=exp[sub], hologram_sha=np.array(sha(holo)),
+                     seed=np.array(0)) if shape == (1024, 1024) else {}
+        save(f"gd_noise_{shape[0]}x{shape[1]}_{'curves' if extra else 'frames'}", q3_sub=q3[sub4], q2_sub=q2[sub4],
+             q3_sha=np.array(sha(q3)), mask_seed=np.array(1), ct2pi=np.array(256), **extra)
+    t = synthetic.noise_target((1024, 1024), seed=0)
+    holo, exp, errs = quiet(alg.gerchberg_saxton, t, ns(max_loops=10))
+    save("gs_noise_1024x1024_curves", errors=np.array(errs), hologram_sub=holo[sub], expected_sub=exp[sub],
+         hologram_sha=np.array(sha(holo)), seed=np.array(0))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     alg = reference_loader.load("algorithms")
+    if "--benched-path" in sys.argv:             # only the round-2 fixtures (the others are unchanged)
+        benched_path_fixtures(alg)
+        return
     gh = reference_loader.load("generate_hologram")
     wfc = reference_loader.load("wavefront_correction")
     dh = reference_loader.load("display_holograms")
@@ -135,6 +161,8 @@ def main():
     holo, exp, errs = quiet(alg.gradient_descent, t, ns(max_loops=100))
     save("gd_noise_768x1024_curves", errors=np.array(errs), hologram_sub=holo[sub], expected_sub=exp[sub],
          hologram_sha=np.array(sha(holo)), seed=np.array(0))
+
+    benched_path_fixtures(alg)
 
     # ---- analytic holograms --------------------------------------------------------------
     d = wfc.deflect_2pi((1.0, 2.0))

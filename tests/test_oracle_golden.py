@@ -125,6 +125,27 @@ def test_full_size_curves(golden):
         np.testing.assert_allclose(np.array(errs)[:4], g["errors"][:4], rtol=1e-9)
 
 
+def test_benched_path_fixtures(golden):
+    """Round-2 fixtures (oracle/make_golden.py --benched-path): config 2 at the metric shape, 100 iterations, and the
+    8-bit frames of the reference's hologram (mask add + floor / PIL-float32 quantisation)."""
+    g = golden("gd_noise_1024x1024_curves")
+    holo, exp, errs, _ = P.gd_run(synthetic.noise_target((1024, 1024), seed=0), 100)
+    mask = synthetic.random_mask((1024, 1024), seed=1)
+    if same_libs(g):
+        np.testing.assert_array_equal(np.array(errs), g["errors"])
+        assert sha(holo) == str(g["hologram_sha"])
+        assert sha(P.quantize_q3(holo, mask, 256)) == str(g["q3_sha"])
+        np.testing.assert_array_equal(P.quantize_q2(holo, mask, 256)[::4, ::4], g["q2_sub"])
+    else:  # pragma: no cover
+        np.testing.assert_allclose(np.array(errs), g["errors"], rtol=1e-9)
+    g = golden("gs_noise_1024x1024_curves")
+    _, _, errs = P.gs_run(synthetic.noise_target((1024, 1024), seed=0), 10)
+    if same_libs(g):
+        np.testing.assert_array_equal(np.array(errs), g["errors"])
+    else:  # pragma: no cover
+        np.testing.assert_allclose(np.array(errs)[:4], g["errors"][:4], rtol=1e-9)
+
+
 def test_analytic(golden):
     g = golden("analytic")
     d = P.deflect_phase((1.0, 2.0))
