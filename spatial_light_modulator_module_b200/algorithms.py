@@ -189,7 +189,8 @@ def _gs_with_snapshots(eng, target, inc, args):
         if last % args.gif_skip == 0:
             _save_snapshot(args, expected, hologram, last)
         done += n
-        if len(res.errors[0]) < n:
+        # the loop condition (algorithms.py:29) holds across chunk borders: a chunk's last error ends the run too
+        if len(res.errors[0]) < n or not (errors[-1] > float(args.tolerance)):
             break
         phasor = eng.phase_phasor(res.hologram, inc)
     return hologram, expected, errors
@@ -206,6 +207,6 @@ def _gd_with_snapshots(eng, target, x0, during, inc, args):
         if last % args.gif_skip == 0:
             _save_snapshot(args, expected, hologram, last)
         done += n
-        if len(res.errors[0]) < n:
+        if len(res.errors[0]) < n or not (errors[-1] > float(args.tolerance)):     # algorithms.py:83
             break
     return hologram, expected, errors

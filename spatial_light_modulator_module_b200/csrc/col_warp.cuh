@@ -44,7 +44,7 @@ template <typename R, int H> struct ColWarpGeom {
     static constexpr size_t OFF_ORDER = OFF_DESC + NBUF * 32;     // [NBUF] staging orders of the sequencer to its helpers
     static constexpr size_t OFF_FMX = OFF_ORDER + NBUF * 8;       // CGM_GD_FUSED: [NBUF][TC] column maxima, [NBUF] plane max
     static constexpr size_t OFF_BAR = OFF_FMX + NBUF * (TC + 2) * 4;
-    static constexpr size_t SMEM = OFF_BAR + 4 * NBUF * 32;
+    static constexpr size_t SMEM = OFF_BAR + 5 * NBUF * 32;
     static_assert(!OK || SMEM <= 232448, "shared memory budget");
 };
 
@@ -204,7 +204,7 @@ SLM_DEV void close_plane(const ColArgs& a, int b, const Partial& tot, double s0,
         st->imax = tot.mx; st->scale = sN;
     } else {
         err = tot.a / hw;                                // algorithms.py:92
-        if (MODE == CGM_GD_FUSED) {                      // every tile of the plane has used the max: record and re-arm
+        if (MODE == CGM_GD_FUSED || MODE == CGM_GD_PIPE) {   // every tile of the plane has used the max: record and re-arm
             const double pm = (double)__uint_as_float(ld_cg(a.fused_max + b));
             st->imax = pm; st->scale = norm / pm;
             a.fused_max[b] = 0u; a.fused_count[b] = 0u;
@@ -220,7 +220,7 @@ SLM_DEV void close_plane(const ColArgs& a, int b, const Partial& tot, double s0,
 // partial sums in the order collect_if_last uses, so both forms give the same bits.
 template <typename R, int H, int MODE>
 SLM_GLOBAL void SLM_LAUNCH_BOUNDS(32, 1) close_planes_kernel(ColGroupArgs ga, int tiles) {
-    constexpr bool IS_GD = MODE == CGM_GD || MODE == CGM_GD_POST || MODE == CGM_GD_FUSED;
+    constexpr bool IS_GD = MODE == CGM_GD || MODE == CGM_GD_POST || MODE == CGM_GD_FUSED || MODE == CGM_GD_PIPE;
     constexpr int FIELDS = MODE == CGM_GS ? F_ALL : (IS_GD ? F_A : F_MX);
     const ColArgs& a = ga.c;
     const int b = blockIdx.x, lane = threadIdx.x;
@@ -240,9 +240,11 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
     using G = ColWarpGeom<R, H>;
     constexpr int TC = G::TC, ROWB = G::ROWB, NBUF = G::NBUF;
     constexpr bool FUSED = MODE == CGM_GD_FUSED;
-    constexpr bool HAS_T = MODE == CGM_GS || MODE == CGM_GD || MODE == CGM_GD_POST || FUSED;
+    constexpr bool PIPE = MODE == CGM_GD_PIPE;                      // group 0 transforms forward, group 1 does the rest of the tile
+    constexpr int STOPS = PIPE ? 1 : G::GROUPS;                     // stop markers that end the kernel (PIPE: both groups see every item)
+    constexpr bool HAS_T = MODE == CGM_GS || MODE == CGM_GD || MODE == CGM_GD_POST || FUSED || PIPE;
     constexpr bool HAS_OUT = MODE != CGM_STATS;
-    constexpr bool IS_GD = MODE == CGM_GD || MODE == CGM_GD_POST || FUSED;
+    constexpr bool IS_GD = MODE == CGM_GD || MODE == CGM_GD_POST || FUSED || PIPE;
     constexpr bool IS_STATS = MODE == CGM_STATS || MODE == CGM_STATS_KEEP;
     constexpr bool HAS_STATS = MODE != CGM_COMPLEX;
     constexpr int FIELDS = MODE == CGM_GS ? F_ALL : (IS_GD ? F_A : F_MX);
@@ -255,6 +257,7 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
     TileBarrier* const done = reinterpret_cast<TileBarrier*>(raw + G::OFF_BAR + NBUF * 32);     // [NBUF] group is through the tile
     TileBarrier* const taken = reinterpret_cast<TileBarrier*>(raw + G::OFF_BAR + 2 * NBUF * 32); // [NBUF] publisher has the tile's sums
     TileBarrier* const ordered = reinterpret_cast<TileBarrier*>(raw + G::OFF_BAR + 3 * NBUF * 32); // [NBUF] a staging order is posted
+    TileBarrier* const fwd = reinterpret_cast<TileBarrier*>(raw + G::OFF_BAR + 4 * NBUF * 32);     // [NBUF] PIPE: the slot holds the transformed field
     auto tile_buf = [&](int s) { return raw + (size_t)s * G::TILE; };
     auto grey_buf = [&](int s) { return raw + G::OFF_GREY + (size_t)s * G::GREY; };
     auto bar = [](TileBarrier* base, int s) { return reinterpret_cast<TileBarrier*>(reinterpret_cast<unsigned char*>(base) + s * 32); };
@@ -270,6 +273,7 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
             mbar_init(bar(done, s), (unsigned)G::GROUP_THREADS);
             mbar_init(bar(taken, s), 1u);
             mbar_init(bar(ordered, s), 1u);
+            mbar_init(bar(fwd, s), (unsigned)G::GROUP_THREADS);
         }
         mbar_fence_init();
     }
@@ -322,7 +326,7 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
         if (!use_t8) return;
         const int who = t - G::COMPUTE - 32;
         int stops = 0;
-        for (unsigned k = 0; stops < G::GROUPS; ++k) {
+        for (unsigned k = 0; stops < STOPS; ++k) {
             const int s = (int)(k % NBUF);
             mbar_wait(bar(ordered, s), (k / NBUF) & 1u);
             const long long g = order[s];
@@ -383,7 +387,7 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
         TileDesc cur = resolve(peek(blockIdx.x));
         unsigned k = 0;                                      // next item (tile or stop marker) to issue
         int stops = 0;                                       // stop markers issued: one per group ends the kernel
-        while (k < (unsigned)NBUF && stops < G::GROUPS) {
+        while (k < (unsigned)NBUF && stops < STOPS) {
             const int s = (int)(k % NBUF);
             stage_grey(s, cur);
             sync_warp();
@@ -403,7 +407,7 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
                 tile_store(tm_out, tile_buf(s), (long long)b * H, H, (long long)tile * ROWB, ROWB, (int)sizeof(R));
                 tile_store_commit();
             }
-            if (stops < G::GROUPS) {
+            if (stops < STOPS) {
                 const Peek ahead = peek(cur.g < 0 ? total : cur.g + gridDim.x);   // in flight during the staging below
                 stage_grey(s, cur);                                       // the group is through this slot's grey rows
                 if (HAS_STATS) mbar_wait(bar(taken, s), par);            // the publisher has this slot's descriptor and sums
@@ -440,6 +444,118 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
     constexpr bool IN_B = MODE == CGM_GD_POST;                       // the tile already holds a transformed field
     constexpr bool OUT_B = MODE == CGM_STATS_KEEP;                   // the transformed field goes back as it is
     cpx<R> v[32];
+    if constexpr (PIPE) {
+        // ================= CGM_GD_PIPE: the two groups share every tile =================
+        // group 0: tile -> med_output = fft2(...) columns (algorithms.py:84), left in the buffer in side-B order; the tile's
+        //          max |F|^2 joins its plane's (atomic max), the plane's arrival count goes up -- and on to the next tile;
+        // group 1: once every tile of the plane has arrived (they are in flight on the other SMs, at most NBUF items
+        //          away), output = |F|^2 * norm / max, the error sum, mask * F * (output - T) and the inverse transform
+        //          (algorithms.py:85-88,92).  Same arithmetic, same bits as the two-pass and the fused forms.
+        float* const fmx = reinterpret_cast<float*>(raw + G::OFF_FMX);
+        if (grp == 0) {
+            for (unsigned k = 0;; ++k) {
+                const int s = (int)(k % NBUF);
+                const unsigned par = (k / NBUF) & 1u;
+                unsigned char* const buf = tile_buf(s);
+                mbar_wait(bar(full, s), par);
+                const TileDesc d = desc[s];
+                if (d.g < 0) break;
+                const int b = (int)(d.g / tiles);
+#pragma unroll
+                for (int p = 0; p < RA; ++p) v[p] = *reinterpret_cast<const cpx<R>*>(buf + my + 2048u * p);
+                sync_named(pair_bar, 64);                    // the partner holds its column too: the pair's chunk is free
+                warp_fft_forward<RA>(v, buf, lm, sm, w1);
+                R m = 0;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) m = fmax(m, cnorm2(v[r]));
+                if (!active) m = 0;
+#pragma unroll
+                for (int sh = 16; sh >= 1; sh >>= 1) m = fmax(m, shfl_xor(m, sh));
+                if (lane == 0) fmx[s * (TC + 2) + c] = m;
+                sync_named(pair_bar, 64);                    // the partner is through its exchange: its rows of my column are free
+                if (active) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) *reinterpret_cast<cpx<R>*>(buf + my + 64u * RA * q) = v[q];
+                }
+                sync_named(9, G::GROUP_THREADS);             // the eight column maxima are in shared memory
+                if (c == 0 && lane == 0) {
+                    float mm = fmx[s * (TC + 2)];
+#pragma unroll
+                    for (int i = 1; i < TC; ++i) mm = fmax(mm, fmx[s * (TC + 2) + i]);
+                    atomic_max_u32(a.fused_max + b, __float_as_uint(mm));       // |F|^2 >= 0: ordered like its bit pattern
+                    fence_device();
+                    atomic_add_u32(a.fused_count + b, 1u);
+                }
+                mbar_arrive(bar(fwd, s));                    // (after the atomics: whoever passes fwd finds this tile counted)
+            }
+            return;
+        }
+        for (unsigned k = 0;; ++k) {
+            const int s = (int)(k % NBUF);
+            const unsigned par = (k / NBUF) & 1u;
+            unsigned char* const buf = tile_buf(s);
+            mbar_wait(bar(full, s), par);
+            const TileDesc d = desc[s];
+            if (d.g < 0) break;
+            const int b = (int)(d.g / tiles), tile = (int)(d.g % tiles);
+            mbar_wait(bar(fwd, s), par);
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v[q] = *reinterpret_cast<const cpx<R>*>(buf + my + 64u * RA * q);
+            if (c == 0 && lane == 0) {
+                // the plane's other tiles: counted already, or being transformed on other SMs right now (cooperative
+                // launch: every CTA is resident).  The time-out only guards against a broken launch.
+                const long long t0 = clock_now();
+                while (ld_acquire(a.fused_count + b) < (unsigned)tiles) {
+                    spin_pause();
+                    if (clock_now() - t0 > (1ll << 32)) { atomic_max_u32(a.fused_count + (size_t)a.max_planes, 1u); break; }
+                }
+                fmx[s * (TC + 2) + TC] = __uint_as_float(ld_cg(a.fused_max + b));
+            }
+            sync_named(10, G::GROUP_THREADS);
+            const R gdk = (R)(d.norm / (double)fmx[s * (TC + 2) + TC]);
+            sync_named(pair_bar, 64);                        // the partner holds its column too: the pair's chunk is free
+            R sa = 0;
+            {
+                const uint8_t* gsrc = grey_buf(s) + (size_t)lane * TC + c;
+                const size_t goff = (size_t)b * H * a.W + (size_t)lane * a.W + tile * TC + c;
+#pragma unroll
+                for (int r0 = 0; r0 < 32; r0 += 8) {
+                    R tv[8], aux[8];
+                    if (use_t8) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { const int gl = gsrc[(size_t)(r0 + i) * RA * TC]; tv[i] = (R)gl; aux[i] = lut_s[gl]; }
+                    } else {
+                        const R* T = static_cast<const R*>(a.Treal) + goff;
+                        const R* Q = static_cast<const R*>(a.plane2) + goff;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            tv[i] = active ? ld_ro(T + (size_t)(r0 + i) * RA * a.W) : (R)0;
+                            aux[i] = active ? ld_ro(Q + (size_t)(r0 + i) * RA * a.W) : (R)0;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {            // algorithms.py:85-88,92
+                        const int r = r0 + i;
+                        const R I = cnorm2(v[r]) * gdk;
+                        const R dd = I - tv[i];
+                        sa += dd * dd;
+                        v[r] = cscale(cscale(v[r], aux[i]), dd);
+                    }
+                }
+            }
+            if (!active) sa = 0;                             // lanes outside side B hold no points
+            Partial p; p.mx = 0; p.a = (double)sa; p.b = 0; p.c = 0;
+            p = warp_reduce<FIELDS>(p);
+            if (lane == 0) red[s * TC + c] = p;              // (the sequencer reissued this slot only after its sums were taken)
+            warp_fft_inverse<RA>(v, buf, lm, sm, w1, active);
+            sync_named(pair_bar, 64);                        // the partner is through its exchange: its rows of my column are free
+#pragma unroll
+            for (int p2 = 0; p2 < RA; ++p2) *reinterpret_cast<cpx<R>*>(buf + my + 2048u * side_a_index<RA>(p2)) = v[p2];
+            fence_async_smem();
+            mbar_arrive(bar(done, s));
+        }
+        return;
+    }
     for (unsigned k = (unsigned)grp;; k += G::GROUPS) {
         const int s = (int)(k % NBUF);
         const unsigned par = (k / NBUF) & 1u;

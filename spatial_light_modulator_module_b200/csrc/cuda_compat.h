@@ -42,6 +42,19 @@ template <class K, class... A> inline void launch_pdl(K kernel, dim3 grid, dim3 
     cfg.attrs = attr; cfg.numAttrs = 1;
     cudaLaunchKernelEx(&cfg, kernel, args...);
 }
+// Cooperative launch: the whole grid is resident at once (the launch fails otherwise), so CTAs may wait for one
+// another through global memory.
+#define SLM_LAUNCH_COOP(kernel, grid, block, smem, stream, ...) slm::launch_coop(kernel, grid, block, smem, stream, __VA_ARGS__)
+template <class K, class... A> inline void launch_coop(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+SLM_DEV void spin_pause() { __nanosleep(20); }       // inside a wait on another CTA's progress
 SLM_DEV void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 SLM_DEV void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 template <typename T> SLM_DEV T ld_ro(const T* p) { return __ldg(p); }     // immutable during the launch

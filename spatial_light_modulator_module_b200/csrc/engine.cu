@@ -46,6 +46,7 @@ struct slm_ctx {
     unsigned* counter = nullptr;
     unsigned* fused = nullptr;                            // [3][max_batch]: plane max bits, tile count of CGM_GD_FUSED, [0] of the third row: time-out flag
     int fused_ctas = 0;                                   // grid of the fused GD column pass (0: two passes)
+    bool pipe_ok = false;                                 // CGM_GD_PIPE may be used (warp-per-column kernel, a plane's tiles fit the CTAs' buffers)
     double *err_curve = nullptr, *lr = nullptr, *norm = nullptr;
     void* lut = nullptr;
     float* lut32 = nullptr;
@@ -169,6 +170,14 @@ static int setup_groups(slm_ctx* c) {
     c->persist_ctas = sms > 0 ? sms : 1;
 #endif
     c->use_groups = true;
+    {
+        // The pipelined one-pass form: a tile waits (in a buffer) for the other tiles of its plane, which sit in at most
+        // ceil(tiles / CTAs) buffers of every other CTA -- that many must exist (three per CTA), or the planes could not
+        // complete.  The warp-per-column kernel only.
+        const char* ck = getenv("SLM_COL_KERNEL");
+        const int tiles = c->W / c->col->cols_per_cta;
+        c->pipe_ok = c->col->group_fused && !(ck && ck[0] == 'g') && tiles <= 3 * c->persist_ctas;
+    }
 #ifndef SLM_EMULATE
     // One fused Fourier-plane pass per GD iteration needs every tile of a plane on an SM at the same time: grid = a
     // whole number of planes' tiles, all CTAs resident (one per SM).  Worth it when that grid fills most of the device.
@@ -500,14 +509,23 @@ extern "C" int slm_gd_run(slm_ctx* c, int batch, const uint8_t* T8, const void* 
     // The fused pass saves a launch and a trip of the field through L2/HBM per iteration, but its CTAs wait for each
     // other once per plane and it leaves the SMs beyond a whole number of planes idle: measured faster for a few
     // planes (latency bound: 2.9 vs 3.3 ms per 100-iteration hologram), slower for a large batch (47.9 vs 46.4 ms).
-    static const char* fused_always = getenv("SLM_FUSED_GD_ALWAYS");      // developer switch (A/B measurements)
-    const bool fused = c->use_groups && c->fused_ctas &&
-                       (fused_always || (long long)batch * (c->W / c->col->cols_per_cta) <= 4LL * c->persist_ctas);
+    // Larger batches: the same single pass with the wait taken out of the SMs' way (CGM_GD_PIPE).  SLM_GD_FORM =
+    // fused | pipe | two_pass overrides the choice (tests, A/B measurements); read per call.
+    const char* form = getenv("SLM_GD_FORM");
+    const bool few = (long long)batch * (c->W / c->col->cols_per_cta) <= 4LL * c->persist_ctas;
+    bool fused = c->use_groups && c->fused_ctas && !getenv("SLM_NO_FUSED_GD") && few;
+    bool pipe = c->use_groups && c->pipe_ok && !getenv("SLM_NO_FUSED_GD") && !fused;
+    if (form && c->use_groups) {
+        fused = form[0] == 'f' && c->fused_ctas;
+        pipe = form[0] == 'p' && c->pipe_ok;
+    }
     for (int k = 0; k < max_loops; ++k) {
         if (fused) {
             // one Fourier-plane pass: the tiles of a plane agree on amax(output_unnormed) (algorithms.py:86) between
             // their forward transforms and the gradient step
             SLM_TRY(launch_group(c, CGM_GD_FUSED, batch, &ca, &c->map_y, 0, 1.0));
+        } else if (pipe) {
+            SLM_TRY(launch_group(c, CGM_GD_PIPE, batch, &ca, &c->map_y, 0, 1.0));
         } else if (c->use_groups) {
             // med_output = fft2(...) is finished in place in X while its max is taken (algorithms.py:84-86),
             // so the gradient pass starts from the transformed field
@@ -528,8 +546,8 @@ extern "C" int slm_gd_run(slm_ctx* c, int batch, const uint8_t* T8, const void* 
     SLM_TIMED(K_ROW_PASS, c->row->row_pass(ALG_GD, ra, c->stream));
     if (expected_out) {
         PlainColArgs ia = stats_args(c, batch, OUT_INTENSITY_GD, expected_out);
-        // two-pass form: X already holds med_output; fused form: transform X once more (same kernel arithmetic), kept
-        if (fused) SLM_TRY(launch_group(c, CGM_STATS_KEEP, batch, nullptr, &c->map_x, 0, 1.0, 1));
+        // two-pass form: X already holds med_output; one-pass forms: transform X once more (same kernel arithmetic), kept
+        if (fused || pipe) SLM_TRY(launch_group(c, CGM_STATS_KEEP, batch, nullptr, &c->map_x, 0, 1.0, 1));
         ia.skip_fft = 1;
         SLM_TIMED(K_COL_PLAIN, c->col->col_plain(ia, c->stream));
     }

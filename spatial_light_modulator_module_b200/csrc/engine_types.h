@@ -81,6 +81,9 @@ enum ColGroupMode {
     CGM_GD_FUSED = 6,    // CGM_GD that takes the plane's max ITSELF: every tile of a plane is in flight at once (grid = a
                          // multiple of the tiles per plane, all CTAs resident), tiles meet at a per-plane counter between
                          // the forward transform and the pointwise step (warp-per-column kernel only)
+    CGM_GD_PIPE = 7,     // CGM_GD_FUSED for any batch, on every SM: the CTA's two compute groups split the tile's work -- one
+                         // forward-transforms tile after tile (and feeds the planes' maxima), the other takes each tile on once
+                         // its plane's maximum is complete -- so nobody idles while a plane's tiles meet.  Cooperative launch.
 };
 struct ColGroupArgs {
     int mode_inverse;        // CGM_COMPLEX: transform direction

@@ -24,6 +24,7 @@ template <typename R, int L> struct ColWarpLaunch<R, L, true> {
     }
     static void prepare() {
         attr<CGM_GS>(); attr<CGM_GD_FUSED>(); attr<CGM_STATS>(); attr<CGM_COMPLEX>(); attr<CGM_STATS_KEEP>(); attr<CGM_GD_POST>();
+        attr<CGM_GD_PIPE>();
     }
     static bool enabled() {
         static const bool on = !(getenv("SLM_COL_KERNEL") && getenv("SLM_COL_KERNEL")[0] == 'g');
@@ -32,7 +33,9 @@ template <typename R, int L> struct ColWarpLaunch<R, L, true> {
     template <int MODE> static void run(int mode, const ColGroupArgs& ga, const TileMap& in, const TileMap& out, dim3 grid, dim3 block,
                                         cudaStream_t s) {
         if (mode != MODE) return;
-        SLM_LAUNCH_PDL((col_warp_kernel<R, L, MODE>), grid, block, WG::SMEM, s, ga, in, out);
+        // (CGM_GD_PIPE: tiles wait for the other tiles of their plane, which other CTAs hold -- all of them must be resident)
+        if (MODE == CGM_GD_PIPE) SLM_LAUNCH_COOP((col_warp_kernel<R, L, MODE>), grid, block, WG::SMEM, s, ga, in, out);
+        else SLM_LAUNCH_PDL((col_warp_kernel<R, L, MODE>), grid, block, WG::SMEM, s, ga, in, out);
         if (MODE != CGM_COMPLEX && ga.defer_close)
             SLM_LAUNCH((close_planes_kernel<R, L, MODE>), dim3((unsigned)ga.c.B), dim3(32), 0, s, ga, ga.c.W / WG::TC);
     }
@@ -42,6 +45,7 @@ template <typename R, int L> struct ColWarpLaunch<R, L, true> {
         const dim3 grid((unsigned)(tiles < ctas ? tiles : ctas)), block(WG::THREADS);
         run<CGM_GS>(mode, ga, in, out, grid, block, s);
         run<CGM_GD_FUSED>(mode, ga, in, out, grid, block, s);
+        run<CGM_GD_PIPE>(mode, ga, in, out, grid, block, s);
         run<CGM_STATS>(mode, ga, in, out, grid, block, s);
         run<CGM_STATS_KEEP>(mode, ga, in, out, grid, block, s);
         run<CGM_GD_POST>(mode, ga, in, out, grid, block, s);
@@ -73,7 +77,7 @@ template <typename R, int L> struct GroupLaunch<R, L, true> {
         static_assert(!ColWarpGeom<R, L>::OK || (ColWarpGeom<R, L>::TC == GG::TC && ColWarpGeom<R, L>::ROWB == GG::ROWB),
                       "both column kernels must share the tile maps and the per-tile partial sums");
         if (ColWarpLaunch<R, L>::launch(mode, ga, in, out, ctas, s)) return 0;
-        if (mode == CGM_GD_FUSED) return -1;                 // only the warp-per-column kernel has it
+        if (mode == CGM_GD_FUSED || mode == CGM_GD_PIPE) return -1;     // only the warp-per-column kernel has them
         const long long tiles = (long long)ga.c.B * (ga.c.W / GG::TC);
         const dim3 grid((unsigned)(tiles < ctas ? tiles : ctas)), block(GG::THREADS);
         run<CGM_GS>(mode, ga, in, out, grid, block, s);

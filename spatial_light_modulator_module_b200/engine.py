@@ -108,6 +108,9 @@ class Engine:
         """max over each plane of a uint8 device stack [B,H,W] -> float64 [B] on the host."""
         return np.ascontiguousarray(dev.reshape(dev.shape[0], -1).amax(dim=1).double().cpu().numpy(), dtype=np.float64)
 
+    def _mem_contiguous(self, dev):
+        return dev.contiguous()
+
     def _mem_is_device(self, obj) -> bool:
         return hasattr(obj, "data_ptr")
 
@@ -161,12 +164,12 @@ class Engine:
         if self._mem_is_device(targets):
             if self._mem_np_dtype(targets) != np.uint8:
                 raise TypeError("device-resident targets must be uint8")
-            t = targets if targets.dim() == 3 else targets[None]
+            t = targets if len(targets.shape) == 3 else targets[None]
             self._shape_check(tuple(t.shape[1:]))
             if norms is None:
-                norms = t.reshape(t.shape[0], -1).amax(dim=1).double().cpu().numpy()
+                norms = self._mem_plane_max(t)
             norms = np.ascontiguousarray(norms, dtype=np.float64)
-            return t.shape[0], t.contiguous(), None, None, norms, True
+            return t.shape[0], self._mem_contiguous(t), None, None, norms, True
         t = np.asarray(targets)
         if t.ndim == 2:
             t = t[None]
@@ -404,12 +407,32 @@ class Engine:
     def to_host_many(self, bufs):
         return self._mem_download_many(list(bufs))
 
-    def to_host_into(self, buf, out: np.ndarray):
+    def to_host_into(self, buf, out: np.ndarray, after=None):
         """Start copying a device buffer into the host array ``out`` (same shape and dtype) while the engine's
-        stream goes on with other work; returns a handle whose ``join()`` waits for the copy."""
-        return self._mem_download_into(buf, out)
+        stream goes on with other work; returns a handle whose ``join()`` waits for the copy.  ``after``: a
+        torch.distributed work handle that must complete first (the collective that fills ``buf``)."""
+        return self._mem_download_into(buf, out, after)
 
-    def _mem_download_into(self, buf, out):
+    def gather_to_root(self, buf, padded_shape, dtype, dist, dst: int = 0):
+        """Device-to-device gather of one equally shaped block per rank onto rank ``dst`` (NCCL over NVLink), ordered
+        behind the engine's stream and not waited for: returns ``.blocks`` (one device buffer per rank on ``dst``,
+        else None) and ``.work`` (pass it to :meth:`to_host_into`).  ``buf`` may be None or shorter than
+        ``padded_shape`` along the first axis (ragged last batch): the tail is padding nobody reads."""
+        return self._mem_gather_to_root(buf, tuple(padded_shape), dtype, dist, dst)
+
+    def _mem_gather_to_root(self, buf, padded_shape, dtype, dist, dst):
+        torch = self._torch
+        with torch.cuda.stream(self._stream):          # the collective is ordered behind the kernels of this stream
+            if buf is None or tuple(buf.shape) != padded_shape:
+                pad = self._mem_empty(padded_shape, dtype)
+                if buf is not None:
+                    pad[:buf.shape[0]].copy_(buf)
+                buf = pad
+            blocks = [torch.empty_like(buf) for _ in range(dist.get_world_size())] if dist.get_rank() == dst else None
+            work = dist.gather(buf, blocks, dst=dst, async_op=True)
+        return _Gathered(blocks, work, buf)
+
+    def _mem_download_into(self, buf, out, after=None):
         import threading
         torch = self._torch
         if not out.flags.c_contiguous or out.dtype != self._mem_np_dtype(buf) or tuple(out.shape) != tuple(buf.shape):
@@ -424,6 +447,8 @@ class Engine:
         dst = torch.from_numpy(out)
         if dst.is_pinned():                              # page-locked destination (host_empty): a plain asynchronous DMA
             with torch.cuda.stream(side):
+                if after is not None:
+                    after.wait()                         # the copy stream (not the engine's) waits for the collective
                 side.wait_event(ready)
                 dst.copy_(buf, non_blocking=True)
                 done = torch.cuda.Event()
@@ -436,6 +461,8 @@ class Engine:
 
         def work():
             with torch.cuda.device(self._dev), torch.cuda.stream(side):
+                if after is not None:
+                    after.wait()
                 side.wait_event(ready)
                 dst.copy_(buf)                           # device -> host array directly (the driver stages pageable memory)
                 side.synchronize()
@@ -446,14 +473,14 @@ class Engine:
     def host_empty(self, shape, dtype) -> np.ndarray:
         """Host array for results that are read back with :meth:`to_host_into`: page-locked (from PyTorch's caching
         host allocator, so repeated calls neither pin nor page-fault again) up to ``SLM_PINNED_RESULT_BYTES``
-        (default 2 GiB), ordinary memory beyond."""
+        (default 8 GiB: a 1024-frame movie of float64 holograms at the SLM shape is 6 GiB), ordinary memory beyond."""
         return self._mem_host_empty(shape, dtype)
 
     def _mem_host_empty(self, shape, dtype):
         import os
         torch = self._torch
         nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
-        if nbytes == 0 or nbytes > int(os.environ.get("SLM_PINNED_RESULT_BYTES", 2 << 30)):
+        if nbytes == 0 or nbytes > int(os.environ.get("SLM_PINNED_RESULT_BYTES", 8 << 30)):
             return np.empty(shape, dtype=dtype)
         tdt = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32, np.dtype(np.uint8): torch.uint8}[np.dtype(dtype)]
         return torch.empty(tuple(shape), dtype=tdt, pin_memory=True).numpy()
@@ -487,6 +514,13 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+
+class _Gathered:
+    """Result of Engine.gather_to_root: keeps the source block alive until the collective has run."""
+
+    def __init__(self, blocks, work, source):
+        self.blocks, self.work, self.source = blocks, work, source
 
 
 # Host arrays a caller passes again and again (same memory) are page-locked in place on their second use, so later

@@ -24,7 +24,7 @@ def main(args):
     hologram = transform_hologram(hologram, args)
     if args.preview:
         show_expected_outcome(hologram, args)
-    save_hologram(hologram, args)
+    save_hologram_and_gif(hologram, args)
 
 
 def expected_outcome(hologram, norm=255, precision="fp64"):
@@ -64,8 +64,44 @@ def make_hologram(args):
     """reference: generate_hologram.py:70-79."""
     algorithm = gerchberg_saxton if args.algorithm == "gerchberg_saxton" else gradient_descent
     target = prepare_target(args.img_name, args)
+    if getattr(args, "gif", False):
+        add_gif_dirs(args)
+        remove_files_in_dir(args.gif_source_dir)
     hologram, _, _ = algorithm(target, args)
     return hologram
+
+
+def add_gif_dirs(args):
+    """reference: generate_hologram.py:90-99 -- where the per-iteration frames and the finished GIF go."""
+    if args.gif_type == "h":
+        args.gif_dest_dir = "holograms"
+    elif args.gif_type == "i":
+        args.gif_dest_dir = "images"
+    os.makedirs(args.gif_dest_dir, exist_ok=True)
+    args.gif_source_dir = f"{args.gif_dest_dir}/gif_source"
+    os.makedirs(args.gif_source_dir, exist_ok=True)
+
+
+def remove_files_in_dir(dir_name):
+    """reference: generate_hologram.py:216-219."""
+    for file in os.listdir(dir_name):
+        os.remove(f"{dir_name}/{file}")
+
+
+def create_gif(img_dir, outgif_path):
+    """All images of ``img_dir`` (in os.listdir order, like generate_hologram.py:206-213) -> one animated GIF.
+    imageio is used when it is installed (the reference's writer), Pillow's GIF encoder otherwise."""
+    files = [f"{img_dir}/{f}" for f in os.listdir(img_dir)]
+    try:
+        import imageio
+    except ImportError:
+        frames = [im.open(f).convert("L") for f in files]
+        if frames:
+            frames[0].save(outgif_path, save_all=True, append_images=frames[1:], loop=0)
+        return
+    with imageio.get_writer(outgif_path, mode="I") as writer:
+        for f in files:
+            writer.append_data(imageio.imread(f))
 
 
 def transform_hologram(hologram, args):
@@ -98,6 +134,14 @@ def save_hologram(hologram, args):
     name = wfc.originalize_name(f"{dest_dir}/{make_hologram_name(args, img_name)}.npy")
     np.save(name, hologram)
     return name
+
+
+def save_hologram_and_gif(hologram, args):
+    """reference: generate_hologram.py:113-128."""
+    save_hologram(hologram, args)
+    if getattr(args, "gif", False):
+        img_name = os.path.basename(args.img_name).split(".")[0] if args.img_name else "analytical"
+        create_gif(args.gif_source_dir, wfc.originalize_name(f"{args.gif_dest_dir}/{make_hologram_name(args, img_name)}.gif"))
 
 
 def make_hologram_name(args, img_name):
@@ -156,3 +200,47 @@ def lens(focal_length, shape, uint8_quirk: bool = True):
     eng = wfc._util_engine()
     out = eng.to_host(eng.lens_phase(focal_length, c.px_distance, c.wavelength, tuple(shape), uint8_quirk))
     return out.astype(np.uint8) if uint8_quirk else out
+
+
+def build_parser():
+    """The reference's command line (generate_hologram.py:222-369): same flags, defaults and types, so existing
+    invocations keep working; ``--precision`` is the one addition."""
+    import argparse
+    p = argparse.ArgumentParser(formatter_class=argparse.ArgumentDefaultsHelpFormatter,
+                                description="Phase hologram for a transmissive SLM, computed on a B200 (drop-in for the "
+                                            "reference's generate_hologram.py).  Holograms are saved as .npy files.")
+    p.add_argument("img_name", nargs="?", default=None, type=str, help="target image inside images/; omit for a pure deflect/lens hologram")
+    p.add_argument("-ii", "--incomming_intensity", type=str, default="uniform", help="illumination image path, or 'uniform'")
+    p.add_argument("-ig", "--initial_guess", type=str, default="random", choices=["random", "fourier"], help="initial guess of gradient_descent")
+    p.add_argument("-dest_dir", "--destination_directory", type=str, default="holograms", help="where the hologram is saved")
+    p.add_argument("-q", "--quarterize", action="store_true", help="shrink the target into one quadrant of a black image")
+    p.add_argument("-i", "--invert", action="store_true", help="invert the target image")
+    p.add_argument("-alg", "--algorithm", default="gerchberg_saxton", choices=["gerchberg_saxton", "gradient_descent"])
+    p.add_argument("-tol", "--tolerance", default=0, metavar="FLOAT", type=float, help="stop when the error falls to this value")
+    p.add_argument("-l", "--max_loops", default=42, metavar="INTEGER", type=int, help="upper bound on the number of iterations")
+    p.add_argument("-lr", "--learning_rate", default=0.005, type=float, help="gradient descent step")
+    p.add_argument("-wa", "--white_attention", metavar="FLOAT", default=1, type=float, help="error weight of white areas (gradient descent)")
+    p.add_argument("-u", "--unsettle", default=0, metavar="INTEGER", type=int, help="number of learning-rate doublings (gradient descent)")
+    p.add_argument("-gif", action="store_true", help="animated GIF of the iterations")
+    p.add_argument("-gif_t", "--gif_type", choices=["h", "i"], default="i", help="GIF of holograms (h) or of reconstructed images (i)")
+    p.add_argument("-gif_skip", default=1, type=int, metavar="INTEGER", help="every gif_skip-th iteration becomes a GIF frame")
+    p.add_argument("-plot_error", action="store_true", help="plot the error curve")
+    p.add_argument("-p", "--preview", action="store_true", help="show the expected outcome")
+    p.add_argument("-deflect", nargs=2, type=float, metavar=("X_ANGLE", "Y_ANGLE"), default=None,
+                   help="add a deflection hologram (units: a quarter of the first diffraction maximum)")
+    p.add_argument("-lens", default=None, type=float, metavar="FOCAL_LENGTH", help="add a lens of this focal length [m]")
+    p.add_argument("--precision", default=None, choices=["fp32", "fp64"], help="engine arithmetic (default fp32)")
+    return p
+
+
+def cli(argv=None):
+    args = build_parser().parse_args(argv)
+    args.random_seed = 42                       # generate_hologram.py:370-371
+    args.print_info = True
+    args.correspond_to2pi = 256                 # read by the "-gif -gif_t h" frames (the reference's parser omits it, SURVEY A.7)
+    os.makedirs(args.destination_directory, exist_ok=True)
+    main(args)
+
+
+if __name__ == "__main__":
+    cli()

@@ -28,95 +28,197 @@ def _dist():
 
 def sequence_holograms(frames, max_loops: int, tolerance: float = 0.0, precision: str = "fp32",
                        batch: int = 32, want_expected: bool = False, engine_factory: Optional[Callable] = None,
-                       gather: bool = True, inc_amp=None, warm_start: bool = False):
-    """GS holograms of ``frames`` (uint8 [F,H,W]); ``inc_amp``: illumination amplitude plane [H,W] shared by all
-    frames (algorithms.py:14-19), None = uniform.
+                       gather: bool = True, inc_amp=None, warm_start: bool = False, output: str = "float64",
+                       mask=None, ct2pi=256, trap_dots=None, on_batch: Optional[Callable] = None):
+    """GS holograms of ``frames`` (uint8 [F,H,W], a host array or a device tensor); ``inc_amp``: illumination amplitude
+    plane [H,W] shared by all frames (algorithms.py:14-19), None = uniform.
+
+    ``output``: "float64" -- the holograms as the reference saves them (generate_hologram_sequence.py:26, 8 bytes per
+    pixel); "uint8" -- the frames the SLM is shown: wavefront-correction ``mask`` added (None: no mask) and quantised
+    with ``ct2pi`` grey levels per 2 pi by the floor rule of move_traps.py:135-140 / display_holograms.py:253-266
+    (1 byte per pixel: an eighth of the read-back and of the gather).
+
+    ``trap_dots`` = (dots int[n,3] of (frame, y, x), number_of_frames, (H, W)) instead of ``frames``: the trap targets
+    are rasterised on the device (traps_images.py:10-16,87-91) -- no frame stack crosses the host at all.
 
     ``warm_start`` (an extension, off by default because it changes the results): every frame of a rank's block
     starts from the previous frame's hologram (``B = inc * exp(1j * hologram)``) instead of the reference's
     ``ifft2(sqrt(target))`` setup, which lets a slowly moving trap pattern converge in a few iterations; the frames
     are then processed one after the other.
 
-    Under an initialised process group every rank passes the SAME ``frames`` and computes only its
-    block; with ``gather`` the full results are returned on rank 0 (other ranks get their own
-    block).  Returns ``(holograms [n,H,W] float64, expected or None, errors list, (lo, hi))``.
+    ``on_batch(lo, hi, holograms, expected)`` is called from a writer thread as soon as global frames [lo, hi) lie in
+    host memory (this rank's own frames; with a gather, rank 0 receives every rank's), while later batches iterate.
+
+    Under an initialised process group every rank passes the SAME ``frames`` and computes only its contiguous block.
+    With ``gather`` the finished frames travel device to device to rank 0 (``torch.distributed.gather`` per batch:
+    NCCL over NVLink on GPUs), which alone reads them back -- batch k is gathered and read back while batch k+1
+    iterates -- and the full movie is returned on rank 0 (other ranks return their own block's error curves and empty
+    arrays).  Returns ``(holograms [n,H,W] float64 | uint8, expected or None, errors list, (lo, hi))``.
     """
-    frames = np.asarray(frames)
-    if frames.ndim != 3:
-        raise ValueError("frames must be [F,H,W]")
+    if output not in ("float64", "uint8"):
+        raise ValueError("output must be 'float64' or 'uint8'")
     dist = _dist()
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
-    lo, hi = hl.shard_range(frames.shape[0], rank, world)
+    if trap_dots is not None:
+        dots, n_frames, shape = trap_dots
+        dots = np.asarray(dots, dtype=np.int64).reshape(-1, 3)
+        shape = tuple(int(v) for v in shape)
+        frames = None
+    else:
+        if not hasattr(frames, "data_ptr"):
+            frames = np.asarray(frames)
+        if len(frames.shape) != 3:
+            raise ValueError("frames must be [F,H,W]")
+        n_frames, shape = int(frames.shape[0]), tuple(int(v) for v in frames.shape[1:])
+    lo, hi = hl.shard_range(n_frames, rank, world)
     n_local = hi - lo
-    shape = frames.shape[1:]
-    batch = max(1, min(batch, max(n_local, 1)))
+    blocks = [hl.shard_range(n_frames, r, world) for r in range(world)]
+    n_max = max(h - l for l, h in blocks)
+    batch = max(1, min(batch, max(n_max, 1)))
     if engine_factory is None:
         from .engine import get_engine
         eng = get_engine(shape, precision, batch)
     else:
         eng = engine_factory(shape, precision, batch)
-    holos = eng.host_empty((n_local,) + shape, np.float64)
-    exps = eng.host_empty((n_local,) + shape, np.float64) if want_expected else None
+    out_dtype = np.float64 if output == "float64" else np.uint8
+    collect = bool(dist and world > 1 and gather)
+    root = rank == 0
+    n_host = n_frames if (collect and root) else (0 if collect else n_local)
+    base = 0 if collect else lo                           # global index of holos[0]
+    holos = eng.host_empty((n_host,) + shape, out_dtype)
+    exps = eng.host_empty((n_host,) + shape, np.float64) if want_expected else None
     errors: List[np.ndarray] = []
+    writer = _Writer(on_batch)
+
+    def finish(res):
+        """device results of one batch in the requested output format"""
+        if output == "float64":
+            return res.hologram
+        from . import _ffi
+        return eng.quantize(res.hologram, mask, ct2pi, _ffi.QUANT_FLOOR)
+
+    def targets_of(s, e):
+        if frames is not None:
+            return frames[lo + s:lo + e]
+        sel = dots[(dots[:, 0] >= lo + s) & (dots[:, 0] < lo + e)].copy()
+        sel[:, 0] -= lo + s
+        return eng.trap_frames(sel, e - s, shape)
+
     if warm_start:
+        if collect:
+            raise ValueError("warm_start chains the frames of a block: gather=False only")
         phasor = None
         for s in range(n_local):
-            res = eng.gs(frames[lo + s:lo + s + 1], max_loops, tolerance, inc_amp=inc_amp, phasor0=phasor, want_expected=want_expected)
-            holos[s] = eng.to_host(res.hologram)[0]
+            res = eng.gs(targets_of(s, s + 1), max_loops, tolerance, inc_amp=inc_amp, phasor0=phasor, want_expected=want_expected)
+            holos[s] = eng.to_host(finish(res))[0]
             if want_expected:
                 exps[s] = eng.to_host(res.expected)[0]
             errors.extend(res.errors)
             phasor = eng.phase_phasor(res.hologram, inc_amp)
-        n_local = 0                                      # nothing left for the batched loop below
-    # the read-back of one batch (float64: 8 bytes per pixel and frame) runs beside the iterations of the next one
-    pending = []
-    for s in range(0, n_local, batch):
+            writer.put([], lo + s, lo + s + 1, holos[s:s + 1], exps[s:s + 1] if want_expected else None)
+        n_local = n_max = 0                              # nothing left for the batched loop below
+    # the read-back (and the gather) of one batch runs beside the iterations of the next one
+    pending: list = []
+    for s in range(0, n_max, batch):
         e = min(s + batch, n_local)
-        res = eng.gs(frames[lo + s:lo + e], max_loops, tolerance, inc_amp=inc_amp, want_expected=want_expected)
-        for job in pending:
-            job.join()
-        pending = [eng.to_host_into(res.hologram, holos[s:e])]
+        res = None
+        if e > s:
+            res = eng.gs(targets_of(s, e), max_loops, tolerance, inc_amp=inc_amp, want_expected=want_expected, norms=None)
+            errors.extend(res.errors)
+        for jobs, a, b in pending:
+            writer.put(jobs, a, b, holos[a - base:b - base], exps[a - base:b - base] if want_expected else None)
+        pending = []
+        if not collect:
+            jobs = [eng.to_host_into(finish(res), holos[s:e])]
+            if want_expected:
+                jobs.append(eng.to_host_into(res.expected, exps[s:e]))
+            pending.append((jobs, lo + s, lo + e))
+            continue
+        # gather this batch of every rank on rank 0's device; rank 0 reads the blocks back
+        parts = [(finish(res) if res is not None else None, holos)]
         if want_expected:
-            pending.append(eng.to_host_into(res.expected, exps[s:e]))
-        errors.extend(res.errors)
-    for job in pending:
-        job.join()
-    if dist and world > 1 and gather:
-        holos, exps, errors = _gather_to_root(dist, frames.shape[0], shape, holos, exps, errors, max_loops)
-        if rank == 0:
-            lo, hi = 0, frames.shape[0]
+            parts.append((res.expected if res is not None else None, exps))
+        by_block = {}
+        for dev_buf, host in parts:
+            got = eng.gather_to_root(dev_buf, (batch,) + shape, host.dtype, dist)
+            if not root:
+                continue
+            for r, (rl, rh) in enumerate(blocks):
+                a, b = rl + s, min(rl + s + batch, rh)
+                if b > a:
+                    by_block.setdefault((a, b), []).append(eng.to_host_into(got.blocks[r][:b - a], host[a:b], after=got.work))
+        pending = [(jobs, a, b) for (a, b), jobs in by_block.items()]
+    for jobs, a, b in pending:
+        writer.put(jobs, a, b, holos[a - base:b - base], exps[a - base:b - base] if want_expected else None)
+    writer.close()
+    if collect:
+        errors = _gather_curves(dist, n_frames, errors, max_loops)
+        if root:
+            lo, hi = 0, n_frames
     return holos, exps, errors, (lo, hi)
 
 
-def _gather_to_root(dist, n_total, shape, holos, exps, errors, max_loops):
-    """Final gather of the per-rank blocks (contiguous, rank order) onto rank 0."""
+class _Writer:
+    """Hands finished batches to ``on_batch`` from one background thread, in order, after their copies have landed
+    (file output of batch k overlaps the iterations of batch k+1).  Without a callback it only joins the copies."""
+
+    def __init__(self, on_batch):
+        import queue
+        import threading
+        self.on_batch, self.error = on_batch, None
+        self.q = queue.Queue() if on_batch else None
+        self.thread = None
+        if on_batch:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+
+    def put(self, jobs, lo, hi, holos, exps):
+        if self.q is None:
+            for j in jobs:
+                j.join()
+            return
+        self.q.put((jobs, lo, hi, holos, exps))
+
+    def _run(self):
+        while True:
+            item = self.q.get()
+            if item is None:
+                return
+            jobs, lo, hi, holos, exps = item
+            try:
+                for j in jobs:
+                    j.join()
+                if self.error is None:
+                    self.on_batch(lo, hi, holos, exps)
+            except Exception as exc:                  # surfaced by close()
+                self.error = exc
+
+    def close(self):
+        if self.q is not None:
+            self.q.put(None)
+            self.thread.join()
+        if self.error is not None:
+            raise self.error
+
+
+def _gather_curves(dist, n_total, errors, max_loops):
+    """The error curves of every rank's block on rank 0 (a few doubles per frame; the other ranks keep their own)."""
     import torch
     rank, world = dist.get_rank(), dist.get_world_size()
-    backend = dist.get_backend()
-    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
     counts = [hl.shard_range(n_total, r, world) for r in range(world)]
     cap = max(h - l for l, h in counts)
-
-    def gather_block(local: np.ndarray, tail_shape) -> Optional[np.ndarray]:
-        pad = torch.zeros((cap,) + tuple(tail_shape), dtype=torch.float64, device=dev)
-        if local.shape[0]:
-            pad[:local.shape[0]] = torch.from_numpy(local).to(dev)
-        bufs = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
-        dist.gather(pad, bufs, dst=0)
-        if rank != 0:
-            return None
-        return np.concatenate([bufs[r][:h - l].cpu().numpy() for r, (l, h) in enumerate(counts)], axis=0)
-
-    curves = np.full((len(errors), max_loops + 1), np.nan)
+    curves = np.full((cap, max_loops + 1), np.nan)
     for i, e in enumerate(errors):
         curves[i, 0] = len(e)
         curves[i, 1:1 + len(e)] = e
-    all_h = gather_block(holos, shape)
-    all_e = gather_block(exps, shape) if exps is not None else None
-    all_c = gather_block(curves, (max_loops + 1,))
+    mine = torch.from_numpy(curves).to(dev)
+    bufs = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+    dist.gather(mine, bufs, dst=0)
     if rank != 0:
-        return holos, exps, errors
-    return all_h, all_e, [row[1:1 + int(row[0])].copy() for row in all_c]
+        return errors
+    rows = np.concatenate([bufs[r][:h - l].cpu().numpy() for r, (l, h) in enumerate(counts)], axis=0)
+    return [row[1:1 + int(row[0])].copy() for row in rows]
 
 
 def generate_hologram_sequence(args):

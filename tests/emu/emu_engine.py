@@ -62,10 +62,27 @@ class EmuEngine(Engine):
         a = np.asarray(dev)
         return a.reshape(a.shape[0], -1).max(axis=1).astype(np.float64)
 
+    def _mem_contiguous(self, dev):
+        return np.ascontiguousarray(dev).view(HostBuf)
+
     def _mem_host_empty(self, shape, dtype):
         return np.empty(shape, dtype=dtype)
 
-    def _mem_download_into(self, buf, out):
+    def _mem_gather_to_root(self, buf, padded_shape, dtype, dist, dst):
+        import torch
+        from spatial_light_modulator_module_b200.engine import _Gathered
+        pad = np.zeros(padded_shape, dtype=dtype)
+        if buf is not None:
+            pad[:buf.shape[0]] = np.asarray(buf)
+        mine = torch.from_numpy(pad)
+        bufs = [torch.empty_like(mine) for _ in range(dist.get_world_size())] if dist.get_rank() == dst else None
+        work = dist.gather(mine, bufs, dst=dst, async_op=True)
+        blocks = [b.numpy().view(HostBuf) for b in bufs] if bufs is not None else None
+        return _Gathered(blocks, work, mine)
+
+    def _mem_download_into(self, buf, out, after=None):
+        if after is not None:
+            after.wait()
         np.copyto(out, np.asarray(buf))
 
         class Done:

@@ -71,8 +71,12 @@ struct State {
     void (*body)(void*) = nullptr;
     void* body_arg = nullptr;
     unsigned long progress = 0;
+    std::vector<unsigned char> smem_store;
 };
-inline State& S() { static State s; return s; }
+// The CTA whose fibres are running.  Ordinary launches run one CTA at a time on `solo`; a cooperative launch
+// (launch_coop) keeps one State per CTA of the grid and switches this pointer as it goes round them.
+inline State*& current() { static State solo; static State* cur = &solo; return cur; }
+inline State& S() { return *current(); }
 
 inline void yield() { State& s = S(); swapcontext(&s.cur->ctx, &s.main_ctx); }
 
@@ -139,8 +143,7 @@ template <class T> inline T shfl_idx(T v, int src) {
     return r;
 }
 
-template <class F> void run_cta(dim3 bidx, dim3 grid, dim3 block, size_t smem_bytes, F& f) {
-    State& s = S();
+template <class F> void setup_cta(State& s, dim3 bidx, dim3 grid, dim3 block, size_t smem_bytes, F& f) {
     const unsigned n = block.x * block.y * block.z;
     const size_t kStack = 256 * 1024;
     if (s.fibres.size() < n) {
@@ -153,8 +156,8 @@ template <class F> void run_cta(dim3 bidx, dim3 grid, dim3 block, size_t smem_by
     s.bar_count = 0;
     for (int i = 0; i < 16; ++i) s.named_count[i] = 0;
     s.block_idx = bidx; s.block_dim = block; s.grid_dim = grid;
-    std::vector<unsigned char> smem(smem_bytes + 256, 0xFF);
-    s.smem = (unsigned char*)(((uintptr_t)smem.data() + 127) & ~(uintptr_t)127);
+    s.smem_store.assign(smem_bytes + 2048, 0xFF);
+    s.smem = (unsigned char*)(((uintptr_t)s.smem_store.data() + 1023) & ~(uintptr_t)1023);
     s.body = [](void* a) { (*static_cast<F*>(a))(); };
     s.body_arg = &f;
     for (unsigned i = 0; i < n; ++i) {
@@ -166,22 +169,55 @@ template <class F> void run_cta(dim3 bidx, dim3 grid, dim3 block, size_t smem_by
         fb.ctx.uc_link = nullptr;
         makecontext(&fb.ctx, (void (*)())trampoline, 0);
     }
-    while (s.alive) {
-        unsigned long before = s.progress;
-        for (unsigned i = 0; i < n; ++i) {
-            if (s.fibres[i].done) continue;
-            s.cur = &s.fibres[i];
-            swapcontext(&s.main_ctx, &s.fibres[i].ctx);
-        }
-        if (s.alive && s.progress == before) { fprintf(stderr, "emu: deadlock in CTA (%u,%u)\n", bidx.x, bidx.y); abort(); }
+}
+// one turn of every live fibre of the CTA
+inline void sweep_cta(State& s) {
+    for (unsigned i = 0; i < s.n; ++i) {
+        if (s.fibres[i].done) continue;
+        s.cur = &s.fibres[i];
+        swapcontext(&s.main_ctx, &s.fibres[i].ctx);
     }
     s.cur = nullptr;
+}
+
+template <class F> void run_cta(dim3 bidx, dim3 grid, dim3 block, size_t smem_bytes, F& f) {
+    State& s = S();
+    setup_cta(s, bidx, grid, block, smem_bytes, f);
+    while (s.alive) {
+        unsigned long before = s.progress;
+        sweep_cta(s);
+        if (s.alive && s.progress == before) { fprintf(stderr, "emu: deadlock in CTA (%u,%u)\n", bidx.x, bidx.y); abort(); }
+    }
 }
 
 template <class F> void launch(dim3 grid, dim3 block, size_t smem_bytes, F f) {
     for (unsigned z = 0; z < grid.z; ++z)
         for (unsigned y = 0; y < grid.y; ++y)
             for (unsigned x = 0; x < grid.x; ++x) run_cta(dim3(x, y, z), grid, block, smem_bytes, f);
+}
+
+// Cooperative launch: every CTA of the (1-D) grid is resident at once, so CTAs may wait for each other through
+// global memory (spin loops must call spin_pause(), which yields here).  CTAs take turns, one sweep each.
+template <class F> void launch_coop(dim3 grid, dim3 block, size_t smem_bytes, F f) {
+    static std::vector<State*> pool;
+    while (pool.size() < grid.x) pool.push_back(new State);
+    State* const saved = current();
+    for (unsigned x = 0; x < grid.x; ++x) { current() = pool[x]; setup_cta(*pool[x], dim3(x, 1, 1), grid, block, smem_bytes, f); }
+    for (;;) {
+        unsigned long alive = 0, moved = 0;
+        for (unsigned x = 0; x < grid.x; ++x) {
+            State& s = *pool[x];
+            if (!s.alive) continue;
+            current() = &s;
+            const unsigned long before = s.progress;
+            sweep_cta(s);
+            moved += s.progress - before;
+            alive += s.alive;
+        }
+        if (!alive) break;
+        if (!moved) { fprintf(stderr, "emu: deadlock in a cooperative grid of %u CTAs\n", grid.x); abort(); }
+    }
+    current() = saved;
 }
 
 struct Idx { unsigned x, y, z; };
@@ -208,6 +244,8 @@ inline Idx thread_idx() {
 #define SLM_LAUNCH(kernel, grid, block, smem, stream, ...) \
     emu::launch(grid, block, smem, [=]() { kernel(__VA_ARGS__); })
 #define SLM_LAUNCH_PDL SLM_LAUNCH
+#define SLM_LAUNCH_COOP(kernel, grid, block, smem, stream, ...) \
+    emu::launch_coop(grid, block, smem, [=]() { kernel(__VA_ARGS__); })
 
 namespace slm {
 template <typename T> inline T ld_ro(const T* p) { return *p; }
@@ -223,6 +261,7 @@ inline unsigned atomic_max_u32(unsigned* p, unsigned v) { unsigned o = *p; if (v
 inline unsigned atomic_add_u32(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 inline unsigned ld_acquire(const unsigned* p) { return *p; }
 inline long long clock_now() { return 0; }
+inline void spin_pause() { emu::yield(); }          // a wait on another CTA's progress: let the other fibres / CTAs run
 }  // namespace slm
 inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }

@@ -49,6 +49,44 @@ def test_two_rank_movie_matches_single_process(tmp_path, n_frames):
     np.testing.assert_array_equal(r0["holos"], ref_h)
     np.testing.assert_array_equal(r0["exps"], ref_e)
     np.testing.assert_array_equal(r0["errors"], np.array(ref_err))
-    lo1, hi1 = int(r1["lo"]), int(r1["hi"])                           # rank 1 keeps its own block
+    lo1, hi1 = int(r1["lo"]), int(r1["hi"])                           # rank 1 computed its own block ...
     assert (lo1, hi1) == ((n_frames + 1) // 2, n_frames)
-    np.testing.assert_array_equal(r1["holos"], ref_h[lo1:hi1])
+    assert r1["holos"].shape[0] == 0                                  # ... and sent it device to device: nothing read back
+    np.testing.assert_array_equal(r1["errors"], np.array(ref_err)[lo1:hi1])
+
+
+def _worker_frames(rank, world, port, n_frames, out_dir):
+    """uint8 SLM frames (mask add + floor quantisation), rasterised trap targets, a batch callback."""
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from spatial_light_modulator_module_b200 import generate_hologram_sequence as ghs, synthetic
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        shape = (64, 128)
+        mask = synthetic.random_mask(shape, seed=4)
+        dots = synthetic.movie_frame_dots(n_frames, rescale_parameter=11.0, shape=shape)
+        seen = []
+        frames, _, errors, (lo, hi) = ghs.sequence_holograms(
+            None, 4, precision="fp64", batch=2, engine_factory=_factory, output="uint8", mask=mask, ct2pi=200,
+            trap_dots=(dots, n_frames, shape), on_batch=lambda a, b, h, e: seen.append((a, b, h.copy())))
+        np.savez(os.path.join(out_dir, f"frames{rank}.npz"), frames=frames, lo=lo, hi=hi, seen_lo=np.array([s[0] for s in seen]),
+                 seen_hi=np.array([s[1] for s in seen]))
+        for a, b, h in seen:
+            np.testing.assert_array_equal(h, frames[a:b])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_uint8_frames_from_device_rasterised_targets(tmp_path):
+    from oracle import numpy_port as P
+    from spatial_light_modulator_module_b200 import generate_hologram_sequence as ghs, synthetic
+    n_frames, shape = 5, (64, 128)
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker_frames, args=(2, port, n_frames, str(tmp_path)), nprocs=2, join=True)
+    holos, _, _, _ = ghs.sequence_holograms(_frames(n_frames), 4, precision="fp64", batch=3, engine_factory=_factory)
+    mask = synthetic.random_mask(shape, seed=4)
+    r0 = np.load(tmp_path / "frames0.npz")
+    assert r0["frames"].dtype == np.uint8 and r0["frames"].shape == (n_frames,) + shape
+    for i in range(n_frames):
+        np.testing.assert_array_equal(r0["frames"][i], P.quantize_q3(holos[i], mask, 200))
+    assert sorted(zip(r0["seen_lo"], r0["seen_hi"])) == [(0, 2), (2, 3), (3, 5)]     # every rank's batches reached the callback

@@ -52,6 +52,37 @@ def test_warp_column_kernel_gd(rows, batch):
     pc.check_gd_vs_oracle(make_engine, (rows, 64), "fp32", "noise", loops=3, batch=batch)
 
 
+@pytest.mark.parametrize("rows,batch", [(1024, 2), (768, 3), (1024, 5)])
+def test_warp_column_kernel_gd_pipelined_one_pass_form(monkeypatch, rows, batch):
+    """CGM_GD_PIPE: the CTA's two compute groups split each tile (forward transform + plane max | gradient step +
+    inverse transform); tiles wait for the other tiles of their plane held by the other CTAs of a cooperative grid
+    (the emulation co-schedules its 3 CTAs).  Against the oracle, and bit-identical to the two-pass form."""
+    import numpy as np
+    from spatial_light_modulator_module_b200 import host_logic as hl, synthetic
+    monkeypatch.setenv("SLM_GD_FORM", "pipe")
+    pc.check_gd_vs_oracle(make_engine, (rows, 64), "fp32", "noise", loops=3, batch=batch)
+    shape, loops = (rows, 64), 4
+    t = np.stack([synthetic.noise_target(shape, seed=i) for i in range(batch)])
+    x0 = np.stack([hl.host_initial_guess("random", shape, 42 + i) for i in range(batch)])
+    during, _ = hl.learning_rate_schedule(0.005, 0, loops)
+    out = {}
+    for form in ("pipe", "two_pass"):
+        monkeypatch.setenv("SLM_GD_FORM", form)
+        eng = make_engine(shape, "fp32", batch)
+        n0 = eng.launch_count()
+        r, _ = eng.gd(t, x0.copy(), during, loops)
+        out[form] = (np.array(r.errors), eng.to_host(r.hologram), eng.to_host(r.expected), eng.launch_count() - n0)
+        eng.close()
+    assert out["pipe"][3] < out["two_pass"][3]                    # one Fourier-plane pass per iteration instead of two
+    for i in range(3):
+        np.testing.assert_array_equal(out["pipe"][i], out["two_pass"][i])
+
+
+def test_warp_column_kernel_gd_pipelined_tolerance(monkeypatch):
+    monkeypatch.setenv("SLM_GD_FORM", "pipe")
+    pc.check_gd_tolerance_and_batch(make_engine, "fp32", shape=(768, 64), loops=6)
+
+
 def test_warp_column_kernel_tolerance_and_batch():
     pc.check_gs_tolerance_and_batch(make_engine, "fp32", shape=(1024, 64))
     pc.check_gd_tolerance_and_batch(make_engine, "fp32", shape=(768, 64), loops=6)
