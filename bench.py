@@ -1,21 +1,32 @@
 #!/usr/bin/env python
-"""Benchmark of the GS/GD hologram path (BASELINE.json metric: iterations/s at 1024^2).
+"""Benchmark of the GS/GD hologram path (BASELINE.json metric: iterations/s at 1024^2, holograms/s, % of HBM roofline).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--alg gd|gs] [--precision fp32|fp64]
-                    [--size 1024] [--batch 32] [--loops 100] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--only headline,gs_1024,...]
 
-A *step* is one pass of the hot path over one batch of synthetic targets: BATCH holograms of
-SIZE x SIZE, LOOPS iterations each (default: config 2 of BASELINE.json -- gradient descent, 100
-iterations, 1024^2 -- followed by the wavefront-mask add + 8-bit quantisation), entirely on the
-device with inputs resident in HBM.  `value` = BATCH*LOOPS*K / time [iterations/s], summed over
-ranks (weak scaling: every rank runs its own batch; the path has no collective).
+ONE JSON line.  Its top level is the headline workload -- BASELINE.json configs[1]: gradient descent, 100 iterations,
+1024x1024, followed by the wavefront-mask add + 8-bit quantisation; a *step* is one batch of 32 such holograms per GPU,
+inputs resident in HBM, `value` = iterations/s summed over the ranks (weak scaling: every rank runs its own batch, the
+path has no collective).  `verified` says whether plane 0 of the timed batch reproduced the reference's error curve and
+8-bit frame (tests/golden/gd_noise_1024x1024_curves.npz, made by the unmodified reference).
 
-`e2e` is the same work through the reference-facing API with HOST buffers
-(algorithms.gradient_descent(target, args) -> numpy, then display_holograms.hologram_to_grey),
-host<->device copies inside the timed region.
+`e2e` is the same work through the reference-facing API with HOST buffers (algorithms.gradient_descent(target, args) ->
+numpy, then display_holograms.hologram_to_grey), host<->device copies inside the timed region, summed over the ranks.
 
-`--impl reference` times the CPU implementation (the oracle's numpy restatement of the reference,
-scipy.fft with all host threads) on a bounded sample of the same workload.
+`configs` holds one sub-record per further workload of BASELINE.json, each timed like the headline (device events,
+warm-up, max over ranks):
+    gs_1024   Gerchberg-Saxton, batch 32 x 1024^2 x 100 iterations (the metric names GS and GD)
+    fp64      GD and GS at 1024^2 in the fp64 parity mode
+    config1   ONE 512x512 GS hologram, 20 iterations: device latency and through gerchberg_saxton(target, args)
+    config3   optical-trap movie, 1024 frames 768x1024 x GS 50 iterations through sequence_holograms: host frames in, host
+              results out (uint8 SLM frames and float64 holograms); under --gpus N the frames are sharded over the ranks
+              and gathered on rank 0 inside the timed region (strong scaling)
+    config4   compare_error_evolution_algorithms shape: 256 targets x 2048^2, GD then GS, 50 iterations, all 512 curves
+              (targets sharded over the ranks)
+    config5   one 16384^2 GS hologram, 20 iterations, slab-decomposed over the ranks (1 GPU: the same code, world = 1)
+    size_4096 GD and GS at 4096^2 (the upper end of the north star's range)
+
+`--impl reference` times the CPU implementation (the oracle's numpy restatement of the reference, scipy.fft with all
+host threads) on a bounded sample of the headline workload.
 """
 from __future__ import annotations
 
@@ -24,9 +35,7 @@ import contextlib
 import io
 import json
 import os
-import subprocess
 import sys
-import tempfile
 import time
 
 import numpy as np
@@ -34,6 +43,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+
+ALL_SECTIONS = ["headline", "gs_1024", "fp64", "config1", "config3", "config4", "config5", "size_4096", "e2e", "cpu"]
 
 
 def parse():
@@ -50,10 +61,12 @@ def parse():
     p.add_argument("--loops", type=int, default=100)
     p.add_argument("--e2e-steps", type=int, default=5)
     p.add_argument("--cpu-loops", type=int, default=40, help="iterations of the CPU baseline sample")
-    p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--no-movie", action="store_true")
+    p.add_argument("--only", default="", help="comma-separated sections (default: all): " + ",".join(ALL_SECTIONS))
+    p.add_argument("--movie-frames", type=int, default=1024)
+    p.add_argument("--config4-targets", type=int, default=256)
+    p.add_argument("--slab-size", type=int, default=16384)
     p.add_argument("--workload", default="batch", choices=["batch", "slab"],
-                   help="batch: configs[1] (default).  slab: ONE size^2 plane row-split over the ranks (configs[4]), GS")
+                   help="slab: only config5 as the line's own workload (one --size^2 plane row-split over the ranks)")
     return p.parse_args()
 
 
@@ -67,32 +80,38 @@ def workload_name(a, shape):
             f"+ wavefront-mask add + 8-bit quantise (BASELINE.json configs[1])")
 
 
-def bytes_per_px(alg, precision):
-    """GS (8c+4), GD (9c+4) algorithmic bytes per pixel per iteration."""
+# ---- byte models ------------------------------------------------------------------------------------------------------
+def survey_bytes_per_px(alg, precision):
+    """four passes per iteration -- GS (8c+4), GD (9c+4) bytes per pixel."""
     c = 8 if precision == "fp32" else 16
     return (8 * c + 4) if alg == "gs" else (9 * c + 4)
 
 
+def design_bytes_per_px(alg, precision, gd_passes=1):
+    """What this design must move: the two transforms that meet at a pointwise step share one pass --
+    GS (4c+4); GD (6c+4) with one Fourier-plane pass per iteration, (8c+4) in the two-pass form."""
+    c = 8 if precision == "fp32" else 16
+    return (4 * c + 4) if alg == "gs" else ((6 * c + 4) if gd_passes == 1 else (8 * c + 4))
+
+
 def kernel_bytes_per_px(kind, alg, precision):
-    """Algorithmic bytes per pixel of ONE launch of a pass kernel (same accounting as SURVEY 8d:
-    every plane the pass must read or write once, target accounted at 4 B/px)."""
+    """Algorithmic bytes per pixel of ONE launch of a pass kernel (every plane the pass must read or write once, the
+    8-bit target accounted at 4 B/px as in SURVEY 8d)."""
     c = 8 if precision == "fp32" else 16
     if kind == "col_pass":
-        return 2 * c + 4                       # read X, write Y, read target
+        return 2 * c + 4                         # read X, write Y, read target
     if kind == "row_pass":
         return 2 * c if alg == "gs" else 4 * c   # GS: read Y, write X; GD: + read x, write x
     if kind == "col_stats":
-        return c                               # read X
+        return 2 * c                             # the max pass of the two-pass GD form keeps the transform: read X, write X
     raise KeyError(kind)
 
 
-def measured_traffic(kind, alg, precision, shape, batch):
-    """DRAM bytes (read + write) per launch of the dominant kernel from the committed ncu capture
-    (profiles/traffic.json), if one exists for exactly this configuration."""
+def measured_traffic(key):
+    """DRAM bytes (read + write) per launch from the committed ncu capture (profiles/traffic.json), or None."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(path):
         return None
-    key = f"{kind}|{alg}|{precision}|{shape[0]}x{shape[1]}|batch{batch}"
     return json.load(open(path)).get(key)
 
 
@@ -109,7 +128,7 @@ class ClockSampler:
     THROTTLE = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
 
     def __init__(self, index, period_s=None):
-        period_s = float(os.environ.get("SLM_BENCH_SAMPLER_PERIOD", "0.2")) if period_s is None else period_s
+        period_s = float(os.environ.get("SLM_BENCH_SAMPLER_PERIOD", "0.05")) if period_s is None else period_s
         self.index, self.period, self.samples, self._stop, self.thread, self.err = index, period_s, [], False, None, None
 
     def start(self):
@@ -153,7 +172,7 @@ class ClockSampler:
                 "sample_ms_max": round(1e3 * max(r[5] for r in rows), 2)}
 
 
-# ------------------------------------------------------------------------------------------------
+# ---- CPU arm ------------------------------------------------------------------------------------------------------------
 def cpu_port_iterations_per_s(alg, shape, loops, workers):
     """Time the oracle's restatement of the reference loop on the host."""
     import scipy.fft
@@ -196,7 +215,202 @@ def run_reference(a):
     }))
 
 
-# ------------------------------------------------------------------------------------------------
+# ---- device arm -----------------------------------------------------------------------------------------------------------
+class Harness:
+    """Timing rules of the contract: warm-up, barrier + synchronize on both sides, CUDA events, max over ranks."""
+
+    def __init__(self, torch, dist, world, dev):
+        self.torch, self.dist, self.world, self.dev = torch, dist, world, dev
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, value):
+        if self.world == 1:
+            return float(value)
+        t = self.torch.tensor([value], device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, value):
+        if self.world == 1:
+            return float(value)
+        t = self.torch.tensor([value], device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def all_ok(self, flag):
+        if self.world == 1:
+            return bool(flag)
+        t = self.torch.tensor([1.0 if flag else 0.0], device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return bool(t.item() > 0.5)
+
+    def time_steps(self, step, warmup, steps):
+        """-> (total ms of `steps` steps as the max over ranks, per-step ms of this rank, result of the last step)"""
+        torch = self.torch
+        out = None
+        for _ in range(warmup):
+            out = step()
+        self.barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        self.barrier()
+        e0.record()
+        for i in range(steps):
+            out = step()
+            marks[i].record()
+        self.barrier()
+        ms = e0.elapsed_time(marks[-1])
+        step_ms = [round(([e0] + marks)[i].elapsed_time(marks[i]), 3) for i in range(steps)]
+        return self.max_over_ranks(ms), step_ms, out
+
+    def wall_steps(self, step, warmup, steps):
+        """Host-clock timing for end-to-end calls (host buffers in and out): seconds per step, max over ranks."""
+        for _ in range(warmup):
+            step()
+        self.barrier()
+        t0 = time.perf_counter()
+        out = None
+        for _ in range(steps):
+            out = step()
+        self.torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / steps
+        self.barrier()
+        return self.max_over_ranks(dt), out
+
+
+def roofline_record(name, alg, precision, npx_total, avg_ms, kind, share, peak, peak_src, traffic_key=None):
+    """traffic_key: "<kind>|<alg>|<precision>|<H>x<W>|batch<B>" in profiles/traffic.json (ncu --set full, per launch)"""
+    bts = kernel_bytes_per_px(kind, alg, precision) * npx_total
+    ach = bts / (avg_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": measured_traffic(traffic_key) if traffic_key else None, "peak_source": peak_src,
+            "alg_bytes_per_launch": bts, "avg_launch_ms": avg_ms, "share_of_step": share}
+
+
+def iteration_rooflines(alg, precision, npx, per_iter_s, peak, gd_passes=1):
+    sv, ds = survey_bytes_per_px(alg, precision) * npx, design_bytes_per_px(alg, precision, gd_passes) * npx
+    return {"survey_model": {"bytes_per_iteration": sv, "achieved_gbs": sv / per_iter_s / 1e9, "frac": sv / per_iter_s / 1e9 / peak,
+                             "note": "SURVEY 8(d): (8c+4) GS / (9c+4) GD B/px -- four unfused passes; a fused design moves fewer bytes, so "
+                                     "this fraction can exceed what the memory system really delivers"},
+            "design_model": {"bytes_per_iteration": ds, "achieved_gbs": ds / per_iter_s / 1e9, "frac": ds / per_iter_s / 1e9 / peak,
+                             "note": "bytes this design must move: (4c+4) GS, (6c+4) GD B/px (one Fourier-plane pass per iteration)"},
+            "peak": peak, "unit": "GB/s"}
+
+
+def kernel_names(alg, gd_form):
+    col = {"gs": "col_warp_kernel<GS> (Fourier-plane pass)",
+           "gd": {"pipe": "col_warp_kernel<GD_PIPE> (Fourier-plane pass, one per iteration)",
+                  "fused": "col_warp_kernel<GD_FUSED> (Fourier-plane pass, one per iteration)",
+                  "two_pass": "col_warp_kernel<GD_POST> (gradient pass)"}[gd_form]}[alg]
+    return {"col_pass": col, "row_pass": f"row_pass_kernel<{'GS' if alg == 'gs' else 'GD'}> (SLM-plane pass)",
+            "col_stats": "col_warp_kernel<STATS_KEEP> (max pass, keeps the transform)"}
+
+
+def profile_kernels(eng, step, steps, alg, precision, npx_total, peak, peak_src, gd_form="pipe", names=None, traffic_prefix=None):
+    """Instrumented re-run of the same steps: per-kernel CUDA-event times from the engine (slm_ctx_profile)."""
+    eng.profile(True)
+    eng.profile_read()
+    for _ in range(steps):
+        step()
+    prof = eng.profile_read()
+    eng.profile(False)
+    names = names or kernel_names(alg, gd_form)
+    kernels = {}
+    tsum = sum(v[0] for v in prof.values()) or 1.0
+    for kind in ("col_pass", "row_pass", "col_stats"):
+        tot, cnt = prof[kind]
+        if cnt:
+            rec = roofline_record(names[kind], alg, precision, npx_total, tot / cnt, kind, tot / tsum, peak, peak_src,
+                                  f"{kind}|{traffic_prefix}" if traffic_prefix else None)
+            rec["launches"] = cnt
+            kernels[kind] = rec
+    dom = max(kernels, key=lambda k: kernels[k]["share_of_step"])
+    return kernels, dict(kernels[dom])
+
+
+def batched_loop_record(h, a, alg, precision, shape, batch, loops, steps, warmup, peak, peak_src, verify=None, extra_step=None):
+    """One sub-record: `batch` holograms of `shape`, `loops` iterations each, device resident; optionally the mask add +
+    quantise behind it (extra_step).  Returns (record, engine state for follow-ups)."""
+    import torch
+    from spatial_light_modulator_module_b200 import host_logic as hl, synthetic
+    from spatial_light_modulator_module_b200.engine import Engine
+    rank = env_rank()[0]
+    npx = shape[0] * shape[1]
+    eng = Engine(shape, precision, batch)
+    tg = [synthetic.noise_target(shape, seed=(0 if (i == 0 and verify) else 1000 * rank + i + 1)) for i in range(batch)]
+    targets = torch.from_numpy(np.stack(tg)).to(h.dev)
+    norms = targets.reshape(batch, -1).amax(dim=1).double().cpu().numpy()
+    during, _ = hl.learning_rate_schedule(0.005, 0, loops)
+    x0 = x = None
+    if alg == "gd":
+        rng = np.random.default_rng(rank)
+        x0 = torch.from_numpy(np.exp(2j * np.pi * rng.random((batch,) + shape)).astype(eng.complex_dtype)).to(h.dev)
+        if verify:                                  # plane 0: the reference's own start, random.seed(42) (algorithms.py:117-121)
+            u = eng.python_random_uniform(42, shape)
+            x0[0].copy_(eng.random_phasor_guess(u, 1.0)[0])
+        x = torch.empty_like(x0)
+    state = {}
+
+    def step():
+        if alg == "gd":
+            x.copy_(x0)
+            res, _ = eng.gd(targets, x, during, loops, want_expected=False, norms=norms)
+        else:
+            res = eng.gs(targets, loops, want_expected=False, norms=norms)
+        state["res"] = res
+        return extra_step(eng, res) if extra_step else res.hologram
+
+    n0 = eng.launch_count()
+    ms, step_ms, out = h.time_steps(step, max(warmup, 3), steps)
+    launches = (eng.launch_count() - n0) * steps // (max(warmup, 3) + steps)
+    iters = batch * loops * steps * h.world
+    per_iter_s = ms * 1e-3 / (batch * loops * steps)
+    sms = torch.cuda.get_device_properties(h.dev).multi_processor_count
+    form = os.environ.get("SLM_GD_FORM") or ("two_pass" if os.environ.get("SLM_NO_FUSED_GD") else ("pipe" if batch * (shape[1] // 8) > 4 * sms else "fused"))
+    if precision == "fp64" or shape[0] not in (768, 1024):
+        form = "two_pass"                            # the one-pass forms exist in the warp-per-column kernel (fp32, 768/1024 rows)
+    rec = {"workload": f"{'gradient_descent' if alg == 'gd' else 'gerchberg_saxton'} {shape[0]}x{shape[1]}, batch {batch}/GPU, {loops} iterations, "
+                       f"{precision}, device resident", "value": iters / (ms * 1e-3), "unit": "iterations/s",
+           "holograms_per_s": batch * steps * h.world / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps, "step_ms": step_ms,
+           "gpu_launches": int(launches), "iteration_roofline": iteration_rooflines(alg, precision, npx, per_iter_s, peak, 1 if form != "two_pass" else 2)}
+    if alg == "gd":
+        rec["gd_form"] = form
+    if rank == 0:
+        names = kernel_names(alg, form)
+        if precision == "fp64" or shape[0] not in (768, 1024):
+            names = {k: v.replace("col_warp_kernel", "col_group_kernel" if shape[0] < 4096 else "col_pass_kernel / col_plain_kernel") for k, v in names.items()}
+        kernels, roof = profile_kernels(eng, step, min(steps, 3), alg, precision, npx * batch, peak, peak_src, form, names,
+                                        f"{alg}|{precision}|{shape[0]}x{shape[1]}|batch{batch}")
+        rec["kernels"], rec["roofline"] = kernels, roof
+    state.update(eng=eng, targets=targets, norms=norms, during=during, x0=x0, x=x, out=out, step=step)
+    return rec, state
+
+
+def verify_headline(state, shape, loops, precision):
+    """Plane 0 of the timed batch against the reference's own run (fixture made by the unmodified reference): error
+    curve within the north star's fp32 tolerance 1e-3 (fp64: 1e-9), 8-bit frame within +-1 LSB on <= 1e-3 of the pixels."""
+    path = os.path.join(ROOT, "tests", "golden", f"gd_noise_{shape[0]}x{shape[1]}_curves.npz")
+    if not os.path.exists(path) or loops != 100:
+        return None, {"skipped": "no reference fixture for this configuration"}
+    g = np.load(path)
+    res, eng = state["res"], state["eng"]
+    e = res.errors[0]
+    ok_len = len(e) == len(g["errors"])
+    curve = float(np.max(np.abs(e - g["errors"]) / g["errors"])) if ok_len else float("inf")
+    frame = eng.to_host(state["out"][0:1])[0][::4, ::4].astype(np.int32)
+    d = (frame - g["q3_sub"].astype(np.int32)) % 256
+    d = np.minimum(d, 256 - d)
+    frac = float(np.mean(d != 0))
+    tol = 1e-3 if precision == "fp32" else 1e-9
+    ok = bool(ok_len and curve < tol and d.max() <= 1 and frac <= 1e-3)
+    return ok, {"error_curve_max_rel": curve, "curve_tolerance": tol, "frame_max_lsb": int(d.max()), "frame_fraction_differing": frac,
+                "fixture": "tests/golden/gd_noise_1024x1024_curves.npz (unmodified reference, algorithms.py:60-112 + move_traps.py:135-140)"}
+
+
 def run_b200(a):
     import torch
     import torch.distributed as dist
@@ -205,276 +419,298 @@ def run_b200(a):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from spatial_light_modulator_module_b200 import _ffi, algorithms, display_holograms, host_logic as hl, synthetic
+    from spatial_light_modulator_module_b200 import _ffi, algorithms, display_holograms, synthetic
     from spatial_light_modulator_module_b200.engine import Engine
 
+    dev = torch.device("cuda", local_rank)
+    h = Harness(torch, dist, world, dev)
+    only = [s for s in a.only.split(",") if s] or ALL_SECTIONS
     shape = (a.height or a.size, a.size)
     npx = shape[0] * shape[1]
-    eng = Engine(shape, a.precision, a.batch)
-    dev = torch.device("cuda", local_rank)
+    peak, peak_src = measured_peak()
+    mask_dev = torch.from_numpy(synthetic.random_mask(shape, seed=1)).to(dev)
+    quant = lambda eng, res: eng.quantize(res.hologram, mask_dev, 256, _ffi.QUANT_FLOOR)      # noqa: E731
 
-    # synthetic inputs, resident in HBM before the timed region
-    targets = torch.from_numpy(np.stack([synthetic.noise_target(shape, seed=1000 * rank + i) for i in range(a.batch)])).to(dev)
-    mask = torch.from_numpy(synthetic.random_mask(shape, seed=1)).to(dev)
-    rng = np.random.default_rng(rank)
-    x0 = torch.from_numpy(np.exp(2j * np.pi * rng.random((a.batch,) + shape)).astype(eng.complex_dtype)).to(dev)
-    x = torch.empty_like(x0)
-    during, _ = hl.learning_rate_schedule(0.005, 0, a.loops)
-    norms = targets.reshape(a.batch, -1).amax(dim=1).double().cpu().numpy()
-
-    def step():
-        if a.alg == "gd":
-            x.copy_(x0)
-            res, _ = eng.gd(targets, x, during, a.loops, want_expected=False, norms=norms)
-        else:
-            res = eng.gs(targets, a.loops, want_expected=False, norms=norms)
-        return eng.quantize(res.hologram, mask, 256, _ffi.QUANT_FLOOR)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
+    # ---- headline: configs[1] ---------------------------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
     if rank == 0 and not os.environ.get("SLM_BENCH_NO_SAMPLER"):
         sampler.start()
-    # Warm-up steps keep their result alive exactly like the timed ones (`q = step()`): the previous frame is still
-    # referenced while the next one is allocated, so the caching allocator needs TWO output blocks -- left to the
-    # timed region, the second one cost a cudaMalloc (2-70 ms) in its second step.
-    q = None
-    for _ in range(max(a.warmup, 3)):
-        q = step()
-    barrier()
-    n0 = eng.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
     wall0 = time.time()
-    marks = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
-    e0.record()
-    for i in range(a.steps):
-        q = step()
-        marks[i].record()
-    e1.record()
-    barrier()
+    head, st = batched_loop_record(h, a, a.alg, a.precision, shape, a.batch, a.loops, a.steps, a.warmup, peak, peak_src,
+                                   verify=(a.alg == "gd"), extra_step=quant)
     wall1 = time.time()
-    ms = e0.elapsed_time(e1)
-    step_ms = [round(([e0] + marks)[i].elapsed_time(marks[i]), 3) for i in range(a.steps)]
-    launches = eng.launch_count() - n0
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
-    if world > 1:
-        tmax = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ms = float(tmax.item())
-    iters_total = a.batch * a.loops * a.steps * world
-    value = iters_total / (ms * 1e-3)
-
-    if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
-
-    # ---- per-kernel device timing (instrumented re-run of the same steps) ------------------------
-    eng.profile(True)
-    eng.profile_read()
-    for _ in range(a.steps):
-        step()
-    prof = eng.profile_read()
-    eng.profile(False)
-    peak, peak_src = measured_peak()
-    kernels = {}
-    for kind in ("col_pass", "row_pass", "col_stats"):
-        tot, cnt = prof[kind]
-        if cnt:
-            avg_ms = tot / cnt
-            bts = kernel_bytes_per_px(kind, a.alg, a.precision) * npx * a.batch
-            kernels[kind] = {"avg_ms": avg_ms, "launches": cnt, "share": None, "alg_bytes": bts,
-                             "achieved_gbs": bts / (avg_ms * 1e-3) / 1e9}
-    tsum = sum(v[0] for v in prof.values())
-    for kind in kernels:
-        kernels[kind]["share"] = prof[kind][0] / tsum
-    dom = max(kernels, key=lambda k: prof[k][0])
-    names = {"col_pass": f"col_group_kernel<{'GS' if a.alg == 'gs' else 'GD_POST'}> (Fourier-plane pass)",
-             "row_pass": "row_pass_kernel (SLM-plane pass)", "col_stats": "col_group_kernel<STATS> (max pre-pass)"}
-    roof = {"bound": "hbm", "kernel": names[dom],
-            "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-            "frac": kernels[dom]["achieved_gbs"] / peak, "traffic": measured_traffic(dom, a.alg, a.precision, shape, a.batch),
-            "peak_source": peak_src,
-            "alg_bytes_per_launch": kernels[dom]["alg_bytes"], "avg_launch_ms": kernels[dom]["avg_ms"],
-            "share_of_step": kernels[dom]["share"]}
-    iter_bytes = bytes_per_px(a.alg, a.precision) * npx
-    per_iter_s = (ms * 1e-3) / (a.batch * a.loops * a.steps)
-    iteration_roofline = {"alg_bytes_per_iteration": iter_bytes, "achieved": iter_bytes / per_iter_s / 1e9, "peak": peak,
-                          "unit": "GB/s", "frac": iter_bytes / per_iter_s / 1e9 / peak,
-                          "note": "SURVEY 8(d) figure ((8c+4) GS / (9c+4) GD bytes per pixel per iteration) / measured time per iteration"}
-
-    # ---- latency of ONE hologram (batch 1), device resident -----------------------------------------
-    eng1 = Engine(shape, a.precision, 1)
-    t1, x1, x01 = targets[:1].contiguous(), x[:1].contiguous(), x0[:1].contiguous()
-
-    def step1():
-        if a.alg == "gd":
-            x1.copy_(x01)
-            r, _ = eng1.gd(t1, x1, during, a.loops, want_expected=False, norms=norms[:1])
-        else:
-            r = eng1.gs(t1, a.loops, want_expected=False, norms=norms[:1])
-        return eng1.quantize(r.hologram, mask, 256, _ffi.QUANT_FLOOR)
-    for _ in range(3):
-        step1()
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(a.steps):
-        step1()
-    e1.record()
-    torch.cuda.synchronize()
-    lat_ms = e0.elapsed_time(e1) / a.steps
-    single = {"ms_per_hologram": lat_ms, "iterations_per_s": a.loops / (lat_ms * 1e-3),
-              "frac_of_hbm_roofline": iter_bytes * a.loops / (lat_ms * 1e-3) / 1e9 / peak,
-              "note": "batch 1: working set fits in L2, launch/latency bound"}
-    eng1.close()
-
-    # ---- config 3 sample: optical-trap movie frames, GS 50 iterations at the SLM shape -----------------------
-    movie = None
-    if not a.no_movie:
-        mshape, mframes, mloops = (768, 1024), 64, 50
-        engm = Engine(mshape, a.precision, mframes)
-        frames_dev = torch.from_numpy(synthetic.movie_frames(mframes)).to(dev)
-        mnorms = np.full(mframes, 255.0)
-        for _ in range(2):
-            engm.gs(frames_dev, mloops, want_expected=False, norms=mnorms)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(3):
-            engm.gs(frames_dev, mloops, want_expected=False, norms=mnorms)
-        e1.record()
-        torch.cuda.synchronize()
-        mt = e0.elapsed_time(e1) / 3 * 1e-3
-        movie = {"workload": f"{mframes} trap frames {mshape[0]}x{mshape[1]}, GS {mloops} iterations, device resident",
-                 "holograms_per_s": mframes / mt, "iterations_per_s": mframes * mloops / mt}
-        engm.close()
-        # the same movie through the drop-in driver: host uint8 frames in, host float64 holograms out
-        from spatial_light_modulator_module_b200 import generate_hologram_sequence as ghs
-        host_frames = synthetic.movie_frames(2 * mframes)
-        for _ in range(2):      # warm-up (the engine page-locks host arrays it is handed a second time; result arrays are pooled)
-            ghs.sequence_holograms(host_frames, mloops, precision=a.precision, batch=mframes // 2, gather=False)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        ghs.sequence_holograms(host_frames, mloops, precision=a.precision, batch=mframes // 2, gather=False)
-        torch.cuda.synchronize()
-        et = time.perf_counter() - t0
-        movie["e2e"] = {"holograms_per_s": 2 * mframes / et / world, "frames": 2 * mframes // world, "batch": mframes // 2,
-                        "h2d_bytes": int(host_frames.nbytes) // world, "d2h_bytes": int(2 * mframes * mshape[0] * mshape[1] * 8) // world,
-                        "api": "generate_hologram_sequence.sequence_holograms(frames_uint8, 50) -> float64 holograms"}
-
-    # ---- end to end through the drop-in API with host buffers ----------------------------------------
-    ns = argparse.Namespace(incomming_intensity="uniform", tolerance=0, max_loops=a.loops, gif=False, print_info=False,
-                            plot_error=False, initial_guess="random", random_seed=42, white_attention=1,
-                            learning_rate=0.005, unsettle=0, precision=a.precision, device=local_rank)
-    host_targets = [synthetic.noise_target(shape, seed=77 + i) for i in range(a.e2e_steps + 1)]
-    host_mask = synthetic.random_mask(shape, seed=1)
-    fn = algorithms.gradient_descent if a.alg == "gd" else algorithms.gerchberg_saxton
-
-    def e2e_once(t):
-        with contextlib.redirect_stdout(io.StringIO()):
-            holo, exp, errs = fn(t, ns)
-        ns.learning_rate = 0.005
-        return display_holograms.hologram_to_grey(holo, host_mask, 256), errs
-    e2e_once(host_targets[-1])
-    e2e_once(host_targets[-1])             # (second warm-up: the engine page-locks a host array it is handed twice -- the mask)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(a.e2e_steps):
-        grey, errs = e2e_once(host_targets[i])
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / a.e2e_steps
+    verified, verification = (None, {"skipped": "GS free-running is chaotic on dense targets (DESIGN.md 2); see tests"})
+    if a.alg == "gd":
+        verified, verification = verify_headline(st, shape, a.loops, a.precision)
+    if verified is not None:
+        verified = h.all_ok(verified)
     csz = 8 if a.precision == "fp32" else 16
-    h2d = npx * 1 + npx * 8 + npx * 8     # target; hologram + mask for the quantiser (the GD initial guess is drawn on the device)
-    d2h = npx * 8 * 2 + a.loops * 8 + npx                                    # hologram, expected, error curve, grey frame
-    e2e = {"value": a.loops / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "ms_per_hologram": 1e3 * e2e_s, "holograms_per_s": 1 / e2e_s,
-           "api": f"algorithms.{fn.__name__}(target_uint8, args) -> numpy; display_holograms.hologram_to_grey(h, mask, 256)"}
+    line = {
+        "metric": "GS/GD iterations/sec at 1024^2", "value": head["value"], "unit": "iterations/s", "n_gpus": world,
+        "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": head["ms_per_step"], "step_ms": head["step_ms"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if a.precision == "fp32" else "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(a, shape), "algorithm": a.alg, "shape": list(shape), "batch_per_gpu": a.batch,
+                   "iterations": a.loops, "precision_mode": f"{a.precision} (north star: fp32 mode with 1e-3 tolerances, fp64 parity mode with 1e-9; "
+                                                            "the reference computes in complex128 -- see configs.fp64)",
+                   "l2": f"inputs larger than L2: {3 * a.batch * npx * csz / 2**20:.0f} MiB of field planes per GPU",
+                   "seeds": "targets default_rng(1000*rank+i+1) (plane 0: seed 0 = the reference fixture), mask default_rng(1)",
+                   "gd_form": head.get("gd_form")},
+        "holograms_per_s": head["holograms_per_s"], "gpu_launches": head["gpu_launches"], "clocks": clocks,
+        "verified": verified, "verification": verification,
+        "roofline": head.get("roofline"), "iteration_roofline": head["iteration_roofline"], "kernels": head.get("kernels"),
+        "targets": {"north_star": ">= 70 % of 8 TB/s on SURVEY 8(d) bytes", "gd_iterations_per_s": 0.7 * 8e12 / (survey_bytes_per_px("gd", "fp32") * npx),
+                    "gs_iterations_per_s": 0.7 * 8e12 / (survey_bytes_per_px("gs", "fp32") * npx)},
+    }
+    configs = {}
 
-    # ---- CPU baseline (oracle port, single core as the reference runs it) ------------------------------
+    # ---- latency of ONE hologram (batch 1), device resident ---------------------------------------------------------
+    if "headline" in only:
+        eng1 = Engine(shape, a.precision, 1)
+        t1, x01 = st["targets"][:1].contiguous(), (st["x0"][:1].contiguous() if st["x0"] is not None else None)
+        x1 = torch.empty_like(x01) if x01 is not None else None
+
+        def step1():
+            if a.alg == "gd":
+                x1.copy_(x01)
+                r, _ = eng1.gd(t1, x1, st["during"], a.loops, want_expected=False, norms=st["norms"][:1])
+            else:
+                r = eng1.gs(t1, a.loops, want_expected=False, norms=st["norms"][:1])
+            return eng1.quantize(r.hologram, mask_dev, 256, _ffi.QUANT_FLOOR)
+        ms1, _, _ = h.time_steps(step1, 3, a.steps)
+        lat = ms1 / a.steps
+        line["single_hologram"] = {"ms_per_hologram": lat, "iterations_per_s": a.loops / (lat * 1e-3),
+                                   "note": "batch 1 (the unit the reference API hands over): the working set fits in L2, launch/latency bound"}
+        eng1.close()
+    st["eng"].close()
+    del st
+
+    if "gs_1024" in only:
+        rec, s2 = batched_loop_record(h, a, "gs", "fp32", (1024, 1024), a.batch, a.loops, max(3, a.steps // 2), 3, peak, peak_src, extra_step=quant)
+        s2["eng"].close()
+        configs["gs_1024"] = rec
+    if "fp64" in only:
+        m64 = torch.from_numpy(synthetic.random_mask((1024, 1024), seed=1)).to(dev)
+        q64 = lambda eng, res: eng.quantize(res.hologram, m64, 256, _ffi.QUANT_FLOOR)      # noqa: E731
+        sub = {}
+        for alg in ("gd", "gs"):
+            rec, s2 = batched_loop_record(h, a, alg, "fp64", (1024, 1024), 16, a.loops, 3, 3, peak, peak_src, verify=(alg == "gd"), extra_step=q64)
+            if alg == "gd":
+                ok, info = verify_headline(s2, (1024, 1024), a.loops, "fp64")
+                rec["verified"], rec["verification"] = (h.all_ok(ok) if ok is not None else None), info
+            s2["eng"].close()
+            sub[alg] = rec
+        configs["fp64"] = sub
+    if "size_4096" in only:
+        sub = {}
+        for alg in ("gd", "gs"):
+            rec, s2 = batched_loop_record(h, a, alg, "fp32", (4096, 4096), 2, 20, 3, 3, peak, peak_src)
+            s2["eng"].close()
+            sub[alg] = rec
+        configs["size_4096"] = sub
+    if "config1" in only:
+        configs["config1"] = run_config1(h, a, local_rank)
+    if "config3" in only:
+        configs["config3"] = run_config3(h, a)
+    if "config4" in only:
+        configs["config4"] = run_config4(h, a, local_rank, peak)
+    if "config5" in only:
+        configs["config5"] = run_config5(h, a.slab_size, 20, "fp32", 2, 1, peak)
+
+    # ---- end to end through the drop-in API with host buffers, every rank at once -------------------------------------
+    if "e2e" in only:
+        ns = argparse.Namespace(incomming_intensity="uniform", tolerance=0, max_loops=a.loops, gif=False, print_info=False,
+                                plot_error=False, initial_guess="random", random_seed=42, white_attention=1,
+                                learning_rate=0.005, unsettle=0, precision=a.precision, device=local_rank)
+        host_targets = [synthetic.noise_target(shape, seed=77 + i + 100 * rank) for i in range(a.e2e_steps + 1)]
+        host_mask = synthetic.random_mask(shape, seed=1)
+        fn = algorithms.gradient_descent if a.alg == "gd" else algorithms.gerchberg_saxton
+        it = {"i": 0}
+
+        def e2e_once():
+            t = host_targets[it["i"] % len(host_targets)]
+            it["i"] += 1
+            with contextlib.redirect_stdout(io.StringIO()):
+                holo, exp, errs = fn(t, ns)
+            ns.learning_rate = 0.005
+            return display_holograms.hologram_to_grey(holo, host_mask, 256)
+        e2e_s, _ = h.wall_steps(e2e_once, 2, a.e2e_steps)     # (2 warm-ups: the engine page-locks a host array it is handed twice -- the mask)
+        h2d = npx * 1 + npx * 8 + npx * 8                    # target; hologram + mask for the quantiser (the GD initial guess is drawn on the device)
+        d2h = npx * 8 * 2 + a.loops * 8 + npx                # hologram, expected, error curve, grey frame
+        line["e2e"] = {"value": world * a.loops / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                       "ms_per_hologram": 1e3 * e2e_s, "holograms_per_s": world / e2e_s, "ranks": world,
+                       "api": f"algorithms.{fn.__name__}(target_uint8, args) -> numpy; display_holograms.hologram_to_grey(h, mask, 256); "
+                              "one hologram at a time per rank, all ranks at once, value = sum over ranks",
+                       "note": "random.seed(42) initial guess: the MT19937 stream is a pure function of (seed, size) and is memoised on the device "
+                               "(the reference's CLI always seeds 42, generate_hologram.py:370); SLM_NO_GUESS_MEMO=1 disables the memo"}
+
+    # ---- CPU baseline (oracle port, single core as the reference runs it), at every N on rank 0 ---------------------------
     cpu = None
-    if not a.no_cpu_baseline and world == 1:
+    if "cpu" in only and rank == 0:
         v, dt = cpu_port_iterations_per_s(a.alg, shape, min(a.cpu_loops, a.loops), 1)
         cpu = {"value": v, "unit": "iterations/s", "cores": 1, "kind": "port",
                "sample": f"1 hologram x {min(a.cpu_loops, a.loops)} iterations of oracle/numpy_port.py ({dt:.1f} s), "
                          f"scipy.fft workers=1 as in the reference; host has {os.cpu_count()} cores"}
-
-    line = {
-        "metric": "GS/GD iterations/sec at 1024^2", "value": value, "unit": "iterations/s", "n_gpus": world,
-        "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "step_ms": step_ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if a.precision == "fp32" else "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a, shape), "algorithm": a.alg, "shape": list(shape), "batch_per_gpu": a.batch,
-                   "iterations": a.loops, "l2": f"inputs larger than L2: {3 * a.batch * npx * csz / 2**20:.0f} MiB of field planes per GPU",
-                   "seeds": "targets default_rng(1000*rank+i), mask default_rng(1)"},
-        "holograms_per_s": a.batch * a.steps * world / (ms * 1e-3),
-        "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof,
-        "iteration_roofline": iteration_roofline, "kernels": kernels, "single_hologram": single, "movie_config3_sample": movie, "cpu_baseline": cpu,
-    }
-    emit(line)
+    line["cpu_baseline"] = cpu
+    line["configs"] = configs
+    if rank == 0:
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+def run_config1(h, a, local_rank):
+    """BASELINE configs[0]: ONE 512x512 GS hologram, 20 iterations (the reference's own CPU-runnable case)."""
+    import torch
+    from spatial_light_modulator_module_b200 import algorithms, synthetic
+    from spatial_light_modulator_module_b200.engine import Engine
+    shape, loops = (512, 512), 20
+    eng = Engine(shape, "fp32", 1)
+    t = synthetic.noise_target(shape, seed=0)
+    td = torch.from_numpy(t[None]).to(h.dev)
+    norms = np.array([float(t.max())])
+    ms, _, _ = h.time_steps(lambda: eng.gs(td, loops, want_expected=True, norms=norms).hologram, 5, 20)
+    ns = argparse.Namespace(incomming_intensity="uniform", tolerance=0, max_loops=loops, gif=False, print_info=False,
+                            plot_error=False, precision="fp32", device=local_rank)
+
+    def once():
+        with contextlib.redirect_stdout(io.StringIO()):
+            return algorithms.gerchberg_saxton(t, ns)
+    s, out = h.wall_steps(once, 3, 20)
+    eng.close()
+    return {"workload": "gerchberg_saxton(target 512x512 uint8 noise, max_loops=20): one hologram (BASELINE.json configs[0])",
+            "device_ms_per_hologram": ms / 20, "device_iterations_per_s": loops / (ms / 20 * 1e-3),
+            "e2e_ms_per_hologram": 1e3 * s, "e2e_iterations_per_s": loops / s, "e2e_holograms_per_s": 1 / s,
+            "final_error": float(out[2][-1]), "h2d_bytes": 512 * 512, "d2h_bytes": 2 * 512 * 512 * 8 + loops * 8,
+            "note": "latency bound: 2 MB of field, 41 launches; the device figure includes setup (ifft2 of the amplitude), the final "
+                    "hologram and the expected outcome"}
+
+
+def run_config3(h, a):
+    """BASELINE configs[2]: optical-trap movie, GS 50 iterations per frame, frames sharded over the ranks, results gathered
+    on rank 0 -- through generate_hologram_sequence.sequence_holograms with host frames in and host results out."""
+    from spatial_light_modulator_module_b200 import generate_hologram_sequence as ghs, synthetic
+    frames_n, loops, shape = a.movie_frames, 50, (768, 1024)
+    frames = synthetic.movie_frames(frames_n)
+    mask = synthetic.random_mask(shape, seed=1)
+    dots = synthetic.movie_frame_dots(frames_n)
+    rec = {"workload": f"{frames_n} trap frames {shape[0]}x{shape[1]} (two circulating dots, generate_traps_image_sequence.py:48-58), GS {loops} "
+                       f"iterations each, sharded over {h.world} GPU(s), gathered on rank 0 (BASELINE.json configs[2])", "frames": frames_n}
+    variants = {
+        "uint8_frames": dict(output="uint8", mask=mask, ct2pi=256),
+        "float64_holograms": dict(output="float64"),
+        "uint8_frames_device_rasterised": dict(output="uint8", mask=mask, ct2pi=256, trap_dots=(dots, frames_n, shape)),
+    }
+    for name, kw in variants.items():
+        src = None if "trap_dots" in kw else frames
+
+        def once():
+            return ghs.sequence_holograms(src, loops, precision="fp32", batch=32, gather=True, **kw)
+        s, out = h.wall_steps(once, 2 if name != "float64_holograms" else 1, 2)
+        per_frame = shape[0] * shape[1] * (1 if kw["output"] == "uint8" else 8)
+        rec[name] = {"holograms_per_s": frames_n / s, "iterations_per_s": frames_n * loops / s, "seconds": s,
+                     "h2d_bytes": 0 if src is None else int(frames.nbytes), "d2h_bytes": frames_n * per_frame,
+                     "gathered_bytes": 0 if h.world == 1 else frames_n * per_frame * (h.world - 1) // h.world,
+                     "final_error_frame0": float(out[2][0][-1]) if env_rank()[0] == 0 else None}
+    rec["note"] = ("timed region: host uint8 frames -> device, 50 iterations per frame, mask add + quantisation (uint8 variants), device-to-device "
+                   "gather on rank 0 (NCCL) and the read-back into page-locked host memory; float64 results are bounded by rank 0's PCIe link "
+                   "(6 MiB per frame), uint8 SLM frames are what display_holograms.py:253-266 consumes")
+    return rec
+
+
+def run_config4(h, a, local_rank, peak):
+    """BASELINE configs[3]: compare_error_evolution_algorithms over many large targets: GD then GS, all curves."""
+    from spatial_light_modulator_module_b200 import compare_error_evolution_algorithms as cmp, host_logic as hl, synthetic
+    rank, world = env_rank()[0], h.world
+    n_total, shape, loops = a.config4_targets, (2048, 2048), 50
+    lo, hi = hl.shard_range(n_total, rank, world)
+    kinds = []
+    for i in range(lo, hi):                                # the mix of SURVEY 8(d): noise, shapes, sparse traps
+        if i % 3 == 0:
+            kinds.append(synthetic.noise_target(shape, seed=i))
+        elif i % 3 == 1:
+            kinds.append(np.roll(synthetic.shapes_target(shape), 7 * i, axis=1))
+        else:
+            kinds.append(synthetic.traps_target(shape, [((37 * i) % shape[0], (91 * i) % shape[1]), ((211 * i) % shape[0], (503 * i) % shape[1])]))
+    targets = np.stack(kinds)
+    ns = argparse.Namespace(max_loops=loops, learning_rate=0.005, white_attention=1, unsettle=0, initial_guess="random", random_seed=42,
+                            precision="fp32", device=local_rank)
+    cmp.fill_unnecessary_args(ns)
+
+    def once():
+        return cmp.error_evolution_curves(targets, ns, batch=32)
+    s, (gd, gs) = h.wall_steps(once, 1, 1)
+    npx = shape[0] * shape[1]
+    it = 2 * n_total * loops
+    bytes_it = (survey_bytes_per_px("gd", "fp32") + survey_bytes_per_px("gs", "fp32")) / 2 * npx
+    return {"workload": f"compare_error_evolution_algorithms.error_evolution_curves: {n_total} targets x 2048x2048 (noise / shapes / traps), GD then "
+                        f"GS, {loops} iterations each, host uint8 targets in, {2 * n_total} error curves out, targets sharded over {world} GPU(s) "
+                        "(BASELINE.json configs[3])",
+            "seconds": s, "holograms_per_s": 2 * n_total / s, "iterations_per_s": it / s, "curves": 2 * n_total,
+            "h2d_bytes": int(n_total * npx), "d2h_bytes": int(2 * n_total * loops * 8),
+            "iteration_roofline_survey_bytes": {"achieved_gbs_per_gpu": bytes_it * it / s / 1e9 / world, "frac": bytes_it * it / s / 1e9 / world / peak,
+                                                "note": "whole call incl. the host->device copy of the targets and the drawing of the random guess"},
+            "gd_final_error_mean": float(np.mean([c[-1] for c in gd])), "gs_final_error_mean": float(np.mean([c[-1] for c in gs])),
+            "gd_curve0_decreasing": bool(gd[0][-1] < gd[0][0]) if len(gd) else None}
+
+
+def run_config5(h, n, loops, precision, steps, warmup, peak):
+    """BASELINE configs[4]: one n x n GS hologram, slab-decomposed over the ranks (strong scaling)."""
+    import torch
+    from spatial_light_modulator_module_b200.slab import SlabEngine
+    rank, world = env_rank()[0], h.world
+    rows = n // world
+    eng = SlabEngine(n, world, rank, precision)
+    slab = eng._mem_upload((np.random.default_rng(100 + rank).random((rows, n)) * 255).astype(np.uint8))   # resident in HBM
+    state = {}
+
+    def step():
+        state["out"] = eng.gs(slab, loops, want_expected=False, on_device=True)
+        return state["out"][0]
+    for _ in range(warmup):
+        eng.gs(slab, 2, want_expected=False, on_device=True)
+    n0 = eng.launch_count()
+    ms, _, _ = h.time_steps(step, 0, steps)
+    launches = eng.launch_count() - n0
+    errs = state["out"][2]
+    c = 8 if precision == "fp32" else 16
+    it_bytes = (8 * c + 4) * n * n
+    per_it = ms * 1e-3 / (steps * loops)
+    eng.close()
+    del slab
+    torch.cuda.empty_cache()
+    return {"workload": f"gerchberg_saxton, one {n}x{n} uint8 noise target, {loops} iterations incl. setup and the final hologram, rows split over "
+                        f"{world} GPU(s), 2 all-to-alls + 1 all-reduce per iteration (BASELINE.json configs[4])",
+            "value": 1.0 / per_it, "unit": "iterations/s", "scaling": "strong", "ms_per_hologram": ms / steps, "gpu_launches": int(launches),
+            "final_error": float(errs[-1]), "iterations": len(errs),
+            "iteration_roofline": {"survey_bytes_per_iteration": it_bytes, "achieved_gbs_per_gpu": it_bytes / per_it / 1e9 / world,
+                                   "frac": it_bytes / per_it / 1e9 / world / peak, "peak": peak, "unit": "GB/s per GPU"}}
+
+
 def run_slab(a):
-    """BASELINE configs[4]: one size^2 GS hologram, slab-decomposed over the ranks (strong scaling)."""
+    """`--workload slab`: config 5 alone, as the line's own workload."""
     import torch
     import torch.distributed as dist
     rank, local_rank, world = env_rank()
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from spatial_light_modulator_module_b200.slab import SlabEngine
-    n, loops = a.size, a.loops
-    rows = n // world
-    eng = SlabEngine(n, world, rank, a.precision)
-    slab = eng._mem_upload((np.random.default_rng(100 + rank).random((rows, n)) * 255).astype(np.uint8))   # resident in HBM
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    h = Harness(torch, dist, world, torch.device("cuda", local_rank))
+    peak, _ = measured_peak()
     sampler = ClockSampler(local_rank)
     if rank == 0 and not os.environ.get("SLM_BENCH_NO_SAMPLER"):
         sampler.start()
-    for _ in range(max(a.warmup, 1)):
-        eng.gs(slab, 2, want_expected=False, on_device=True)
-    barrier()
-    n0 = eng.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.time()
-    e0.record()
-    for _ in range(a.steps):
-        holo, _, errs = eng.gs(slab, loops, want_expected=False, on_device=True)
-    e1.record()
-    barrier()
-    wall1 = time.time()
-    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        tmax = torch.tensor([ms], device=torch.device("cuda", local_rank), dtype=torch.float64)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ms = float(tmax.item())
-    launches = eng.launch_count() - n0
+    rec = run_config5(h, a.size, a.loops, a.precision, a.steps, max(a.warmup, 1), peak)
+    clocks = sampler.stop(wall0, time.time()) if rank == 0 else None
     if rank == 0:
-        peak, peak_src = measured_peak()
-        c = 8 if a.precision == "fp32" else 16
-        it_bytes = (8 * c + 4) * n * n
-        per_it = ms * 1e-3 / (a.steps * loops)
-        emit(({
-            "metric": f"GS iterations/sec on one {n}^2 plane (slab-decomposed)", "value": 1.0 / per_it, "unit": "iterations/s",
-            "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 1), "ms_per_step": ms / a.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32" if a.precision == "fp32" else "f64", "data": "synthetic",
-            "config": {"workload": f"gerchberg_saxton, one {n}x{n} uint8 noise target, {loops} iterations incl. setup and the final "
-                                   f"hologram read-back, rows split over {world} GPU(s), 2 all-to-alls + 1 all-reduce per iteration "
-                                   f"(BASELINE.json configs[4])"},
-            "gpu_launches": int(launches), "final_error": float(errs[-1]), "clocks": clocks,
-            "iteration_roofline": {"alg_bytes_per_iteration": it_bytes, "achieved": it_bytes / per_it / 1e9 / world, "peak": peak,
-                                   "unit": "GB/s per GPU", "frac": it_bytes / per_it / 1e9 / world / peak, "peak_source": peak_src},
-        }))
+        emit({"metric": f"GS iterations/sec on one {a.size}^2 plane (slab-decomposed)", "value": rec["value"], "unit": "iterations/s",
+              "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 1), "ms_per_step": rec["ms_per_hologram"], "higher_is_better": True,
+              "scaling": "strong", "vs_baseline": None, "dtype": "f32" if a.precision == "fp32" else "f64", "data": "synthetic",
+              "config": {"workload": rec["workload"]}, "gpu_launches": rec["gpu_launches"], "final_error": rec["final_error"], "clocks": clocks,
+              "iteration_roofline": rec["iteration_roofline"]})
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -490,8 +726,7 @@ _REAL_STDOUT = 1
 if __name__ == "__main__":
     args = parse()
     # watchdog: a run that takes absurdly long (default 20 min; SLM_BENCH_WATCHDOG=seconds) dumps every thread's stack
-    # to stderr and exits instead of hanging its launcher (one 2-GPU run of this round stalled after NCCL's init and
-    # could not be reproduced in five repeats)
+    # to stderr and exits instead of hanging its launcher
     import faulthandler
     faulthandler.dump_traceback_later(float(os.environ.get("SLM_BENCH_WATCHDOG", "1200")), exit=True)
     # libraries (NCCL's version banner, ...) write to file descriptor 1: keep it for the JSON line alone

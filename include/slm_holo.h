@@ -134,8 +134,31 @@ int slm_rows_gs_row_pass(slm_ctx* ctx, const void* in, void* out, const void* in
  * partial[rows][4]; intensity (nullable, device double, same layout) receives |C|^2. */
 int slm_rows_gs_fourier_pass(slm_ctx* ctx, const void* in, void* out, int block_w, const uint8_t* target_u8,
                              const double* amp_lut, double scale_prev, double* partial, double* intensity);
+/* The same with the previous iteration's scale read from device memory (loop state kept on the device: no host
+ * round trip per iteration; see slm_rows_close). */
+int slm_rows_gs_fourier_pass_dev(slm_ctx* ctx, const void* in, void* out, int block_w, const uint8_t* target_u8,
+                                 const double* amp_lut, const double* scale_prev_dev, double* partial, double* intensity);
+/* partial[rows][4] -> out4 (device double[4]: max, three sums) by one CTA in a fixed order.  With n_peers > 0 the four
+ * numbers are also stored into every peer's gathered[self] (peer_gathered[r] = rank r's device double[n_peers][4],
+ * mapped into this process: peer memory over NVLink) -- otherwise the caller all-gathers out4. */
+int slm_rows_reduce(slm_ctx* ctx, const double* partial, int rows, double* out4, const void* const* peer_gathered,
+                    int n_peers, int self);
+/* Close one GS iteration of the distributed plane from every rank's four numbers (gathered: device double[world][4],
+ * rank order): scale = norm / max (algorithms.py:37), error (algorithms.py:38,162) appended to err_curve (device),
+ * loop condition (algorithms.py:29).  state: device double[4] = {scale (in: the one the pass used; out: the new one),
+ * last error, iterations done, loop-ended flag}.  prepass != 0: only the scale (exact scale of iteration 0). */
+int slm_rows_close(slm_ctx* ctx, const double* gathered, int world, double norm, double hw, int prepass, double tolerance,
+                   double* state, double* err_curve);
 /* row slab [rows][W] <-> exchange layout [W/rows][rows][rows] (each block transposed); elem_bytes 1, 8 or 16. */
 int slm_transpose_blocks(slm_ctx* ctx, const void* in, void* out, int rows, int W, int elem_bytes, int from_exchange);
+
+/* The transposing copy AS the all-to-all: block q goes straight into rank q's memory (peers[q], mapped into this
+ * process -- CUDA peer memory over NVLink), so the blocks cross the links while they are being transposed and no
+ * send/receive staging exists.  from_exchange = 0: peers[q] is rank q's receive buffer (exchange layout), block `self`
+ * of it is written; from_exchange = 1: peers[q] is rank q's row slab, columns [self*rows, (self+1)*rows) are written.
+ * The caller orders the ranks (a device-side barrier before the consumers run and before the buffers are reused). */
+int slm_transpose_blocks_peer(slm_ctx* ctx, const void* in, const void* const* peers, int n_peers, int self, int rows, int W,
+                              int elem_bytes, int from_exchange);
 
 /* error_evolution and its length per plane (algorithms.py:25,39,93) of the last run.
  * err: host double[batch][max_loops]; iters: host int[batch].  Synchronises the stream. */

@@ -237,6 +237,73 @@ SLM_GLOBAL void transpose_blocks_kernel(const T* in, T* out, int h, int W, int f
     }
 }
 
+// The same, with every block going to (or coming from the point of view of) ANOTHER device: `peers.p[q]` is the
+// base of rank q's buffer, mapped into this process (peer memory over NVLink), `self` this rank.
+//   push      (from_exchange = 0): peer q's receive buffer, block `self`:  p[q][self][c][i] = in[i][q*h + c]
+//   push back (from_exchange = 1): peer q's row slab, my columns:           p[q][i][self*h + c] = in[q][c][i]
+// The stores ARE the all-to-all: the blocks cross the links while the tiles are being transposed.
+struct PeerPtrs { void* p[16]; };
+template <typename T>
+SLM_GLOBAL void transpose_blocks_peer_kernel(const T* in, PeerPtrs peers, int h, int W, int from_exchange, int self) {
+    SLM_STATIC_SMEM T tile[32][33];
+    const int q = blockIdx.z, tc = blockIdx.y * 32, ti = blockIdx.x * 32;
+    const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+    T* out = static_cast<T*>(peers.p[q]);
+    if (!from_exchange) {
+#pragma unroll
+        for (int k = 0; k < 32; k += 8) tile[ty + k][tx] = in[(size_t)(ti + ty + k) * W + (size_t)q * h + tc + tx];     // [i][c]
+        sync_cta();
+        const size_t blk = (size_t)self * h * h;
+#pragma unroll
+        for (int k = 0; k < 32; k += 8) out[blk + (size_t)(tc + ty + k) * h + ti + tx] = tile[tx][ty + k];              // [c][i]
+    } else {
+        const size_t blk = (size_t)q * h * h;
+#pragma unroll
+        for (int k = 0; k < 32; k += 8) tile[ty + k][tx] = in[blk + (size_t)(tc + ty + k) * h + ti + tx];               // [c][i]
+        sync_cta();
+#pragma unroll
+        for (int k = 0; k < 32; k += 8) out[(size_t)(ti + ty + k) * W + (size_t)self * h + tc + tx] = tile[tx][ty + k];  // [i][c]
+    }
+}
+
+// ---- loop state of the row-slab GS on the device (no host round trip per iteration) ---------------------------------
+// partial[rows][4] (max |C|^2, sum r^2, sum r*u, sum u^2 per line) -> out[4] for this rank: ONE CTA, fixed order.
+SLM_GLOBAL void rows_reduce_kernel(const double* partial, int rows, double* out, PeerPtrs peers, int n_peers, int self) {
+    Partial q; q.mx = 0; q.a = 0; q.b = 0; q.c = 0;
+    for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+        Partial r; r.mx = partial[4 * i]; r.a = partial[4 * i + 1]; r.b = partial[4 * i + 2]; r.c = partial[4 * i + 3];
+        q = combine<F_ALL>(q, r);
+    }
+    q = block_reduce<256, F_ALL>(q, threadIdx.x);
+    if (threadIdx.x == 0) {
+        out[0] = q.mx; out[1] = q.a; out[2] = q.b; out[3] = q.c;
+        for (int r = 0; r < n_peers; ++r) {                       // peer mode: every rank's `gathered[self]` (else the caller all-gathers)
+            double* g = static_cast<double*>(peers.p[r]) + 4 * self;
+            g[0] = q.mx; g[1] = q.a; g[2] = q.b; g[3] = q.c;
+        }
+    }
+}
+// gathered[world][4] -> the plane's max and sums (rank order: the same bits on every rank); closes the iteration like
+// close_plane<GS>: state[0] = scale (in: the one the pass used, out: norm / max), state[1] = error, state[2] = iterations
+// done (as a double), state[3] = loop-ended flag.  prepass: only the scale (exact scale of iteration 0).
+SLM_GLOBAL void rows_close_kernel(const double* gathered, int world, double norm, double hw, int prepass, int as_float,
+                                  double tolerance, double* state, double* err_curve) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double mx = 0, a = 0, b = 0, c = 0;
+    for (int r = 0; r < world; ++r) {
+        mx = fmax(mx, gathered[4 * r]); a += gathered[4 * r + 1]; b += gathered[4 * r + 2]; c += gathered[4 * r + 3];
+    }
+    const double s = norm / mx;                                   // algorithms.py:37
+    if (prepass) { state[0] = s; return; }
+    const double s0u = as_float ? (double)(float)state[0] : state[0];          // the scale the kernel used
+    const double dl = s0u != 0.0 ? s / s0u - 1.0 : 0.0;
+    const double err = (a + 2.0 * dl * b + dl * dl * c) / hw;     // algorithms.py:38,162
+    const int k = (int)state[2];
+    err_curve[k] = err;
+    state[0] = s; state[1] = err; state[2] = (double)(k + 1);
+    state[3] = !(err > tolerance) ? 1.0 : 0.0;                    // loop condition, algorithms.py:29
+}
+
 // complex<R> <-> complex128 / real conversions at the boundary (numpy hands over complex128)
 template <typename TS, typename TD>
 SLM_GLOBAL void convert_kernel(const TS* in, TD* out, long long n) {

@@ -715,6 +715,66 @@ extern "C" int slm_rows_gs_fourier_pass(slm_ctx* c, const void* in, void* out, i
     return 0;
 }
 
+extern "C" int slm_rows_gs_fourier_pass_dev(slm_ctx* c, const void* in, void* out, int block_w, const uint8_t* target_u8,
+                                            const double* amp_lut, const double* scale_prev_dev, double* partial, double* intensity) {
+    if (!c || !in || !out || !target_u8 || !amp_lut || !partial || !scale_prev_dev) return fail(SLM_ERR_ARG, "slm_rows_gs_fourier_pass_dev: bad argument");
+    if (!block_width_ok(c, block_w))
+        return fail(SLM_ERR_SHAPE, "slm_rows_gs_fourier_pass_dev: the exchange block width must be a power-of-two multiple of the line's thread count");
+    SLM_CUDA(cudaSetDevice(c->device));
+    SLM_TRY(upload_lut(c, amp_lut));
+    RowFourierArgs fa{};
+    fa.rows = c->H; fa.block_w = block_w; fa.in = in; fa.out = out; fa.T8 = target_u8; fa.lut = c->lut; fa.s0 = 0.0; fa.s0_dev = scale_prev_dev;
+    fa.partial = partial; fa.intensity = intensity; fa.tw = c->tw_row;
+    SLM_TIMED(K_COL_PASS, c->row->row_fourier(fa, c->stream));
+    return 0;
+}
+
+static int peer_ptrs(const void* const* peers, int n, PeerPtrs* out, const char* who) {
+    if (n < 0 || n > 16 || (n && !peers)) return fail(SLM_ERR_ARG, std::string(who) + ": at most 16 peers");
+    for (int i = 0; i < 16; ++i) out->p[i] = i < n ? const_cast<void*>(peers[i]) : nullptr;
+    return 0;
+}
+
+extern "C" int slm_rows_reduce(slm_ctx* c, const double* partial, int rows, double* out4, const void* const* peer_gathered,
+                               int n_peers, int self) {
+    if (!c || !partial || !out4 || rows < 1) return fail(SLM_ERR_ARG, "slm_rows_reduce: bad argument");
+    SLM_CUDA(cudaSetDevice(c->device));
+    PeerPtrs pp;
+    SLM_TRY(peer_ptrs(peer_gathered, n_peers, &pp, "slm_rows_reduce"));
+    { LaunchTimer t_(c, K_ELEMENTWISE); SLM_LAUNCH(rows_reduce_kernel, dim3(1), dim3(256), 0, c->stream, partial, rows, out4, pp, n_peers, self); }
+    SLM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int slm_rows_close(slm_ctx* c, const double* gathered, int world, double norm, double hw, int prepass, double tolerance,
+                              double* state, double* err_curve) {
+    if (!c || !gathered || !state || world < 1 || (!prepass && !err_curve)) return fail(SLM_ERR_ARG, "slm_rows_close: bad argument");
+    SLM_CUDA(cudaSetDevice(c->device));
+    { LaunchTimer t_(c, K_ELEMENTWISE); SLM_LAUNCH(rows_close_kernel, dim3(1), dim3(32), 0, c->stream, gathered, world, norm, hw, prepass,
+                                                    c->prec == PREC_F32 ? 1 : 0, tolerance, state, err_curve); }
+    SLM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int slm_transpose_blocks_peer(slm_ctx* c, const void* in, const void* const* peers, int n_peers, int self, int rows, int W,
+                                         int elem_bytes, int from_exchange) {
+    if (!c || !in || n_peers < 1 || self < 0 || self >= n_peers) return fail(SLM_ERR_ARG, "slm_transpose_blocks_peer: bad argument");
+    if (rows < 32 || rows % 32 || W != rows * n_peers) return fail(SLM_ERR_SHAPE, "slm_transpose_blocks_peer: W must be rows * peers, rows a multiple of 32");
+    SLM_CUDA(cudaSetDevice(c->device));
+    PeerPtrs pp;
+    SLM_TRY(peer_ptrs(peers, n_peers, &pp, "slm_transpose_blocks_peer"));
+    const dim3 grid(rows / 32, rows / 32, W / rows), block(256);
+    {
+        LaunchTimer t_(c, K_ELEMENTWISE);
+        if (elem_bytes == 16) SLM_LAUNCH((transpose_blocks_peer_kernel<cpx<double>>), grid, block, 0, c->stream, static_cast<const cpx<double>*>(in), pp, rows, W, from_exchange, self);
+        else if (elem_bytes == 8) SLM_LAUNCH((transpose_blocks_peer_kernel<double>), grid, block, 0, c->stream, static_cast<const double*>(in), pp, rows, W, from_exchange, self);
+        else if (elem_bytes == 1) SLM_LAUNCH((transpose_blocks_peer_kernel<unsigned char>), grid, block, 0, c->stream, static_cast<const unsigned char*>(in), pp, rows, W, from_exchange, self);
+        else return fail(SLM_ERR_ARG, "slm_transpose_blocks_peer: elem_bytes must be 1, 8 or 16");
+    }
+    SLM_CUDA(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int slm_transpose_blocks(slm_ctx* c, const void* in, void* out, int rows, int W, int elem_bytes, int from_exchange) {
     if (!c || !in || !out || in == out) return fail(SLM_ERR_ARG, "slm_transpose_blocks: bad argument");
     if (rows < 32 || rows % 32 || W % rows) return fail(SLM_ERR_SHAPE, "slm_transpose_blocks: rows must be a multiple of 32 dividing W");

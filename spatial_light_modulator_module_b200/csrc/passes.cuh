@@ -550,7 +550,7 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), (RowGeom<R, W>::MIN_
     }
     line_fft<R, W, -1, 1>(v, line, j, tw, sync);              // second half of C = fft2(B)
     R mx = 0, sa = 0, sb = 0, sc = 0;
-    const R s0r = (R)a.s0;
+    const R s0r = (R)(a.s0_dev ? ld_cg(a.s0_dev) : a.s0);
 #pragma unroll
     for (int r = 0; r < E; ++r) {
         const R m2 = cnorm2(v[r]);

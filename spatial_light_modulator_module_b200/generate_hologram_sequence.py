@@ -223,8 +223,10 @@ def _gather_curves(dist, n_total, errors, max_loops):
 
 def generate_hologram_sequence(args):
     """Drop-in for the reference driver (generate_hologram_sequence.py:10-32): reads
-    ``images/moving_traps/<source_dir>/<i>.png``, writes ``<i>.npy`` holograms (and preview PNGs).
-    Optional ``args.batch`` / ``args.precision`` tune the engine."""
+    ``images/moving_traps/<source_dir>/<i>.png``, writes ``<i>.npy`` holograms (and preview PNGs) -- from a writer
+    thread, batch by batch, while the following batches iterate on the device.  Optional ``args.batch`` /
+    ``args.precision`` tune the engine.  Under an initialised process group every rank computes and writes its own
+    block of frames (no gather: the files are the result)."""
     from PIL import Image as im
     dest_dir_holograms = f"holograms/{args.source_dir}_{args.version}_holograms"
     dest_dir_preview = f"images/moving_traps/{args.source_dir}_{args.version}_preview"
@@ -240,17 +242,20 @@ def generate_hologram_sequence(args):
     if getattr(args, "incomming_intensity", "uniform") != "uniform":
         from .algorithms import _illumination
         inc = _illumination(args, frames.shape[1:])
-    holos, exps, errors, (lo, hi) = sequence_holograms(
+    from .display_holograms import preview_to_grey
+
+    def write(lo, hi, holos, exps):
+        for k in range(hi - lo):
+            i = lo + k
+            print(f"\rcreating {i}. hologram ", end="")
+            np.save(f"{dest_dir_holograms}/{i}.npy", holos[k])
+            if args.preview:
+                im.fromarray(preview_to_grey(exps[k])).save(f"{dest_dir_preview}/{i}.png")
+
+    _, _, errors, _ = sequence_holograms(
         frames, int(args.max_loops), float(args.tolerance), getattr(args, "precision", None) or
         os.environ.get("SLM_PRECISION", "fp32"), int(getattr(args, "batch", 32)), bool(args.preview), gather=False,
-        inc_amp=inc)
-    from .display_holograms import preview_to_grey
-    for k in range(hi - lo):
-        i = lo + k
-        print(f"\rcreating {i}. hologram ", end="")
-        np.save(f"{dest_dir_holograms}/{i}.npy", holos[k])
-        if args.preview:
-            im.fromarray(preview_to_grey(exps[k])).save(f"{dest_dir_preview}/{i}.png")
+        inc_amp=inc, on_batch=write)
     plot_error_evolution([list(e) for e in errors])
     return errors
 
@@ -265,3 +270,34 @@ def plot_error_evolution(err_evl_list):
         plt.plot(err_evl, label=i)
     plt.legend()
     plt.show()
+
+
+def build_parser():
+    """The reference's command line (generate_hologram_sequence.py:43-103): same arguments and defaults;
+    ``--batch`` and ``--precision`` are additions."""
+    import argparse
+    p = argparse.ArgumentParser(formatter_class=argparse.ArgumentDefaultsHelpFormatter,
+                                description="Holograms of a sequence of trap images (images/moving_traps/<source_dir>/<i>.png) "
+                                            "-> holograms/<source_dir>_<version>_holograms/<i>.npy, computed in batches on a B200.")
+    p.add_argument("source_dir", type=str, help="directory with the trap images, inside images/moving_traps")
+    p.add_argument("-v", "--version", type=str, help="tag appended to the output directory names")
+    p.add_argument("-ii", "--incomming_intensity", metavar="PATH", type=str, default="uniform", help="illumination image path, or 'uniform'")
+    p.add_argument("-ct2pi", "--correspond_to2pi", metavar="INT", required=True, type=int, help="grey level that corresponds to a 2 pi phase shift")
+    p.add_argument("-tol", "--tolerance", metavar="FLOAT", default=0, type=float, help="stop when the error falls to this value")
+    p.add_argument("-loops", "--max_loops", metavar="INT", default=5, type=int, help="upper bound on the number of iterations")
+    p.add_argument("-p", "--preview", action="store_true", help="also write the expected images of the holograms")
+    p.add_argument("--batch", type=int, default=32, help="frames per device batch")
+    p.add_argument("--precision", default=None, choices=["fp32", "fp64"], help="engine arithmetic (default fp32)")
+    return p
+
+
+def cli(argv=None):
+    args = build_parser().parse_args(argv)
+    args.gif = False                       # generate_hologram_sequence.py:105-107
+    args.plot_error = False
+    args.print_info = False
+    generate_hologram_sequence(args)
+
+
+if __name__ == "__main__":
+    cli()

@@ -11,10 +11,19 @@ Rank p owns rows [p*h, (p+1)*h) of the N x N field, h = N / world.  One GS itera
     all-reduce    max |C|^2 and the three error sums (4 doubles)
     exchange      all-to-all back -> unpack into the row slab
 
-i.e. two all-to-alls and one tiny all-reduce per iteration; the target is exchanged once.  All array
-work is done by kernels of libslmholo (``slm_rows_*``, ``slm_transpose_blocks``); torch.distributed
-(NCCL over NVLink on GPUs) moves the blocks.  The loop is closed on the host (one scalar read per
-iteration), which is negligible next to a multi-millisecond iteration at these sizes.
+i.e. two all-to-alls and one tiny all-gather per iteration; the target is exchanged once.  All array work is done by
+kernels of libslmholo (``slm_rows_*``, ``slm_transpose_blocks*``).  The loop state (scale, error curve, iteration
+count) lives on the device: with ``tolerance <= 0`` -- every caller of the reference -- no iteration waits for the host.
+
+Two ways of moving the blocks:
+
+* **peer memory** (GPUs, world > 1, ``torch.distributed._symmetric_memory`` available): the row slabs and receive
+  buffers of all ranks are allocated symmetrically and mapped into every process; the transposing pack kernel stores
+  each block straight into its destination rank's buffer (``slm_transpose_blocks_peer``), so the transposition IS the
+  all-to-all -- the blocks cross NVLink while they are being transposed, nothing is staged -- and the ranks meet at a
+  device-side barrier.  The four reduction numbers travel the same way.  No NCCL call inside the loop.
+* **collectives** (fallback, and the CPU test-suite on gloo): pack -> ``all_to_all_single`` -> line pass -> ``all_gather``
+  of four doubles -> ``all_to_all_single`` -> unpack, all ordered on the engine's stream.
 """
 from __future__ import annotations
 
@@ -30,7 +39,7 @@ from .engine import Engine, _PREC, _NP_REAL, _NP_CPLX
 class SlabEngine(Engine):
     """Row-slab context: ``rows`` = N / world lines of N points on this rank's device."""
 
-    def __init__(self, n: int, world: int, rank: int, precision: str = "fp32", device=None, stream=None, group=None):
+    def __init__(self, n: int, world: int, rank: int, precision: str = "fp32", device=None, stream=None, group=None, peer=None):
         if n % world:
             raise ValueError("the grid size must be divisible by the number of ranks")
         self.n, self.world, self.rank, self.rows = int(n), int(world), int(rank), int(n) // int(world)
@@ -49,6 +58,60 @@ class SlabEngine(Engine):
         _ffi.check(self._lib, rc)
         self._ctx = ctx
         self._amp_lut = hl.amplitude_lut()
+        self._peer = None                     # symmetric allocation shared with the other ranks (peer-memory exchange)
+        self.peer_status = "single rank" if self.world == 1 else "collectives"
+        if self.world > 1 and peer is not False and self.world <= 16:
+            self._peer_setup(required=bool(peer))
+
+    # ---- peer memory (GPUs only; the CPU test-suite overrides this with a no-op) -----------------------------------
+    def _peer_setup(self, required: bool):
+        """One symmetric allocation per rank holding its two row slabs, its receive buffer and the gathered reduction
+        numbers; every rank learns the others' base pointers (torch's symmetric memory does the mapping)."""
+        import os
+        if os.environ.get("SLM_SLAB_NO_PEER"):
+            return
+        try:
+            torch = self._torch
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm
+            cs = np.dtype(self.complex_dtype).itemsize
+            plane = self.rows * self.n * cs
+            align = lambda v: (v + 1023) // 1024 * 1024       # noqa: E731
+            offs, total = {}, 0
+            for name, size in (("X", plane), ("Y", plane), ("Rv", plane), ("Tx", self.rows * self.n), ("gathered", 2 * self.world * 32)):
+                offs[name] = total
+                total += align(size)
+            with torch.cuda.stream(self._stream):
+                buf = symm.empty((total,), dtype=torch.uint8, device=self._dev)
+                group = self.group if self.group is not None else dist.group.WORLD
+                hdl = symm.rendezvous(buf, group)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            if len(ptrs) != self.world:
+                raise RuntimeError("symmetric memory handle does not cover the group")
+            self._peer = {"buf": buf, "hdl": hdl, "ptrs": ptrs, "offs": offs}
+            self.peer_status = "peer memory (torch symmetric memory, stores over NVLink)"
+        except Exception as exc:                  # no symmetric memory on this system: keep the collectives
+            self._peer = None
+            self.peer_status = f"collectives (peer memory unavailable: {type(exc).__name__}: {exc})"
+            if required:
+                raise
+
+    def _peer_view(self, name, shape, dtype):
+        torch = self._torch
+        tdt = {np.dtype(np.complex64): torch.complex64, np.dtype(np.complex128): torch.complex128, np.dtype(np.uint8): torch.uint8,
+               np.dtype(np.float64): torch.float64}[np.dtype(dtype)]
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        off = self._peer["offs"][name]
+        return self._peer["buf"][off:off + n].view(tdt).view(tuple(shape))
+
+    def _peer_array(self, name, extra=0):
+        """(void*)[world]: where `name` (+ `extra` bytes) lies in every rank's symmetric allocation"""
+        off = self._peer["offs"][name] + extra
+        return (C.c_void_p * self.world)(*[p + off for p in self._peer["ptrs"]])
+
+    def _peer_barrier(self):
+        with self._torch.cuda.stream(self._stream):
+            self._peer["hdl"].barrier(channel=0)
 
     # ---- hooks the test-suite overrides together with the _mem_* ones ------------------------------------
     def _as_torch(self, buf):
@@ -61,13 +124,28 @@ class SlabEngine(Engine):
         return dist
 
     # ---- collectives ---------------------------------------------------------------------------------------
+    def _on_stream(self):
+        """Collectives are ordered against torch's CURRENT stream: make that the engine's."""
+        import contextlib
+        torch = getattr(self, "_torch", None)
+        return torch.cuda.stream(self._stream) if torch is not None and getattr(self, "_stream", None) is not None else contextlib.nullcontext()
+
     def _all_to_all(self, send, recv):
         if self.world == 1:
             self._copy(send, recv)
             return
         dist = self._dist()
-        self._sync()
-        dist.all_to_all_single(self._as_torch(recv), self._as_torch(send), group=self.group)
+        with self._on_stream():
+            dist.all_to_all_single(self._as_torch(recv), self._as_torch(send), group=self.group)
+
+    def _all_gather4(self, mine, gathered):
+        """every rank's four reduction numbers (device double[4]) -> gathered [world][4] on every rank, rank order"""
+        if self.world == 1:
+            self._copy(mine, gathered[0])
+            return
+        dist = self._dist()
+        with self._on_stream():
+            dist.all_gather(list(self._as_torch(gathered).unbind(0)), self._as_torch(mine), group=self.group)
 
     def _all_reduce(self, values: np.ndarray, op: str) -> np.ndarray:
         if self.world == 1:
@@ -77,7 +155,8 @@ class SlabEngine(Engine):
         t = torch.from_numpy(np.ascontiguousarray(values, dtype=np.float64))
         if dist.get_backend(self.group) == "nccl":
             t = t.to(self._dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM, group=self.group)
+        with self._on_stream():
+            dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM, group=self.group)
         return t.cpu().numpy()
 
     def _sync(self):
@@ -91,18 +170,29 @@ class SlabEngine(Engine):
         self._check(self._lib.slm_transpose_blocks(self._ctx, self._mem_ptr(src), self._mem_ptr(dst), self.rows, self.n,
                                                    elem_bytes, int(from_exchange)))
 
-    def _exchange(self, slab, send, recv, elem_bytes):
-        """row slab -> exchange layout of the columns this rank owns (in ``recv``)."""
+    def _exchange(self, slab, send, recv, elem_bytes, peer_name=None):
+        """row slab -> exchange layout of the columns this rank owns (in ``recv``; ``peer_name``: recv is that symmetric
+        buffer on every rank, so the blocks are stored straight into their destinations)."""
         if self.world == 1:
             self._transpose(slab, recv, elem_bytes, False)
+            return
+        if self._peer is not None and peer_name is not None:
+            self._check(self._lib.slm_transpose_blocks_peer(self._ctx, self._mem_ptr(slab), self._peer_array(peer_name), self.world,
+                                                            self.rank, self.rows, self.n, elem_bytes, 0))
+            self._peer_barrier()                 # every block of `recv` has landed (and every rank is done with `slab`)
             return
         self._transpose(slab, send, elem_bytes, False)
         self._all_to_all(send, recv)
 
-    def _exchange_back(self, lines, recv, slab, elem_bytes):
-        """exchange layout (after a pass over the owned columns) -> row slab."""
+    def _exchange_back(self, lines, recv, slab, elem_bytes, peer_name=None):
+        """exchange layout (after a pass over the owned columns) -> row slab (``peer_name``: the symmetric slab)."""
         if self.world == 1:
             self._transpose(lines, slab, elem_bytes, True)
+            return
+        if self._peer is not None and peer_name is not None:
+            self._check(self._lib.slm_transpose_blocks_peer(self._ctx, self._mem_ptr(lines), self._peer_array(peer_name), self.world,
+                                                            self.rank, self.rows, self.n, elem_bytes, 1))
+            self._peer_barrier()
             return
         self._all_to_all(lines, recv)
         self._transpose(recv, slab, elem_bytes, True)
@@ -111,12 +201,6 @@ class SlabEngine(Engine):
         lut = self._dp(self._amp_lut) if u8 is not None else None
         self._check(self._lib.slm_rows_fft(self._ctx, self._mem_ptr(src), self._mem_ptr(u8), lut, self._mem_ptr(dst),
                                            int(inverse), int(block_in), int(block_out)))
-
-    def _partial_totals(self, partial) -> Tuple[float, np.ndarray]:
-        p = self.to_host(partial).reshape(self.rows, 4)
-        mx = self._all_reduce(np.array([p[:, 0].max()]), "max")[0]
-        sums = self._all_reduce(p[:, 1:].sum(axis=0), "sum")
-        return float(mx), sums
 
     # ---- Gerchberg-Saxton on the distributed plane --------------------------------------------------------------
     def gs(self, target_slab, max_loops: int, tolerance: float = 0.0, want_expected: bool = True, on_device: bool = False):
@@ -137,79 +221,111 @@ class SlabEngine(Engine):
             T, local_max = self._mem_upload(t), float(t.max())
         h, n, cs = self.rows, self.n, np.dtype(self.complex_dtype).itemsize
         norm = float(self._all_reduce(np.array([local_max]), "max")[0])
-        Tx_send, Tx = self._mem_empty((self.world, h, h), np.uint8), self._mem_empty((self.world, h, h), np.uint8)
-        self._exchange(T, Tx_send, Tx, 1)                                    # target columns, once
-        X = self._mem_empty(self.shape, self.complex_dtype)                  # row slab
-        S = self._mem_empty((self.world, h, h), self.complex_dtype)          # exchange layout (send / lines)
-        Rv = self._mem_empty((self.world, h, h), self.complex_dtype)         # exchange layout (receive)
+        peer = self._peer is not None
+        blocks = (self.world, h, h)
+        Tx_send = None if peer else self._mem_empty(blocks, np.uint8)
+        Tx = self._peer_view("Tx", blocks, np.uint8) if peer else self._mem_empty(blocks, np.uint8)
+        self._exchange(T, Tx_send, Tx, 1, "Tx")                              # target columns, once
+        X = self._peer_view("X", self.shape, self.complex_dtype) if peer else self._mem_empty(self.shape, self.complex_dtype)   # row slabs
+        Y = self._peer_view("Y", self.shape, self.complex_dtype) if peer else self._mem_empty(self.shape, self.complex_dtype)
+        S = self._mem_empty(blocks, self.complex_dtype)                      # exchange layout: lines (and the send side of the collectives)
+        Rv = self._peer_view("Rv", blocks, self.complex_dtype) if peer else self._mem_empty(blocks, self.complex_dtype)  # receive side
         partial = self._mem_empty((h, 4), np.float64)
         # A = ifft2(sqrt(T))  (algorithms.py:27), unnormalised: only its phase is used.  For 8-bit targets the
         # reference computes it (and the first phasor) in complex64, so an fp64 plane borrows an fp32 engine.
         if self.precision == "fp32":
-            self._setup_field(T, X, S, Rv)
+            self._setup_field(T, X, S, Rv, "Rv", "X")
             A0, field_kind = X, 1
         else:
-            helper = type(self)(self.n, self.world, self.rank, "fp32", self._device_index, None, self.group)
+            helper = type(self)(self.n, self.world, self.rank, "fp32", self._device_index, None, self.group, peer=False)
             A0 = helper._mem_empty(self.shape, np.complex64)
-            helper._setup_field(T, A0, helper._mem_empty((self.world, h, h), np.complex64),
-                                helper._mem_empty((self.world, h, h), np.complex64))
+            helper._setup_field(T, A0, helper._mem_empty(blocks, np.complex64), helper._mem_empty(blocks, np.complex64))
             helper._sync()
             helper.close()
             field_kind = 2
-        Y = self._mem_empty(self.shape, self.complex_dtype)
         hw = float(n) * float(n)
-        errors: List[float] = []
-        s_prev = None
-        inten = self._mem_empty((self.world, h, h), np.float64) if want_expected else None
-        src, field = A0, field_kind
+        # loop state on the device: {scale, last error, iterations done, loop ended}, the error curve, the ranks' sums
+        state = self._mem_upload(np.array([1.0, 0.0, 0.0, 0.0]))
+        curve = self._mem_empty((max_loops,), np.float64)
+        mine = self._mem_empty((4,), np.float64)
+        # (two slots used in turn: a rank may run one closing step ahead of a peer that is still reading the previous one)
+        gathered = self._peer_view("gathered", (2, self.world, 4), np.float64) if peer else self._mem_empty((2, self.world, 4), np.float64)
+        self._slot = 0
+        inten = None
+        if want_expected:
+            inten = self._mem_empty(blocks, np.float64)
+        check_every = tolerance > 0                                           # the host must see every error to stop the loop
+        src, field, done_iters = A0, field_kind, 0
         for k in range(max_loops):
             cur = X if src is Y else Y                                        # receives the row-transformed B
             self._check(self._lib.slm_rows_gs_row_pass(self._ctx, self._mem_ptr(src), self._mem_ptr(cur), None, int(field), 0, None))
-            self._exchange(cur, S, Rv, cs)
-            if s_prev is None:                                                # exact scale of iteration 0: max pre-pass
-                self._fourier(Rv, S, Tx, 1.0, partial, None)
-                mx, _ = self._partial_totals(partial)
-                s_prev = norm / mx
+            self._exchange(cur, S, Rv, cs, "Rv")
+            if k == 0:                                                        # exact scale of iteration 0: max pre-pass
+                self._fourier(Rv, S, Tx, state, partial, None)
+                self._close(partial, mine, gathered, norm, hw, True, tolerance, state, curve)
             last = k == max_loops - 1
-            self._fourier(Rv, S, Tx, s_prev, partial, inten if (want_expected and (last or tolerance > 0)) else None)
-            mx, (a, b, c) = self._partial_totals(partial)
-            s = norm / mx                                                     # algorithms.py:37
-            s0u = float(self.real_dtype(s_prev))                              # the scale the kernel used
-            dl = s / s0u - 1.0 if s0u != 0.0 else 0.0
-            err = (a + 2.0 * dl * b + dl * dl * c) / hw                       # algorithms.py:38,162
-            errors.append(np.float64(err))
-            s_prev = s
-            self._exchange_back(S, Rv, cur, cs)                               # D with the columns inverse-transformed
-            src, field = cur, 0
-            if not (err > tolerance):
+            self._fourier(Rv, S, Tx, state, partial, inten if (want_expected and (last or check_every or k == 0)) else None)
+            self._close(partial, mine, gathered, norm, hw, False, tolerance, state, curve)
+            self._exchange_back(S, Rv, cur, cs, "X" if cur is X else "Y")     # D with the columns inverse-transformed
+            src, field, done_iters = cur, 0, k + 1
+            if check_every or k == 0:                                         # (k == 0: an all-zero target ends the loop at once, algorithms.py:29)
+                st = self.to_host(state)
+                if st[3] != 0.0:
+                    break
+        errors = [np.float64(e) for e in self.to_host(curve)[:done_iters]]
+        for i, e in enumerate(errors):                                        # tolerance <= 0: the loop ran on; cut where the reference stops
+            if not (e > tolerance):
+                errors = errors[:i + 1]
                 break
+        s_last = float(self.to_host(state)[0])
         holo = self._mem_empty(self.shape, np.float64)
         self._check(self._lib.slm_rows_gs_row_pass(self._ctx, self._mem_ptr(src), None, None, 0, 1, self._mem_ptr(holo)))
         expected = None
         if want_expected:
-            recv_i = self._mem_empty((self.world, h, h), np.float64)
             exp_slab = self._mem_empty(self.shape, np.float64)
-            self._all_to_all(inten, recv_i)
-            self._transpose(recv_i, exp_slab, 8, True)
+            if self.world == 1:
+                self._transpose(inten, exp_slab, 8, True)
+            else:
+                recv_i = self._mem_empty(blocks, np.float64)
+                self._all_to_all(inten, recv_i)
+                self._transpose(recv_i, exp_slab, 8, True)
             if on_device:
-                exp_slab *= s_prev                                            # expected_outcome *= norm / max, :37
+                exp_slab *= s_last                                            # expected_outcome *= norm / max, :37
                 expected = exp_slab
             else:
-                expected = self.to_host(exp_slab) * s_prev
+                expected = self.to_host(exp_slab) * s_last
         return (holo if on_device else self.to_host(holo)), expected, errors
 
-    def _setup_field(self, T, X, S, Rv):
+    def _close(self, partial, mine, gathered, norm, hw, prepass, tolerance, state, curve):
+        """this rank's sums -> every rank -> scale / error / loop condition in `state` (all on the device)"""
+        peer = self._peer is not None
+        slot, self._slot = self._slot, self._slot ^ 1
+        self._check(self._lib.slm_rows_reduce(self._ctx, self._mem_ptr(partial), self.rows, self._mem_ptr(mine),
+                                              self._peer_array("gathered", slot * self.world * 32) if peer else None,
+                                              self.world if peer else 0, self.rank))
+        if peer:
+            self._peer_barrier()
+        else:
+            self._all_gather4(mine, gathered[slot])
+        self._check(self._lib.slm_rows_close(self._ctx, self._mem_ptr(gathered[slot]), self.world, float(norm), float(hw), int(prepass),
+                                             float(tolerance), self._mem_ptr(state), self._mem_ptr(curve)))
+
+    def _setup_field(self, T, X, S, Rv, peer_recv=None, peer_slab=None):
         """A = ifft2(amplitude) of the distributed target into the row slab X (this engine's precision)."""
         h, cs = self.rows, np.dtype(self.complex_dtype).itemsize
         self._rows_fft(None, X, True, u8=T)
-        self._exchange(X, S, Rv, cs)
+        self._exchange(X, S, Rv, cs, peer_recv)
         self._rows_fft(Rv, S, True, block_in=h, block_out=h)
-        self._exchange_back(S, Rv, X, cs)
+        self._exchange_back(S, Rv, X, cs, peer_slab)
 
-    def _fourier(self, lines_in, lines_out, Tx, s_prev, partial, inten):
-        self._check(self._lib.slm_rows_gs_fourier_pass(self._ctx, self._mem_ptr(lines_in), self._mem_ptr(lines_out), self.rows,
-                                                       self._mem_ptr(Tx), self._dp(self._amp_lut), float(s_prev),
-                                                       self._mem_ptr(partial), self._mem_ptr(inten)))
+    def _fourier(self, lines_in, lines_out, Tx, state, partial, inten):
+        self._check(self._lib.slm_rows_gs_fourier_pass_dev(self._ctx, self._mem_ptr(lines_in), self._mem_ptr(lines_out), self.rows,
+                                                           self._mem_ptr(Tx), self._dp(self._amp_lut), self._mem_ptr(state),
+                                                           self._mem_ptr(partial), self._mem_ptr(inten)))
+
+    def close(self):
+        self._peer = None
+        super().close()
 
 
 def gerchberg_saxton_slab(target, max_loops: int, tolerance: float = 0.0, precision: str = "fp32", want_expected: bool = True,

@@ -364,6 +364,24 @@ def check_gif_snapshots(make_engine_unused, precision, tmp_path, gs_fn, gd_fn, n
             last = np.array(im.open(d / "2.png"))
             ref = (P.preview_to_L(exp) if gtype == "i" else P.preview_to_L((holo + np.pi) * 256 / (2 * np.pi)))
             assert np.mean(last != ref) < 1e-3
+        # the loop condition holds across the chunk borders of a snapshot run (algorithms.py:29,83): with gif_skip = 1
+        # every chunk is ONE iteration, and the run must still stop where the uninterrupted one does
+        b = ns(max_loops=12, precision=precision, **kw)
+        _, _, errs0 = fn(t, b)
+        tol = float(0.5 * (errs0[4] + errs0[5]))
+        stop = int(np.argmax(~(np.array(errs0) > tol))) + 1
+        assert 1 < stop < 12
+        for skip in (1, 2):
+            d = tmp_path / f"alg{which}_tol{skip}"
+            d.mkdir()
+            a = ns(max_loops=12, tolerance=tol, gif=True, gif_skip=skip, gif_type="i", gif_source_dir=str(d), precision=precision, **kw)
+            _, _, errs = fn(t, a)
+            assert len(errs) == stop
+            assert len(list(d.iterdir())) == (stop - 1) // skip + 1            # frames of iterations 0, skip, 2 skip, ... < stop
+            if which == 1:
+                c_ = ns(max_loops=12, tolerance=tol, precision=precision, **kw)
+                fn(t, c_)
+                assert a.learning_rate == c_.learning_rate
 
 
 def check_single_trap_and_frames(make_engine, golden):

@@ -1,6 +1,8 @@
 """Host-side logic of the drop-in shims against numpy / the oracle / the reference goldens."""
 import random
 
+import os
+
 import numpy as np
 import pytest
 
@@ -103,3 +105,43 @@ def test_snapshot_chunks():
         assert [e for e in ends if e % skip == 0] == [i for i in range(loops) if i % skip == 0]
     with pytest.raises(ZeroDivisionError):
         hl.snapshot_chunks(5, 0)
+
+
+def test_command_lines_match_the_reference_defaults():
+    """generate_hologram.py:222-371 and generate_hologram_sequence.py:43-107: flags, defaults and the attributes the
+    drivers add after parsing."""
+    from spatial_light_modulator_module_b200 import generate_hologram as gh, generate_hologram_sequence as ghs
+    a = gh.build_parser().parse_args([])
+    assert (a.img_name, a.incomming_intensity, a.initial_guess, a.destination_directory) == (None, "uniform", "random", "holograms")
+    assert (a.algorithm, a.tolerance, a.max_loops, a.learning_rate, a.white_attention, a.unsettle) == ("gerchberg_saxton", 0, 42, 0.005, 1, 0)
+    assert (a.gif, a.gif_type, a.gif_skip, a.plot_error, a.preview, a.deflect, a.lens) == (False, "i", 1, False, False, None, None)
+    assert isinstance(a.white_attention, int)            # the int default wraps in uint8 (SURVEY A.2); "-wa 1" gives a float
+    b = gh.build_parser().parse_args(["duck.png", "-alg", "gradient_descent", "-l", "100", "-wa", "1", "-deflect", "1", "2", "-lens", "0.5", "-q", "-i"])
+    assert (b.img_name, b.algorithm, b.max_loops, b.deflect, b.lens, b.quarterize, b.invert) == ("duck.png", "gradient_descent", 100, [1.0, 2.0], 0.5, True, True)
+    assert isinstance(b.white_attention, float)
+    s = ghs.build_parser().parse_args(["seq", "-ct2pi", "256"])
+    assert (s.source_dir, s.version, s.incomming_intensity, s.correspond_to2pi, s.tolerance, s.max_loops, s.preview) == \
+        ("seq", None, "uniform", 256, 0, 5, False)
+    with pytest.raises(SystemExit):
+        ghs.build_parser().parse_args(["seq"])            # -ct2pi is required
+
+
+def test_gif_directories_and_assembly(tmp_path, monkeypatch):
+    """generate_hologram.py:90-99,206-219: where the frames go, and the GIF made of them."""
+    import argparse
+    from PIL import Image as im
+    from spatial_light_modulator_module_b200 import generate_hologram as gh
+    monkeypatch.chdir(tmp_path)
+    a = argparse.Namespace(gif_type="i")
+    gh.add_gif_dirs(a)
+    assert (a.gif_dest_dir, a.gif_source_dir) == ("images", "images/gif_source") and os.path.isdir("images/gif_source")
+    h = argparse.Namespace(gif_type="h")
+    gh.add_gif_dirs(h)
+    assert h.gif_source_dir == "holograms/gif_source"
+    for i in range(3):
+        im.fromarray(np.full((8, 8), 60 * i, dtype=np.uint8)).save(f"{a.gif_source_dir}/{i}.png")
+    gh.create_gif(a.gif_source_dir, "images/out.gif")
+    g = im.open("images/out.gif")
+    assert getattr(g, "n_frames", 1) == 3
+    gh.remove_files_in_dir(a.gif_source_dir)
+    assert os.listdir(a.gif_source_dir) == []
