@@ -56,8 +56,14 @@ def _slab_worker(rank, world, port, n, loops, out_dir):
                             device_id=torch.device("cuda", rank))
     try:
         t = synthetic.noise_target((n, n), seed=6)
-        h, e, errs = slab.gerchberg_saxton_slab(t, loops, precision="fp32")
-        np.savez(os.path.join(out_dir, f"slab{rank}.npz"), h=h, e=e, errs=np.array(errs))
+        for tag, env in (("peer", None), ("coll", "1")):
+            os.environ.pop("SLM_SLAB_NO_PEER", None)
+            if env:
+                os.environ["SLM_SLAB_NO_PEER"] = env
+            eng = slab.SlabEngine(n, world, rank, "fp32")
+            h, e, errs = eng.gs(t[rank * (n // world):(rank + 1) * (n // world)], loops)
+            np.savez(os.path.join(out_dir, f"slab_{tag}{rank}.npz"), h=h, e=e, errs=np.array(errs), status=np.array(eng.peer_status))
+            eng.close()
     finally:
         dist.destroy_process_group()
 
@@ -74,9 +80,51 @@ def test_two_gpu_slab_gs_matches_single_gpu(tmp_path):
     mp.spawn(_slab_worker, args=(2, 29700 + os.getpid() % 200, n, loops, str(tmp_path)), nprocs=2, join=True)
     eng = SlabEngine(n, 1, 0, "fp32")
     h, e, errs = eng.gs(synthetic.noise_target((n, n), seed=6), loops)
-    r0, r1 = np.load(tmp_path / "slab0.npz"), np.load(tmp_path / "slab1.npz")
-    np.testing.assert_array_equal(np.concatenate([r0["h"], r1["h"]]), h)
-    np.testing.assert_allclose(np.concatenate([r0["e"], r1["e"]]), e, rtol=1e-12)
-    np.testing.assert_array_equal(r0["errs"], r1["errs"])
-    assert np.max(np.abs(r0["errs"] - np.array(errs)) / np.array(errs)) < 1e-12
+    statuses = {}
+    for tag in ("peer", "coll"):       # blocks stored straight into the peer's memory / NCCL all-to-all: the same bits
+        r0, r1 = np.load(tmp_path / f"slab_{tag}0.npz"), np.load(tmp_path / f"slab_{tag}1.npz")
+        statuses[tag] = str(r0["status"])
+        np.testing.assert_array_equal(np.concatenate([r0["h"], r1["h"]]), h)
+        np.testing.assert_allclose(np.concatenate([r0["e"], r1["e"]]), e, rtol=1e-12)
+        np.testing.assert_array_equal(r0["errs"], r1["errs"])
+        assert np.max(np.abs(r0["errs"] - np.array(errs)) / np.array(errs)) < 1e-12
+    print("slab exchange:", statuses)
+    assert statuses["coll"].startswith("collectives")
     eng.close()
+
+
+def _frames_worker(rank, world, port, n_frames, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from spatial_light_modulator_module_b200 import generate_hologram_sequence as ghs, synthetic
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        mask = synthetic.random_mask((768, 1024), seed=2)
+        dots = synthetic.movie_frame_dots(n_frames, rescale_parameter=5.0)
+        frames, _, errors, (lo, hi) = ghs.sequence_holograms(None, 6, precision="fp32", batch=3, output="uint8", mask=mask, ct2pi=256,
+                                                             trap_dots=(dots, n_frames, (768, 1024)))
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "frames0.npz"), frames=frames, lo=lo, hi=hi)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_uint8_frames_gathered_device_to_device(tmp_path):
+    """Config 3's output format: device-rasterised trap targets, GS, mask add + quantisation, NCCL gather of the 8-bit
+    frames onto rank 0 -- equal to quantising the single-GPU float64 holograms."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from spatial_light_modulator_module_b200 import display_holograms as dh, generate_hologram_sequence as ghs, synthetic
+    n = 7
+    mp.spawn(_frames_worker, args=(2, 29900 + os.getpid() % 90, n, str(tmp_path)), nprocs=2, join=True)
+    ref_h, _, _, _ = ghs.sequence_holograms(synthetic.movie_frames(n, rescale_parameter=5.0), 6, precision="fp32", batch=4)
+    r0 = np.load(tmp_path / "frames0.npz")
+    assert (int(r0["lo"]), int(r0["hi"])) == (0, n) and r0["frames"].dtype == np.uint8
+    mask = synthetic.random_mask((768, 1024), seed=2)
+    for i in range(n):
+        np.testing.assert_array_equal(r0["frames"][i], dh.hologram_to_grey(ref_h[i], mask, 256))
