@@ -457,14 +457,17 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
                 const int s = (int)(k % NBUF);
                 const unsigned par = (k / NBUF) & 1u;
                 unsigned char* const buf = tile_buf(s);
+                SLM_STAMP(t == 0, k, 0);
                 mbar_wait(bar(full, s), par);
                 const TileDesc d = desc[s];
                 if (d.g < 0) break;
+                SLM_STAMP(t == 0, k, 1);
                 const int b = (int)(d.g / tiles);
 #pragma unroll
                 for (int p = 0; p < RA; ++p) v[p] = *reinterpret_cast<const cpx<R>*>(buf + my + 2048u * p);
                 sync_named(pair_bar, 64);                    // the partner holds its column too: the pair's chunk is free
                 warp_fft_forward<RA>(v, buf, lm, sm, w1);
+                SLM_STAMP(t == 0, k, 2);
                 R m = 0;
 #pragma unroll
                 for (int r = 0; r < 32; ++r) m = fmax(m, cnorm2(v[r]));
@@ -487,6 +490,7 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
                     atomic_add_u32(a.fused_count + b, 1u);
                 }
                 mbar_arrive(bar(fwd, s));                    // (after the atomics: whoever passes fwd finds this tile counted)
+                SLM_STAMP(t == 0, k, 3);
             }
             return;
         }
@@ -498,7 +502,9 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
             const TileDesc d = desc[s];
             if (d.g < 0) break;
             const int b = (int)(d.g / tiles), tile = (int)(d.g % tiles);
+            SLM_STAMP(t == G::GROUP_THREADS, k, 4);
             mbar_wait(bar(fwd, s), par);
+            SLM_STAMP(t == G::GROUP_THREADS, k, 5);
 #pragma unroll
             for (int q = 0; q < 32; ++q) v[q] = *reinterpret_cast<const cpx<R>*>(buf + my + 64u * RA * q);
             if (c == 0 && lane == 0) {
@@ -512,6 +518,7 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
                 fmx[s * (TC + 2) + TC] = __uint_as_float(ld_cg(a.fused_max + b));
             }
             sync_named(10, G::GROUP_THREADS);
+            SLM_STAMP(t == G::GROUP_THREADS, k, 6);
             const R gdk = (R)(d.norm / (double)fmx[s * (TC + 2) + TC]);
             sync_named(pair_bar, 64);                        // the partner holds its column too: the pair's chunk is free
             R sa = 0;
@@ -547,12 +554,15 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
             Partial p; p.mx = 0; p.a = (double)sa; p.b = 0; p.c = 0;
             p = warp_reduce<FIELDS>(p);
             if (lane == 0) red[s * TC + c] = p;              // (the sequencer reissued this slot only after its sums were taken)
+            SLM_STAMP(t == G::GROUP_THREADS, k, 7);
             warp_fft_inverse<RA>(v, buf, lm, sm, w1, active);
+            SLM_STAMP(t == G::GROUP_THREADS, k, 8);
             sync_named(pair_bar, 64);                        // the partner is through its exchange: its rows of my column are free
 #pragma unroll
             for (int p2 = 0; p2 < RA; ++p2) *reinterpret_cast<cpx<R>*>(buf + my + 2048u * side_a_index<RA>(p2)) = v[p2];
             fence_async_smem();
             mbar_arrive(bar(done, s));
+            SLM_STAMP(t == G::GROUP_THREADS, k, 9);
         }
         return;
     }

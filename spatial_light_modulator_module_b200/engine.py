@@ -85,24 +85,40 @@ class Engine:
             return torch.empty(tuple(shape), dtype=tdt, device=self._dev)
 
     def _mem_upload(self, array: np.ndarray):
+        """Host array -> device tensor.  Large arrays travel on a copy stream of their own and the engine's stream waits
+        for them by an event, so an upload neither waits for kernels already queued nor holds them up (the movie driver
+        sends batch k+1 while batch k iterates)."""
         torch = self._torch
         array = np.ascontiguousarray(array)
         host = torch.from_numpy(array)
         nbytes = host.numel() * host.element_size()
-        with torch.cuda.stream(self._stream):
-            if nbytes >= (1 << 20) and _dma_ready(torch, host, array):
+        if not ((1 << 20) <= nbytes <= (1 << 30)):
+            with torch.cuda.stream(self._stream):
+                return host.to(self._dev, non_blocking=False)
+        if getattr(self, "_upload_stream", None) is None:
+            self._upload_stream = torch.cuda.Stream(self._dev)
+        side = self._upload_stream
+        with torch.cuda.stream(side):
+            locked = _dma_ready(torch, host, array)
+            if locked:
                 # page-locked already (a result of to_host(), or a caller's array seen before, e.g. the one
                 # wavefront-correction mask every frame is added to): DMA straight from it, no staging copy
-                dev = host.to(self._dev, non_blocking=True)
-                self._stream.synchronize()
-                return dev
-            if (1 << 20) <= nbytes <= (1 << 30):                     # large planes: stage through pinned memory
-                pinned = torch.empty(host.shape, dtype=host.dtype, pin_memory=True)
-                pinned.copy_(host)
-                dev = pinned.to(self._dev, non_blocking=True)
-                self._stream.synchronize()                             # the pinned staging buffer is released below
-                return dev
-            return host.to(self._dev, non_blocking=False)
+                src = host
+            else:
+                src = torch.empty(host.shape, dtype=host.dtype, pin_memory=True)      # staging (pooled by torch, reused once its copy is done)
+                src.copy_(host)
+            dev = src.to(self._dev, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(side)
+        self._stream.wait_event(done)
+        dev.record_stream(self._stream)
+        if locked:
+            done.synchronize()            # the caller may change its array as soon as we return: wait for THIS copy (not for the kernels)
+        return dev
+
+    def upload(self, array):
+        """Start sending a host array to the device (see :meth:`_mem_upload`); the result can be handed to gs / gd."""
+        return self._mem_upload(np.asarray(array))
 
     def _mem_plane_max(self, dev) -> np.ndarray:
         """max over each plane of a uint8 device stack [B,H,W] -> float64 [B] on the host."""

@@ -98,8 +98,12 @@ def sequence_holograms(frames, max_loops: int, tolerance: float = 0.0, precision
         return eng.quantize(res.hologram, mask, ct2pi, _ffi.QUANT_FLOOR)
 
     def targets_of(s, e):
+        """this rank's frames [s, e) on the device (host frames: the copy is started here and not waited for)"""
+        if e <= s:
+            return None
         if frames is not None:
-            return frames[lo + s:lo + e]
+            block = frames[lo + s:lo + e]
+            return block if hasattr(block, "data_ptr") else eng.upload(block)
         sel = dots[(dots[:, 0] >= lo + s) & (dots[:, 0] < lo + e)].copy()
         sel[:, 0] -= lo + s
         return eng.trap_frames(sel, e - s, shape)
@@ -119,11 +123,13 @@ def sequence_holograms(frames, max_loops: int, tolerance: float = 0.0, precision
         n_local = n_max = 0                              # nothing left for the batched loop below
     # the read-back (and the gather) of one batch runs beside the iterations of the next one
     pending: list = []
+    ahead = targets_of(0, min(batch, n_local))
     for s in range(0, n_max, batch):
         e = min(s + batch, n_local)
-        res = None
+        res, cur = None, ahead
+        ahead = targets_of(s + batch, min(s + 2 * batch, n_local))        # the next batch's frames travel beside this batch's iterations
         if e > s:
-            res = eng.gs(targets_of(s, e), max_loops, tolerance, inc_amp=inc_amp, want_expected=want_expected, norms=None)
+            res = eng.gs(cur, max_loops, tolerance, inc_amp=inc_amp, want_expected=want_expected, norms=None)
             errors.extend(res.errors)
         for jobs, a, b in pending:
             writer.put(jobs, a, b, holos[a - base:b - base], exps[a - base:b - base] if want_expected else None)

@@ -6,6 +6,8 @@ import sys
 
 import numpy as np
 import pytest
+
+from tests.conftest import free_port
 import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -38,7 +40,7 @@ def _worker(rank, world, port, n_frames, out_dir):
 @pytest.mark.parametrize("n_frames", [5, 4])
 def test_two_rank_movie_matches_single_process(tmp_path, n_frames):
     from spatial_light_modulator_module_b200 import generate_hologram_sequence as ghs
-    port = 29500 + (os.getpid() % 2000) + n_frames
+    port = free_port()
     mp.spawn(_worker, args=(2, port, n_frames, str(tmp_path)), nprocs=2, join=True)
     ref_h, ref_e, ref_err, (lo, hi) = ghs.sequence_holograms(_frames(n_frames), 5, precision="fp64", batch=3,
                                                             want_expected=True, engine_factory=_factory)
@@ -81,7 +83,7 @@ def test_two_rank_uint8_frames_from_device_rasterised_targets(tmp_path):
     from oracle import numpy_port as P
     from spatial_light_modulator_module_b200 import generate_hologram_sequence as ghs, synthetic
     n_frames, shape = 5, (64, 128)
-    port = 31500 + (os.getpid() % 2000)
+    port = free_port()
     mp.spawn(_worker_frames, args=(2, port, n_frames, str(tmp_path)), nprocs=2, join=True)
     holos, _, _, _ = ghs.sequence_holograms(_frames(n_frames), 4, precision="fp64", batch=3, engine_factory=_factory)
     mask = synthetic.random_mask(shape, seed=4)

@@ -7,6 +7,8 @@ import sys
 import numpy as np
 import pytest
 
+from tests.conftest import free_port
+
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -36,7 +38,7 @@ def test_two_gpu_movie_matches_single_gpu(tmp_path):
     import torch.multiprocessing as mp
     from spatial_light_modulator_module_b200 import generate_hologram_sequence as ghs, synthetic
     n = 7
-    mp.spawn(_worker, args=(2, 29650 + os.getpid() % 300, n, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, free_port(), n, str(tmp_path)), nprocs=2, join=True)
     ref_h, ref_e, ref_err, _ = ghs.sequence_holograms(synthetic.movie_frames(n, rescale_parameter=5.0), 6, precision="fp32",
                                                       batch=4, want_expected=True)
     r0 = np.load(tmp_path / "rank0.npz")
@@ -77,7 +79,7 @@ def test_two_gpu_slab_gs_matches_single_gpu(tmp_path):
     from spatial_light_modulator_module_b200 import synthetic
     from spatial_light_modulator_module_b200.slab import SlabEngine
     n, loops = 2048, 5
-    mp.spawn(_slab_worker, args=(2, 29700 + os.getpid() % 200, n, loops, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_slab_worker, args=(2, free_port(), n, loops, str(tmp_path)), nprocs=2, join=True)
     eng = SlabEngine(n, 1, 0, "fp32")
     h, e, errs = eng.gs(synthetic.noise_target((n, n), seed=6), loops)
     statuses = {}
@@ -121,7 +123,7 @@ def test_two_gpu_uint8_frames_gathered_device_to_device(tmp_path):
     import torch.multiprocessing as mp
     from spatial_light_modulator_module_b200 import display_holograms as dh, generate_hologram_sequence as ghs, synthetic
     n = 7
-    mp.spawn(_frames_worker, args=(2, 29900 + os.getpid() % 90, n, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_frames_worker, args=(2, free_port(), n, str(tmp_path)), nprocs=2, join=True)
     ref_h, _, _, _ = ghs.sequence_holograms(synthetic.movie_frames(n, rescale_parameter=5.0), 6, precision="fp32", batch=4)
     r0 = np.load(tmp_path / "frames0.npz")
     assert (int(r0["lo"]), int(r0["hi"])) == (0, n) and r0["frames"].dtype == np.uint8

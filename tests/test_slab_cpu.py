@@ -6,6 +6,8 @@ import sys
 
 import numpy as np
 import pytest
+
+from tests.conftest import free_port
 import torch.multiprocessing as mp
 from scipy.fft import fft, ifft
 
@@ -93,7 +95,7 @@ def test_two_rank_slab_gs_matches_single_rank(tmp_path):
     from spatial_light_modulator_module_b200 import synthetic
     from tests.emu.emu_engine import EmuSlabEngine
     n, loops = 256, 4
-    mp.spawn(_worker, args=(2, 29800 + os.getpid() % 150, n, loops, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, free_port(), n, loops, str(tmp_path)), nprocs=2, join=True)
     t = synthetic.noise_target((n, n), seed=6)
     eng = EmuSlabEngine(n, 1, 0, "fp32")
     h, e, errs = eng.gs(t, loops)
