@@ -292,6 +292,64 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
         if (!HAS_STATS) return;
         const int lane = t - G::COMPUTE - 96;
         const double hw = (double)H * (double)a.W;
+        if constexpr (PIPE) {
+            // Two duties, polled in turn so neither holds the other up: (i) a tile that group 0 has transformed hands its
+            // max |F|^2 to its plane (atomic max, then the plane's arrival count) -- kept off the compute warps' path, an
+            // atomic's round trip is longer than a quarter of a tile's transform; (ii) the sums of a finished tile, as in
+            // the other modes.
+            float* const fmx = reinterpret_cast<float*>(raw + G::OFF_FMX);
+            unsigned kf = 0, kd = 0;
+            bool fend = false;
+            for (;;) {
+                bool moved = false;
+                if (!fend) {
+                    const int s = (int)(kf % NBUF);
+                    const unsigned par = (kf / NBUF) & 1u;
+                    if (mbar_test(bar(full, s), par)) {
+                        const long long g = desc[s].g;
+                        if (g < 0) fend = true;
+                        else if (mbar_test(bar(fwd, s), par)) {
+                            if (lane == 0) {
+                                const int b = (int)(g / tiles);
+                                float mm = fmx[s * (TC + 2)];
+#pragma unroll
+                                for (int i = 1; i < TC; ++i) mm = fmax(mm, fmx[s * (TC + 2) + i]);
+                                atomic_max_u32(a.fused_max + b, __float_as_uint(mm));       // |F|^2 >= 0: ordered like its bit pattern
+                                fence_device();
+                                atomic_add_u32(a.fused_count + b, 1u);
+                            }
+                            ++kf; moved = true;
+                        }
+                    }
+                }
+                const int s = (int)(kd % NBUF);
+                const unsigned par = (kd / NBUF) & 1u;
+                if ((kd < kf || fend) && mbar_test(bar(full, s), par)) {
+                    const TileDesc d = desc[s];
+                    if (d.g < 0) break;
+                    if (mbar_test(bar(done, s), par)) {
+                        const int b = (int)(d.g / tiles), tile = (int)(d.g % tiles);
+                        Partial q; q.mx = 0; q.a = 0; q.b = 0; q.c = 0;
+                        if (lane < TC) q = red[s * TC + lane];
+                        q = warp_reduce<FIELDS>(q);
+                        if (lane == 0) mbar_arrive(bar(taken, s));
+                        Partial* plane_partials = a.partial + (size_t)b * tiles;
+                        if (ga.defer_close) {
+                            if (lane == 0) plane_partials[tile] = q;
+                        } else {
+                            unsigned ticket = 0;
+                            if (lane == 0) ticket = publish_partial(q, plane_partials, tile, tiles, a.counter + b);
+                            Partial tot;
+                            if (collect_if_last<FIELDS>(ticket, lane, plane_partials, tiles, tot) && lane == 0)
+                                close_plane<R, H, MODE>(a, b, tot, d.scale, d.norm);
+                        }
+                        ++kd; moved = true;
+                    }
+                }
+                if (!moved) spin_pause();
+            }
+            return;
+        }
         for (unsigned k = 0;; ++k) {
             const int s = (int)(k % NBUF);
             const unsigned par = (k / NBUF) & 1u;
@@ -446,8 +504,9 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
     cpx<R> v[32];
     if constexpr (PIPE) {
         // ================= CGM_GD_PIPE: the two groups share every tile =================
-        // group 0: tile -> med_output = fft2(...) columns (algorithms.py:84), left in the buffer in side-B order; the tile's
-        //          max |F|^2 joins its plane's (atomic max), the plane's arrival count goes up -- and on to the next tile;
+        // group 0: tile -> med_output = fft2(...) columns (algorithms.py:84), left in the buffer in side-B order, its eight
+        //          column maxima beside it (the publisher warp adds them to the plane's max and arrival count) -- and on
+        //          to the next tile;
         // group 1: once every tile of the plane has arrived (they are in flight on the other SMs, at most NBUF items
         //          away), output = |F|^2 * norm / max, the error sum, mask * F * (output - T) and the inverse transform
         //          (algorithms.py:85-88,92).  Same arithmetic, same bits as the two-pass and the fused forms.
@@ -462,7 +521,6 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
                 const TileDesc d = desc[s];
                 if (d.g < 0) break;
                 SLM_STAMP(t == 0, k, 1);
-                const int b = (int)(d.g / tiles);
 #pragma unroll
                 for (int p = 0; p < RA; ++p) v[p] = *reinterpret_cast<const cpx<R>*>(buf + my + 2048u * p);
                 sync_named(pair_bar, 64);                    // the partner holds its column too: the pair's chunk is free
@@ -480,16 +538,7 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
 #pragma unroll
                     for (int q = 0; q < 32; ++q) *reinterpret_cast<cpx<R>*>(buf + my + 64u * RA * q) = v[q];
                 }
-                sync_named(9, G::GROUP_THREADS);             // the eight column maxima are in shared memory
-                if (c == 0 && lane == 0) {
-                    float mm = fmx[s * (TC + 2)];
-#pragma unroll
-                    for (int i = 1; i < TC; ++i) mm = fmax(mm, fmx[s * (TC + 2) + i]);
-                    atomic_max_u32(a.fused_max + b, __float_as_uint(mm));       // |F|^2 >= 0: ordered like its bit pattern
-                    fence_device();
-                    atomic_add_u32(a.fused_count + b, 1u);
-                }
-                mbar_arrive(bar(fwd, s));                    // (after the atomics: whoever passes fwd finds this tile counted)
+                mbar_arrive(bar(fwd, s));                    // the publisher warp takes the eight column maxima to the plane's
                 SLM_STAMP(t == 0, k, 3);
             }
             return;

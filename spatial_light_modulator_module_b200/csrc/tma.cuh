@@ -34,6 +34,7 @@ inline void mbar_fence_init() {}
 inline void mbar_check(TileBarrier* b) { if (b->pending == 0 && b->tx == 0) { b->phase ^= 1u; b->pending = b->init; } }
 inline void mbar_arrive(TileBarrier* b) { emu::S().progress++; b->pending--; mbar_check(b); }
 inline void mbar_wait(TileBarrier* b, unsigned parity) { while ((b->phase & 1u) == (parity & 1u)) emu::yield(); }
+inline bool mbar_test(TileBarrier* b, unsigned parity) { return (b->phase & 1u) != (parity & 1u); }
 inline unsigned emu_swz(int row_bytes, unsigned off) {
     return row_bytes == 64 ? tile_swizzle<64>(off) : row_bytes == 32 ? tile_swizzle<32>(off) : off;
 }
@@ -90,6 +91,17 @@ SLM_DEV void mbar_wait(TileBarrier* b, unsigned parity) {
         "}\n" ::"r"(smem_addr(b)),
         "r"(parity & 1u)
         : "memory");
+}
+// has the phase with parity `parity` completed?  (no waiting)
+SLM_DEV bool mbar_test(TileBarrier* b, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n" : "=r"(ok) : "r"(smem_addr(b)), "r"(parity & 1u) : "memory");
+    return ok != 0;
 }
 // One thread: arm `bar` with the tile's byte count (this is also its arrival) and issue one bulk
 // tensor copy per box of rows.  col_byte0 / row_bytes in bytes; the map's elements are 4- or 8-byte reals.
