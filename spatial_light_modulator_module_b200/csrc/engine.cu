@@ -223,7 +223,11 @@ static int launch_group(slm_ctx* c, int mode, int batch, const ColArgs* loop, co
     ga.c.B = batch; ga.c.W = c->W; ga.c.stats = c->stats; ga.c.partial = c->partial; ga.c.counter = c->counter;
     ga.c.norm = c->norm; ga.c.tw = c->tw_col;
     ga.c.fused_max = c->fused; ga.c.fused_count = c->fused + c->max_batch; ga.c.max_planes = c->max_batch;
-    const int ctas = mode == CGM_GD_FUSED ? c->fused_ctas : c->persist_ctas;
+    int ctas = mode == CGM_GD_FUSED ? c->fused_ctas : c->persist_ctas;
+    if (mode == CGM_GD_PIPE) {
+        static const char* pc = getenv("SLM_PIPE_CTAS");         // developer switch (A/B measurements)
+        if (pc && atoi(pc) > 0 && atoi(pc) <= c->persist_ctas) ctas = atoi(pc);
+    }
     const int kind = (mode == CGM_STATS || mode == CGM_STATS_KEEP) ? K_COL_STATS : (mode == CGM_COMPLEX ? K_COL_PLAIN : K_COL_PASS);
     SLM_TIMED(kind, c->col->col_group(mode, ga, &c->map_x, map_out ? map_out : &c->map_x, ctas, c->stream));
     if (ga.defer_close) c->launches++;               // the closing kernel behind the pass
