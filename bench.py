@@ -269,11 +269,11 @@ class Harness:
 
     def wall_steps(self, step, warmup, steps):
         """Host-clock timing for end-to-end calls (host buffers in and out): seconds per step, max over ranks."""
+        out = None
         for _ in range(warmup):
-            step()
+            out = step()                 # (kept alive like a timed step's result: see time_steps)
         self.barrier()
         t0 = time.perf_counter()
-        out = None
         for _ in range(steps):
             out = step()
         self.torch.cuda.synchronize()

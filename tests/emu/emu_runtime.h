@@ -257,8 +257,9 @@ inline void fence_device() {}
 inline void fence_block() {}
 inline unsigned atomic_add_shared(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 inline unsigned atomic_inc_wrap(unsigned* p, unsigned limit) { unsigned o = *p; *p = (o >= limit) ? 0 : o + 1; return o; }
-inline unsigned atomic_max_u32(unsigned* p, unsigned v) { unsigned o = *p; if (v > o) *p = v; return o; }
-inline unsigned atomic_add_u32(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
+// (global atomics change what OTHER CTAs see: they count as progress for the cooperative grid's dead-lock detection)
+inline unsigned atomic_max_u32(unsigned* p, unsigned v) { emu::S().progress++; unsigned o = *p; if (v > o) *p = v; return o; }
+inline unsigned atomic_add_u32(unsigned* p, unsigned v) { emu::S().progress++; unsigned o = *p; *p = o + v; return o; }
 inline unsigned ld_acquire(const unsigned* p) { return *p; }
 inline long long clock_now() { return 0; }
 inline void spin_pause() { emu::yield(); }          // a wait on another CTA's progress: let the other fibres / CTAs run
