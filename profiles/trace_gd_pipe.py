@@ -39,3 +39,12 @@ for (a, b), nm in names.items():
 for ev, nm in ((0, "group 0"), (4, "group 1")):
     per = (tr[:, 1:, ev] - tr[:, :-1, ev])[valid[:, 1:] & valid[:, :-1]]
     print(f"  {nm}: tile period median {np.median(per) / 1e3:6.2f} us")
+
+# one CTA's timeline, a few consecutive tiles (us from the kernel's start)
+t0 = tr[:, 0, 0].min()
+for cta in (5, 140):
+    print(f"CTA {cta}: tile | g0: ask  got  fwd-done arrive | g1: ask  fwd  ready  grad  inv  done | seq: done-seen taken store-read(slot free)")
+    for k in range(8, 16):
+        r = (tr[cta, k] - t0) / 1e3
+        print(f"   {k:3d} | " + " ".join(f"{r[i]:7.2f}" for i in (0, 1, 2, 3)) + " | " + " ".join(f"{r[i]:7.2f}" for i in (4, 5, 6, 7, 8, 9)) +
+              " | " + " ".join(f"{r[i]:7.2f}" for i in (10, 11, 12)))

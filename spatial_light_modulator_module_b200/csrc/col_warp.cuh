@@ -492,6 +492,7 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
             const int s = (int)(kd % NBUF);
             const unsigned par = (kd / NBUF) & 1u;
             mbar_wait(bar(done, s), par);
+            SLM_STAMP(lane == 0, kd, 10);
             if (HAS_OUT && lane == 0) {
                 const TileDesc d = desc[s];
                 const int b = (int)(d.g / tiles), tile = (int)(d.g % tiles);
@@ -502,7 +503,9 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
                 const Peek ahead = peek(cur.g < 0 ? total : cur.g + gridDim.x);   // in flight during the staging below
                 stage_grey(s, cur);                                       // the group is through this slot's grey rows
                 if (HAS_STATS) mbar_wait(bar(taken, s), par);            // the publisher has this slot's descriptor and sums
+                SLM_STAMP(lane == 0, kd, 11);
                 if (lane == 0) tile_store_wait_read();                   // the store has drained the buffer
+                SLM_STAMP(lane == 0, kd, 12);
                 sync_warp();
                 post(s, cur);
                 ++k;
