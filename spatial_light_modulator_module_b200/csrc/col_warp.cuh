@@ -44,7 +44,7 @@ template <typename R, int H> struct ColWarpGeom {
     static constexpr size_t OFF_ORDER = OFF_DESC + NBUF * 32;     // [NBUF] staging orders of the sequencer to its helpers
     static constexpr size_t OFF_FMX = OFF_ORDER + NBUF * 8;       // CGM_GD_FUSED: [NBUF][TC] column maxima, [NBUF] plane max
     static constexpr size_t OFF_BAR = OFF_FMX + NBUF * (TC + 2) * 4;
-    static constexpr size_t SMEM = OFF_BAR + 6 * NBUF * 32;
+    static constexpr size_t SMEM = OFF_BAR + 5 * NBUF * 32;
     static_assert(!OK || SMEM <= 232448, "shared memory budget");
 };
 
@@ -258,7 +258,6 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
     TileBarrier* const taken = reinterpret_cast<TileBarrier*>(raw + G::OFF_BAR + 2 * NBUF * 32); // [NBUF] publisher has the tile's sums
     TileBarrier* const ordered = reinterpret_cast<TileBarrier*>(raw + G::OFF_BAR + 3 * NBUF * 32); // [NBUF] a staging order is posted
     TileBarrier* const fwd = reinterpret_cast<TileBarrier*>(raw + G::OFF_BAR + 4 * NBUF * 32);     // [NBUF] PIPE: the slot holds the transformed field
-    TileBarrier* const ready = reinterpret_cast<TileBarrier*>(raw + G::OFF_BAR + 5 * NBUF * 32);   // [NBUF] PIPE: the plane's max is known (in fmx)
     auto tile_buf = [&](int s) { return raw + (size_t)s * G::TILE; };
     auto grey_buf = [&](int s) { return raw + G::OFF_GREY + (size_t)s * G::GREY; };
     auto bar = [](TileBarrier* base, int s) { return reinterpret_cast<TileBarrier*>(reinterpret_cast<unsigned char*>(base) + s * 32); };
@@ -275,7 +274,6 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
             mbar_init(bar(taken, s), 1u);
             mbar_init(bar(ordered, s), 1u);
             mbar_init(bar(fwd, s), (unsigned)G::GROUP_THREADS);
-            mbar_init(bar(ready, s), 1u);
         }
         mbar_fence_init();
     }
@@ -295,18 +293,17 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
         const int lane = t - G::COMPUTE - 96;
         const double hw = (double)H * (double)a.W;
         if constexpr (PIPE) {
-            // Three duties, polled in turn so none holds the others up:  (i) a tile that group 0 has transformed hands its
-            // max |F|^2 to its plane (atomic max, then the plane's arrival count);  (ii) once every tile of that plane has
-            // arrived (they are in flight on the other SMs) the plane's max goes into shared memory and group 1 is told --
-            // all of this kept off the compute warps' path: a round trip to L2 is a quarter of a tile's transform;
-            // (iii) the sums of a finished tile, as in the other modes.
+            // Two duties, polled in turn so neither holds the other up: (i) a tile that group 0 has transformed hands its
+            // max |F|^2 to its plane (atomic max, then the plane's arrival count) -- kept off the compute warps' path: a
+            // round trip to L2 is a quarter of a tile's transform; (ii) the sums of a finished tile, as in the other modes.
+            // (Watching the planes' arrival counts here as well, to spare group 1 its polling, made both duties late:
+            //  measured 0.251 instead of 0.238 ms per pass.)
             float* const fmx = reinterpret_cast<float*>(raw + G::OFF_FMX);
-            unsigned kf = 0, kr = 0, kd = 0;     // next tile to hand its max over / to declare ready / to publish
+            unsigned kf = 0, kd = 0;             // next tile to hand its max over / to publish
             bool fend = false;                   // group 0 has reached the stop marker
-            long long t_idle = clock_now();
             for (;;) {
-                // lane 0 looks at the barriers and the plane's arrival count; every lane acts on what IT saw
-                enum { EV_FSTOP = 1, EV_FWD = 2, EV_READY = 4, EV_DSTOP = 8, EV_DONE = 16, EV_GIVE_UP = 32 };
+                // lane 0 looks at the barriers; every lane acts on what IT saw
+                enum { EV_FSTOP = 1, EV_FWD = 2, EV_DSTOP = 8, EV_DONE = 16 };
                 unsigned ev = 0;
                 if (lane == 0) {
                     if (!fend) {
@@ -316,13 +313,6 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
                             if (desc[s].g < 0) ev |= EV_FSTOP;
                             else if (mbar_test(bar(fwd, s), par)) ev |= EV_FWD;
                         }
-                    }
-                    if (kr < kf) {
-                        const int b = (int)(desc[kr % NBUF].g / tiles);
-                        // (should the launch's CTAs ever not be resident together -- it is a cooperative launch -- give up
-                        //  after ~2 s with the error flag set instead of hanging the device)
-                        if (ld_acquire(a.fused_count + b) >= (unsigned)tiles) ev |= EV_READY;
-                        else if (clock_now() - t_idle > (1ll << 32)) ev |= EV_READY | EV_GIVE_UP;
                     }
                     if (kd < kf || fend) {
                         const int s = (int)(kd % NBUF);
@@ -348,16 +338,6 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
                     }
                     ++kf;
                 }
-                if (ev & EV_READY) {
-                    const int s = (int)(kr % NBUF);
-                    if (lane == 0) {
-                        const int b = (int)(desc[s].g / tiles);
-                        if (ev & EV_GIVE_UP) atomic_max_u32(a.fused_count + (size_t)a.max_planes, 1u);
-                        fmx[s * (TC + 2) + TC] = __uint_as_float(ld_cg(a.fused_max + b));
-                        mbar_arrive(bar(ready, s));
-                    }
-                    ++kr;
-                }
                 if (ev & EV_DSTOP) break;
                 if (ev & EV_DONE) {
                     const int s = (int)(kd % NBUF);
@@ -379,7 +359,7 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
                     }
                     ++kd;
                 }
-                if (ev & (EV_FWD | EV_READY | EV_DONE | EV_FSTOP)) t_idle = clock_now(); else spin_pause();
+                if (!(ev & (EV_FWD | EV_DONE | EV_FSTOP))) spin_pause();
             }
             return;
         }
@@ -592,7 +572,17 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
             SLM_STAMP(t == G::GROUP_THREADS, k, 5);
 #pragma unroll
             for (int q = 0; q < 32; ++q) v[q] = *reinterpret_cast<const cpx<R>*>(buf + my + 64u * RA * q);
-            mbar_wait(bar(ready, s), par);                   // the publisher warp has seen every tile of the plane arrive
+            if (c == 0 && lane == 0) {
+                // the plane's other tiles: counted already, or being transformed on other SMs right now (cooperative
+                // launch: every CTA is resident).  The time-out only guards against a broken launch.
+                const long long t0 = clock_now();
+                while (ld_acquire(a.fused_count + b) < (unsigned)tiles) {
+                    spin_pause();
+                    if (clock_now() - t0 > (1ll << 32)) { atomic_max_u32(a.fused_count + (size_t)a.max_planes, 1u); break; }
+                }
+                fmx[s * (TC + 2) + TC] = __uint_as_float(ld_cg(a.fused_max + b));
+            }
+            sync_named(10, G::GROUP_THREADS);
             SLM_STAMP(t == G::GROUP_THREADS, k, 6);
             const R gdk = (R)(d.norm / (double)fmx[s * (TC + 2) + TC]);
             sync_named(pair_bar, 64);                        // the partner holds its column too: the pair's chunk is free

@@ -350,6 +350,45 @@ def test_sequence_driver_files(tmp_path, monkeypatch):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_sequence_warm_start(precision):
+    """SURVEY 8 f-4, opt-in: frame n starts from frame n-1's hologram.  Equals the hand-made chain of single GS runs, and
+    on a slowly moving trap pattern the warm-started frames begin from a far smaller error than cold ones."""
+    from spatial_light_modulator_module_b200 import generate_hologram_sequence as ghs
+    frames = synthetic.movie_frames(4, rescale_parameter=0.2)
+    holos, _, errors, _ = ghs.sequence_holograms(frames, 6, precision=precision, warm_start=True, gather=False)
+    eng = make_engine(frames.shape[1:], precision, 1)
+    phasor = None
+    for i in range(4):
+        r = eng.gs(frames[i], 6, phasor0=phasor)
+        np.testing.assert_array_equal(holos[i], eng.to_host(r.hologram)[0])
+        np.testing.assert_array_equal(errors[i], r.errors[0])
+        phasor = eng.phase_phasor(r.hologram)
+    _, _, cold_errors, _ = ghs.sequence_holograms(frames, 6, precision=precision)
+    assert errors[3][0] < 0.5 * cold_errors[3][0]
+    eng.close()
+
+
+def test_sequence_uint8_frames_and_writer_callback():
+    """8-bit SLM frames (mask add + floor quantisation) straight from the movie driver, device-rasterised
+    trap targets, batches handed to a writer callback while later ones iterate -- equal to quantising the float64
+    holograms of the host-frame path."""
+    from spatial_light_modulator_module_b200 import display_holograms as dh, generate_hologram_sequence as ghs
+    n, shape = 9, (768, 1024)
+    mask = synthetic.random_mask(shape, seed=3)
+    seen = []
+    frames8, _, errs8, _ = ghs.sequence_holograms(None, 5, precision="fp32", batch=4, output="uint8", mask=mask, ct2pi=200,
+                                                  trap_dots=(synthetic.movie_frame_dots(n, rescale_parameter=7.0), n, shape),
+                                                  on_batch=lambda a, b, h, e: seen.append((a, b, h.copy())))
+    holos, _, errs, _ = ghs.sequence_holograms(synthetic.movie_frames(n, rescale_parameter=7.0), 5, precision="fp32", batch=4)
+    assert frames8.dtype == np.uint8 and [(a, b) for a, b, _ in seen] == [(0, 4), (4, 8), (8, 9)]
+    for i in range(n):
+        np.testing.assert_array_equal(frames8[i], dh.hologram_to_grey(holos[i], mask, 200))
+        np.testing.assert_array_equal(errs8[i], errs[i])
+    for a, b, h in seen:
+        np.testing.assert_array_equal(h, frames8[a:b])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
 def test_random_phasor_guess(golden, precision):
     pc.check_random_phasor_guess(make_engine, golden, precision)
 
