@@ -137,7 +137,11 @@ int slm_rows_gs_fourier_pass(slm_ctx* ctx, const void* in, void* out, int block_
 /* The same with the previous iteration's scale read from device memory (loop state kept on the device: no host
  * round trip per iteration; see slm_rows_close). */
 int slm_rows_gs_fourier_pass_dev(slm_ctx* ctx, const void* in, void* out, int block_w, const uint8_t* target_u8,
-                                 const double* amp_lut, const double* scale_prev_dev, double* partial, double* intensity);
+                                 const double* amp_lut, const double* scale_prev_dev, double* partial, double* intensity,
+                                 int line0, int nlines /* 0: all lines; else a part, so the way back of finished lines can start */);
+/* slm_rows_gs_row_pass (not the final pass, uniform illumination) on rows [row0, row0 + nrows) of the slab only: the
+ * transposing stores of finished rows (slm_transpose_blocks_peer with a part) run beside the pass over the next rows. */
+int slm_rows_gs_row_pass_part(slm_ctx* ctx, const void* in, void* out, int in_is_field, int row0, int nrows);
 /* partial[rows][4] -> out4 (device double[4]: max, three sums) by one CTA in a fixed order.  With n_peers > 0 the four
  * numbers are also stored into every peer's gathered[self] (peer_gathered[r] = rank r's device double[n_peers][4],
  * mapped into this process: peer memory over NVLink) -- otherwise the caller all-gathers out4. */
@@ -158,7 +162,8 @@ int slm_transpose_blocks(slm_ctx* ctx, const void* in, void* out, int rows, int 
  * of it is written; from_exchange = 1: peers[q] is rank q's row slab, columns [self*rows, (self+1)*rows) are written.
  * The caller orders the ranks (a device-side barrier before the consumers run and before the buffers are reused). */
 int slm_transpose_blocks_peer(slm_ctx* ctx, const void* in, const void* const* peers, int n_peers, int self, int rows, int W,
-                              int elem_bytes, int from_exchange);
+                              int elem_bytes, int from_exchange, int first, int count /* 0: everything; else rows (way out) or
+                              lines (way back) [first, first + count) */);
 
 /* error_evolution and its length per plane (algorithms.py:25,39,93) of the last run.
  * err: host double[batch][max_loops]; iters: host int[batch].  Synchronises the stream. */

@@ -42,11 +42,12 @@ SIGNATURES = {
     "slm_rows_fft": (_i, [_vp, _vp, _vp, _dp, _vp, _i, _i, _i]),
     "slm_rows_gs_row_pass": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "slm_rows_gs_fourier_pass": (_i, [_vp, _vp, _vp, _i, _vp, _dp, _d, _vp, _vp]),
-    "slm_rows_gs_fourier_pass_dev": (_i, [_vp, _vp, _vp, _i, _vp, _dp, _vp, _vp, _vp]),
+    "slm_rows_gs_fourier_pass_dev": (_i, [_vp, _vp, _vp, _i, _vp, _dp, _vp, _vp, _vp, _i, _i]),
+    "slm_rows_gs_row_pass_part": (_i, [_vp, _vp, _vp, _i, _i, _i]),
     "slm_rows_reduce": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i]),
     "slm_rows_close": (_i, [_vp, _vp, _i, _d, _d, _i, _d, _vp, _vp]),
     "slm_transpose_blocks": (_i, [_vp, _vp, _vp, _i, _i, _i, _i]),
-    "slm_transpose_blocks_peer": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i]),
+    "slm_transpose_blocks_peer": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i]),
     "slm_read_curves": (_i, [_vp, _i, _i, _dp, _ip]),
     "slm_expected_outcome": (_i, [_vp, _i, _vp, _dp, _vp]),
     "slm_deflect_phase": (_i, [_vp, _i, _i, _d, _d, _d, _vp]),

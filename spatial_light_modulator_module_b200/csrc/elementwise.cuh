@@ -244,9 +244,9 @@ SLM_GLOBAL void transpose_blocks_kernel(const T* in, T* out, int h, int W, int f
 // The stores ARE the all-to-all: the blocks cross the links while the tiles are being transposed.
 struct PeerPtrs { void* p[16]; };
 template <typename T>
-SLM_GLOBAL void transpose_blocks_peer_kernel(const T* in, PeerPtrs peers, int h, int W, int from_exchange, int self) {
+SLM_GLOBAL void transpose_blocks_peer_kernel(const T* in, PeerPtrs peers, int h, int W, int from_exchange, int self, int i0, int c0) {
     SLM_STATIC_SMEM T tile[32][33];
-    const int q = blockIdx.z, tc = blockIdx.y * 32, ti = blockIdx.x * 32;
+    const int q = blockIdx.z, tc = c0 + blockIdx.y * 32, ti = i0 + blockIdx.x * 32;    // (i0, c0: the part of every block this launch moves)
     const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
     T* out = static_cast<T*>(peers.p[q]);
     if (!from_exchange) {

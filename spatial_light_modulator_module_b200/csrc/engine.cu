@@ -705,6 +705,22 @@ extern "C" int slm_rows_gs_row_pass(slm_ctx* c, const void* in, void* out, const
     return 0;
 }
 
+extern "C" int slm_rows_gs_row_pass_part(slm_ctx* c, const void* in, void* out, int in_is_field, int row0, int nrows) {
+    if (!c || !in || !out) return fail(SLM_ERR_ARG, "slm_rows_gs_row_pass_part: bad argument");
+    if (row0 < 0 || nrows < 1 || row0 + nrows > c->H || row0 % c->row->rows_per_cta || nrows % c->row->rows_per_cta)
+        return fail(SLM_ERR_ARG, "slm_rows_gs_row_pass_part: bad row range");
+    SLM_CUDA(cudaSetDevice(c->device));
+    const size_t cs = 2 * real_size(c->prec), off = (size_t)row0 * c->W;
+    const size_t cs_in = in_is_field == 2 ? 2 * sizeof(float) : cs;
+    const char* src = static_cast<const char*>(in) + off * cs_in;
+    RowArgs ra{};
+    ra.B = 1; ra.H = nrows; ra.Y = src; ra.field = src; ra.A32 = src; ra.X = static_cast<char*>(out) + off * cs; ra.stats = c->stats;
+    ra.inv_hw = 1.0; ra.tw = c->tw_row;
+    ra.source = in_is_field == 2 ? ROW_FROM_A32 : (in_is_field ? ROW_FROM_A : ROW_FROM_Y);
+    SLM_TIMED(K_ROW_PASS, c->row->row_pass(ALG_GS, ra, c->stream));
+    return 0;
+}
+
 extern "C" int slm_rows_gs_fourier_pass(slm_ctx* c, const void* in, void* out, int block_w, const uint8_t* target_u8,
                                         const double* amp_lut, double scale_prev, double* partial, double* intensity) {
     if (!c || !in || !out || !target_u8 || !amp_lut || !partial) return fail(SLM_ERR_ARG, "slm_rows_gs_fourier_pass: bad argument");
@@ -720,14 +736,18 @@ extern "C" int slm_rows_gs_fourier_pass(slm_ctx* c, const void* in, void* out, i
 }
 
 extern "C" int slm_rows_gs_fourier_pass_dev(slm_ctx* c, const void* in, void* out, int block_w, const uint8_t* target_u8,
-                                            const double* amp_lut, const double* scale_prev_dev, double* partial, double* intensity) {
+                                            const double* amp_lut, const double* scale_prev_dev, double* partial, double* intensity,
+                                            int line0, int nlines) {
     if (!c || !in || !out || !target_u8 || !amp_lut || !partial || !scale_prev_dev) return fail(SLM_ERR_ARG, "slm_rows_gs_fourier_pass_dev: bad argument");
+    if (line0 < 0 || nlines < 0 || line0 + nlines > c->H || line0 % c->row->rows_per_cta || nlines % c->row->rows_per_cta)
+        return fail(SLM_ERR_ARG, "slm_rows_gs_fourier_pass_dev: bad line range");
     if (!block_width_ok(c, block_w))
         return fail(SLM_ERR_SHAPE, "slm_rows_gs_fourier_pass_dev: the exchange block width must be a power-of-two multiple of the line's thread count");
     SLM_CUDA(cudaSetDevice(c->device));
     SLM_TRY(upload_lut(c, amp_lut));
     RowFourierArgs fa{};
     fa.rows = c->H; fa.block_w = block_w; fa.in = in; fa.out = out; fa.T8 = target_u8; fa.lut = c->lut; fa.s0 = 0.0; fa.s0_dev = scale_prev_dev;
+    fa.row0 = line0; fa.nrows = nlines;
     fa.partial = partial; fa.intensity = intensity; fa.tw = c->tw_row;
     SLM_TIMED(K_COL_PASS, c->row->row_fourier(fa, c->stream));
     return 0;
@@ -761,18 +781,22 @@ extern "C" int slm_rows_close(slm_ctx* c, const double* gathered, int world, dou
 }
 
 extern "C" int slm_transpose_blocks_peer(slm_ctx* c, const void* in, const void* const* peers, int n_peers, int self, int rows, int W,
-                                         int elem_bytes, int from_exchange) {
+                                         int elem_bytes, int from_exchange, int first, int count) {
     if (!c || !in || n_peers < 1 || self < 0 || self >= n_peers) return fail(SLM_ERR_ARG, "slm_transpose_blocks_peer: bad argument");
     if (rows < 32 || rows % 32 || W != rows * n_peers) return fail(SLM_ERR_SHAPE, "slm_transpose_blocks_peer: W must be rows * peers, rows a multiple of 32");
+    if (count == 0) { first = 0; count = rows; }
+    if (first < 0 || count < 32 || first % 32 || count % 32 || first + count > rows) return fail(SLM_ERR_ARG, "slm_transpose_blocks_peer: bad part");
     SLM_CUDA(cudaSetDevice(c->device));
     PeerPtrs pp;
     SLM_TRY(peer_ptrs(peers, n_peers, &pp, "slm_transpose_blocks_peer"));
-    const dim3 grid(rows / 32, rows / 32, W / rows), block(256);
+    // a part: rows [first, first + count) of the slab on the way out, lines [first, first + count) on the way back
+    const int i0 = from_exchange ? 0 : first, c0 = from_exchange ? first : 0;
+    const dim3 grid((from_exchange ? rows : count) / 32, (from_exchange ? count : rows) / 32, W / rows), block(256);
     {
         LaunchTimer t_(c, K_ELEMENTWISE);
-        if (elem_bytes == 16) SLM_LAUNCH((transpose_blocks_peer_kernel<cpx<double>>), grid, block, 0, c->stream, static_cast<const cpx<double>*>(in), pp, rows, W, from_exchange, self);
-        else if (elem_bytes == 8) SLM_LAUNCH((transpose_blocks_peer_kernel<double>), grid, block, 0, c->stream, static_cast<const double*>(in), pp, rows, W, from_exchange, self);
-        else if (elem_bytes == 1) SLM_LAUNCH((transpose_blocks_peer_kernel<unsigned char>), grid, block, 0, c->stream, static_cast<const unsigned char*>(in), pp, rows, W, from_exchange, self);
+        if (elem_bytes == 16) SLM_LAUNCH((transpose_blocks_peer_kernel<cpx<double>>), grid, block, 0, c->stream, static_cast<const cpx<double>*>(in), pp, rows, W, from_exchange, self, i0, c0);
+        else if (elem_bytes == 8) SLM_LAUNCH((transpose_blocks_peer_kernel<double>), grid, block, 0, c->stream, static_cast<const double*>(in), pp, rows, W, from_exchange, self, i0, c0);
+        else if (elem_bytes == 1) SLM_LAUNCH((transpose_blocks_peer_kernel<unsigned char>), grid, block, 0, c->stream, static_cast<const unsigned char*>(in), pp, rows, W, from_exchange, self, i0, c0);
         else return fail(SLM_ERR_ARG, "slm_transpose_blocks_peer: elem_bytes must be 1, 8 or 16");
     }
     SLM_CUDA(cudaGetLastError());

@@ -147,6 +147,7 @@ struct RowFourierArgs {
     const void* lut;         // R[256] amplitude by grey level
     double s0;               // scale of the previous iteration (algorithms.py:37) ...
     const double* s0_dev;    // ... or, when not null, where it lies in device memory (loop state kept on the device)
+    int row0, nrows;         // the lines [row0, row0 + nrows) only (nrows == 0: all) -- chunks that overlap the exchange
     double* partial;         // device [rows][4]: max |C|^2, sum r^2, sum r*u, sum u^2 per line
     double* intensity;       // device double, same layout, or null: |C|^2 (final expected_outcome, unscaled)
     const void* tw;

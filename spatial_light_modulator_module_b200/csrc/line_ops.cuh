@@ -119,7 +119,7 @@ template <typename R, int L> struct RowLaunch {
         return check();
     }
     static int row_fourier(const RowFourierArgs& a, cudaStream_t s) {
-        const dim3 grid((unsigned)(a.rows / RG::NR)), block(RG::THREADS);
+        const dim3 grid((unsigned)((a.nrows ? a.nrows : a.rows) / RG::NR)), block(RG::THREADS);
         SLM_LAUNCH((row_fourier_kernel<R, L>), grid, block, RG::SMEM, s, a);
         return check();
     }

@@ -533,7 +533,7 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), (RowGeom<R, W>::MIN_
     constexpr int E = P::E, M = P::M;
     SLM_DYN_SMEM(raw);
     const int t = threadIdx.x, rr = t / M, j = t % M;
-    const long long row = (long long)blockIdx.x * G::NR + rr;
+    const long long row = (long long)a.row0 + (long long)blockIdx.x * G::NR + rr;
     cpx<R>* line = reinterpret_cast<cpx<R>*>(raw) + (size_t)rr * P::NP;
     const typename G::Sync sync{1 + rr / G::LPG};
     const cpx<R>* tw = static_cast<const cpx<R>*>(a.tw);

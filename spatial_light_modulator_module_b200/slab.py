@@ -28,6 +28,7 @@ Two ways of moving the blocks:
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Tuple
 
 import numpy as np
@@ -67,7 +68,6 @@ class SlabEngine(Engine):
     def _peer_setup(self, required: bool):
         """One symmetric allocation per rank holding its two row slabs, its receive buffer and the gathered reduction
         numbers; every rank learns the others' base pointers (torch's symmetric memory does the mapping)."""
-        import os
         if os.environ.get("SLM_SLAB_NO_PEER"):
             return
         try:
@@ -88,8 +88,16 @@ class SlabEngine(Engine):
             ptrs = [int(p) for p in hdl.buffer_ptrs]
             if len(ptrs) != self.world:
                 raise RuntimeError("symmetric memory handle does not cover the group")
-            self._peer = {"buf": buf, "hdl": hdl, "ptrs": ptrs, "offs": offs}
-            self.peer_status = "peer memory (torch symmetric memory, stores over NVLink)"
+            # a second stream (and a library context bound to it) carries the transposing stores, so that the blocks of
+            # the rows / lines already done cross the links while the pass works on the next ones
+            comm_stream = torch.cuda.Stream(self._dev)
+            comm_ctx = C.c_void_p()
+            _ffi.check(self._lib, self._lib.slm_rows_create(C.byref(comm_ctx), self._device_index, self.rows, self.n,
+                                                            _PREC[self.precision], C.c_void_p(comm_stream.cuda_stream)))
+            self._peer = {"buf": buf, "hdl": hdl, "ptrs": ptrs, "offs": offs, "comm_stream": comm_stream, "comm_ctx": comm_ctx}
+            parts = int(os.environ.get("SLM_SLAB_PARTS", "4"))
+            self._parts = parts if parts > 1 and self.rows % (32 * parts) == 0 else 1
+            self.peer_status = f"peer memory (torch symmetric memory, stores over NVLink, {self._parts} part(s) per pass)"
         except Exception as exc:                  # no symmetric memory on this system: keep the collectives
             self._peer = None
             self.peer_status = f"collectives (peer memory unavailable: {type(exc).__name__}: {exc})"
@@ -178,7 +186,7 @@ class SlabEngine(Engine):
             return
         if self._peer is not None and peer_name is not None:
             self._check(self._lib.slm_transpose_blocks_peer(self._ctx, self._mem_ptr(slab), self._peer_array(peer_name), self.world,
-                                                            self.rank, self.rows, self.n, elem_bytes, 0))
+                                                            self.rank, self.rows, self.n, elem_bytes, 0, 0, 0))
             self._peer_barrier()                 # every block of `recv` has landed (and every rank is done with `slab`)
             return
         self._transpose(slab, send, elem_bytes, False)
@@ -191,11 +199,49 @@ class SlabEngine(Engine):
             return
         if self._peer is not None and peer_name is not None:
             self._check(self._lib.slm_transpose_blocks_peer(self._ctx, self._mem_ptr(lines), self._peer_array(peer_name), self.world,
-                                                            self.rank, self.rows, self.n, elem_bytes, 1))
+                                                            self.rank, self.rows, self.n, elem_bytes, 1, 0, 0))
             self._peer_barrier()
             return
         self._all_to_all(lines, recv)
         self._transpose(recv, slab, elem_bytes, True)
+
+    # ---- one GS iteration with the exchange overlapped (peer memory, several parts per pass) ------------------------
+    def _after(self, waiter, stream):
+        """`waiter` (a stream) waits for what `stream` has been given so far"""
+        ev = self._torch.cuda.Event()
+        ev.record(stream)
+        waiter.wait_event(ev)
+
+    def _row_pass_and_push(self, src, cur, field, cs):
+        """SLM-plane pass over the slab in parts; the blocks of a finished part are stored into the peers' receive buffers
+        (comm stream) while the pass works on the next part.  Returns with the engine's stream waiting for the barrier."""
+        A, B, part = self._stream, self._peer["comm_stream"], self.rows // self._parts
+        peers = self._peer_array("Rv")
+        for j in range(self._parts):
+            self._check(self._lib.slm_rows_gs_row_pass_part(self._ctx, self._mem_ptr(src), self._mem_ptr(cur), int(field), j * part, part))
+            self._after(B, A)
+            self._check(self._lib.slm_transpose_blocks_peer(self._peer["comm_ctx"], self._mem_ptr(cur), peers, self.world, self.rank,
+                                                            self.rows, self.n, cs, 0, j * part, part))
+        with self._torch.cuda.stream(B):
+            self._peer["hdl"].barrier(channel=0)          # every rank's blocks have landed
+        self._after(A, B)
+
+    def _fourier_and_push_back(self, Rv, S, Tx, state, partial, inten, cur_name, cs, mine, slot):
+        """Fourier-plane pass over this rank's lines in parts; finished lines go back into the peers' row slabs meanwhile.
+        Ends with this rank's four sums stored on every rank and all ranks past the barrier."""
+        A, B, part = self._stream, self._peer["comm_stream"], self.rows // self._parts
+        peers = self._peer_array(cur_name)
+        for j in range(self._parts):
+            self._fourier(Rv, S, Tx, state, partial, inten, j * part, part)
+            self._after(B, A)
+            self._check(self._lib.slm_transpose_blocks_peer(self._peer["comm_ctx"], self._mem_ptr(S), peers, self.world, self.rank,
+                                                            self.rows, self.n, cs, 1, j * part, part))
+        self._check(self._lib.slm_rows_reduce(self._ctx, self._mem_ptr(partial), self.rows, self._mem_ptr(mine),
+                                              self._peer_array("gathered", slot * self.world * 32), self.world, self.rank))
+        self._after(B, A)
+        with self._torch.cuda.stream(B):
+            self._peer["hdl"].barrier(channel=0)          # the lines are back in the slabs, the sums on every rank
+        self._after(A, B)
 
     def _rows_fft(self, src, dst, inverse, block_in=0, block_out=0, u8=None):
         lut = self._dp(self._amp_lut) if u8 is not None else None
@@ -258,15 +304,26 @@ class SlabEngine(Engine):
         src, field, done_iters = A0, field_kind, 0
         for k in range(max_loops):
             cur = X if src is Y else Y                                        # receives the row-transformed B
-            self._check(self._lib.slm_rows_gs_row_pass(self._ctx, self._mem_ptr(src), self._mem_ptr(cur), None, int(field), 0, None))
-            self._exchange(cur, S, Rv, cs, "Rv")
+            overlap = peer and getattr(self, "_parts", 1) > 1
+            if overlap:
+                self._row_pass_and_push(src, cur, field, cs)
+            else:
+                self._check(self._lib.slm_rows_gs_row_pass(self._ctx, self._mem_ptr(src), self._mem_ptr(cur), None, int(field), 0, None))
+                self._exchange(cur, S, Rv, cs, "Rv")
             if k == 0:                                                        # exact scale of iteration 0: max pre-pass
                 self._fourier(Rv, S, Tx, state, partial, None)
                 self._close(partial, mine, gathered, norm, hw, True, tolerance, state, curve)
             last = k == max_loops - 1
-            self._fourier(Rv, S, Tx, state, partial, inten if (want_expected and (last or check_every or k == 0)) else None)
-            self._close(partial, mine, gathered, norm, hw, False, tolerance, state, curve)
-            self._exchange_back(S, Rv, cur, cs, "X" if cur is X else "Y")     # D with the columns inverse-transformed
+            want_i = inten if (want_expected and (last or check_every or k == 0)) else None
+            if overlap:
+                slot, self._slot = self._slot, self._slot ^ 1
+                self._fourier_and_push_back(Rv, S, Tx, state, partial, want_i, "X" if cur is X else "Y", cs, mine, slot)
+                self._check(self._lib.slm_rows_close(self._ctx, self._mem_ptr(gathered[slot]), self.world, float(norm), float(hw), 0,
+                                                     float(tolerance), self._mem_ptr(state), self._mem_ptr(curve)))
+            else:
+                self._fourier(Rv, S, Tx, state, partial, want_i)
+                self._close(partial, mine, gathered, norm, hw, False, tolerance, state, curve)
+                self._exchange_back(S, Rv, cur, cs, "X" if cur is X else "Y") # D with the columns inverse-transformed
             src, field, done_iters = cur, 0, k + 1
             if check_every or k == 0:                                         # (k == 0: an all-zero target ends the loop at once, algorithms.py:29)
                 st = self.to_host(state)
@@ -318,12 +375,14 @@ class SlabEngine(Engine):
         self._rows_fft(Rv, S, True, block_in=h, block_out=h)
         self._exchange_back(S, Rv, X, cs, peer_slab)
 
-    def _fourier(self, lines_in, lines_out, Tx, state, partial, inten):
+    def _fourier(self, lines_in, lines_out, Tx, state, partial, inten, line0=0, nlines=0):
         self._check(self._lib.slm_rows_gs_fourier_pass_dev(self._ctx, self._mem_ptr(lines_in), self._mem_ptr(lines_out), self.rows,
                                                            self._mem_ptr(Tx), self._dp(self._amp_lut), self._mem_ptr(state),
-                                                           self._mem_ptr(partial), self._mem_ptr(inten)))
+                                                           self._mem_ptr(partial), self._mem_ptr(inten), int(line0), int(nlines)))
 
     def close(self):
+        if self._peer is not None and self._peer.get("comm_ctx") is not None and getattr(self, "_ctx", None):
+            self._lib.slm_ctx_destroy(self._peer["comm_ctx"])
         self._peer = None
         super().close()
 

@@ -58,10 +58,10 @@ def _slab_worker(rank, world, port, n, loops, out_dir):
                             device_id=torch.device("cuda", rank))
     try:
         t = synthetic.noise_target((n, n), seed=6)
-        for tag, env in (("peer", None), ("coll", "1")):
+        for tag, env in (("peer", {}), ("peer1", {"SLM_SLAB_PARTS": "1"}), ("coll", {"SLM_SLAB_NO_PEER": "1"})):
             os.environ.pop("SLM_SLAB_NO_PEER", None)
-            if env:
-                os.environ["SLM_SLAB_NO_PEER"] = env
+            os.environ.pop("SLM_SLAB_PARTS", None)
+            os.environ.update(env)
             eng = slab.SlabEngine(n, world, rank, "fp32")
             h, e, errs = eng.gs(t[rank * (n // world):(rank + 1) * (n // world)], loops)
             np.savez(os.path.join(out_dir, f"slab_{tag}{rank}.npz"), h=h, e=e, errs=np.array(errs), status=np.array(eng.peer_status))
@@ -83,7 +83,8 @@ def test_two_gpu_slab_gs_matches_single_gpu(tmp_path):
     eng = SlabEngine(n, 1, 0, "fp32")
     h, e, errs = eng.gs(synthetic.noise_target((n, n), seed=6), loops)
     statuses = {}
-    for tag in ("peer", "coll"):       # blocks stored straight into the peer's memory / NCCL all-to-all: the same bits
+    # blocks stored straight into the peer's memory (in parts beside the passes / in one go) / NCCL all-to-all: the same bits
+    for tag in ("peer", "peer1", "coll"):
         r0, r1 = np.load(tmp_path / f"slab_{tag}0.npz"), np.load(tmp_path / f"slab_{tag}1.npz")
         statuses[tag] = str(r0["status"])
         np.testing.assert_array_equal(np.concatenate([r0["h"], r1["h"]]), h)
