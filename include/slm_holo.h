@@ -165,6 +165,10 @@ int slm_transpose_blocks_peer(slm_ctx* ctx, const void* in, const void* const* p
                               int elem_bytes, int from_exchange, int first, int count /* 0: everything; else rows (way out) or
                               lines (way back) [first, first + count) */);
 
+/* Strided device-to-device copy on the context's stream (cudaMemcpy2DAsync): `rows` runs of width_bytes.  dst may be
+ * peer memory; the copy engines move the blocks while the SMs compute (the slab path's overlapped exchange). */
+int slm_copy2d_async(slm_ctx* ctx, void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows);
+
 /* error_evolution and its length per plane (algorithms.py:25,39,93) of the last run.
  * err: host double[batch][max_loops]; iters: host int[batch].  Synchronises the stream. */
 int slm_read_curves(slm_ctx* ctx, int batch, int max_loops, double* err, int* iters);

@@ -8,13 +8,10 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 from spatial_light_modulator_module_b200.slab import SlabEngine
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
-for mode in ("peer", "peer1", "coll"):
-    os.environ.pop("SLM_SLAB_NO_PEER", None)
-    os.environ.pop("SLM_SLAB_PARTS", None)
-    if mode == "coll":
-        os.environ["SLM_SLAB_NO_PEER"] = "1"
-    if mode == "peer1":
-        os.environ["SLM_SLAB_PARTS"] = "1"
+for mode in ("copy", "store", "peer1", "coll"):
+    for k in ("SLM_SLAB_NO_PEER", "SLM_SLAB_PARTS", "SLM_SLAB_EXCHANGE"):
+        os.environ.pop(k, None)
+    os.environ.update({"copy": {}, "store": {"SLM_SLAB_EXCHANGE": "store"}, "peer1": {"SLM_SLAB_PARTS": "1"}, "coll": {"SLM_SLAB_NO_PEER": "1"}}[mode])
     eng = SlabEngine(n, world, rank, "fp32")
     rows = n // world
     slab = eng._mem_upload((np.random.default_rng(100 + rank).random((rows, n)) * 255).astype(np.uint8))

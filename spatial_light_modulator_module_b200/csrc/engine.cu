@@ -803,6 +803,24 @@ extern "C" int slm_transpose_blocks_peer(slm_ctx* c, const void* in, const void*
     return 0;
 }
 
+extern "C" int slm_copy2d_async(slm_ctx* c, void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows) {
+    if (!c || !dst || !src || !width_bytes || !rows || dst_pitch < width_bytes || src_pitch < width_bytes)
+        return fail(SLM_ERR_ARG, "slm_copy2d_async: bad argument");
+    SLM_CUDA(cudaSetDevice(c->device));
+#ifdef SLM_EMULATE
+    for (size_t r = 0; r < rows; ++r) memcpy(static_cast<char*>(dst) + r * dst_pitch, static_cast<const char*>(src) + r * src_pitch, width_bytes);
+#else
+    // device to device, possibly to ANOTHER device's memory mapped into this process: the copy engines carry it
+    // (over NVLink) while the SMs run the passes
+    if (dst_pitch == width_bytes && src_pitch == width_bytes)
+        SLM_CUDA(cudaMemcpyAsync(dst, src, width_bytes * rows, cudaMemcpyDeviceToDevice, c->stream));
+    else
+        SLM_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows, cudaMemcpyDeviceToDevice, c->stream));
+#endif
+    c->launches++;
+    return 0;
+}
+
 extern "C" int slm_transpose_blocks(slm_ctx* c, const void* in, void* out, int rows, int W, int elem_bytes, int from_exchange) {
     if (!c || !in || !out || in == out) return fail(SLM_ERR_ARG, "slm_transpose_blocks: bad argument");
     if (rows < 32 || rows % 32 || W % rows) return fail(SLM_ERR_SHAPE, "slm_transpose_blocks: rows must be a multiple of 32 dividing W");

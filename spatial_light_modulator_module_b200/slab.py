@@ -78,7 +78,8 @@ class SlabEngine(Engine):
             plane = self.rows * self.n * cs
             align = lambda v: (v + 1023) // 1024 * 1024       # noqa: E731
             offs, total = {}, 0
-            for name, size in (("X", plane), ("Y", plane), ("Rv", plane), ("Tx", self.rows * self.n), ("gathered", 2 * self.world * 32)):
+            for name, size in (("X", plane), ("Y", plane), ("Rv", plane), ("Rb", plane), ("Tx", self.rows * self.n),
+                               ("gathered", 2 * self.world * 32)):
                 offs[name] = total
                 total += align(size)
             with torch.cuda.stream(self._stream):
@@ -97,7 +98,13 @@ class SlabEngine(Engine):
             self._peer = {"buf": buf, "hdl": hdl, "ptrs": ptrs, "offs": offs, "comm_stream": comm_stream, "comm_ctx": comm_ctx}
             parts = int(os.environ.get("SLM_SLAB_PARTS", "4"))
             self._parts = parts if parts > 1 and self.rows % (32 * parts) == 0 else 1
-            self.peer_status = f"peer memory (torch symmetric memory, stores over NVLink, {self._parts} part(s) per pass)"
+            # how the blocks travel when a pass is split in parts: "copy" -- packed by a local transposing kernel, then moved
+            # by the COPY ENGINES into the peers' memory while the SMs go on with the next part (the passes hold the whole
+            # register file, so a storing kernel cannot run beside them); "store" -- the transposing kernel stores straight
+            # into the peers' memory (between the parts)
+            self._how = os.environ.get("SLM_SLAB_EXCHANGE", "copy") if self._parts > 1 else "store"
+            self.peer_status = (f"peer memory (torch symmetric memory over NVLink; {self._parts} part(s) per pass, "
+                                f"{'copy engines beside the passes' if self._how == 'copy' else 'transposing stores'})")
         except Exception as exc:                  # no symmetric memory on this system: keep the collectives
             self._peer = None
             self.peer_status = f"collectives (peer memory unavailable: {type(exc).__name__}: {exc})"
@@ -243,6 +250,58 @@ class SlabEngine(Engine):
             self._peer["hdl"].barrier(channel=0)          # the lines are back in the slabs, the sums on every rank
         self._after(A, B)
 
+    # ---- the same with the COPY ENGINES moving the blocks while the SMs compute ------------------------------------------
+    def _copy_blocks(self, src_buf, dst_name, first, count, cs, rows_part):
+        """comm stream: my blocks for every peer -> the peer's buffer `dst_name`, block `self.rank`.  rows_part: the part is
+        a range of slab rows i (way out: [q][c][i in part] -- h runs of `count` elements); else a range of lines c (way
+        back: [q][c in part][i] -- one contiguous run)."""
+        h, ctx = self.rows, self._peer["comm_ctx"]
+        base = self._mem_ptr(src_buf).value
+        dst_off = self._peer["offs"][dst_name]
+        for d in range(1, self.world + 1):                         # start with the neighbour: the ranks do not all hit rank 0 first
+            q = (self.rank + d) % self.world
+            src = base + (q * h * h + (first if rows_part else first * h)) * cs
+            dst = self._peer["ptrs"][q] + dst_off + (self.rank * h * h + (first if rows_part else first * h)) * cs
+            if rows_part:
+                self._check(self._lib.slm_copy2d_async(ctx, C.c_void_p(dst), h * cs, C.c_void_p(src), h * cs, count * cs, h))
+            else:
+                self._check(self._lib.slm_copy2d_async(ctx, C.c_void_p(dst), count * h * cs, C.c_void_p(src), count * h * cs, count * h * cs, 1))
+
+    def _pack_ptrs(self, S):
+        """peer-pointer table that makes slm_transpose_blocks_peer write block q of the LOCAL buffer S (it writes block
+        `self.rank` of table entry q)"""
+        cs = np.dtype(self.complex_dtype).itemsize
+        base = self._mem_ptr(S).value
+        return (C.c_void_p * self.world)(*[base + (q - self.rank) * self.rows * self.rows * cs for q in range(self.world)])
+
+    def _row_pass_and_copy(self, src, cur, field, S, cs):
+        A, B, part = self._stream, self._peer["comm_stream"], self.rows // self._parts
+        pack = self._pack_ptrs(S)
+        for j in range(self._parts):
+            self._check(self._lib.slm_rows_gs_row_pass_part(self._ctx, self._mem_ptr(src), self._mem_ptr(cur), int(field), j * part, part))
+            self._check(self._lib.slm_transpose_blocks_peer(self._ctx, self._mem_ptr(cur), pack, self.world, self.rank, self.rows, self.n,
+                                                            cs, 0, j * part, part))          # pack: [q][c][i in part] of S
+            self._after(B, A)
+            self._copy_blocks(S, "Rv", j * part, part, cs, True)
+        with self._torch.cuda.stream(B):
+            self._peer["hdl"].barrier(channel=0)
+        self._after(A, B)
+
+    def _fourier_and_copy_back(self, Rv, S, Rb, Tx, state, partial, inten, cur, cs, mine, slot):
+        A, B, part = self._stream, self._peer["comm_stream"], self.rows // self._parts
+        self._after(B, A)                                          # (the comm stream's copies out of S are over: ordered by the barrier)
+        for j in range(self._parts):
+            self._fourier(Rv, S, Tx, state, partial, inten, j * part, part)
+            self._after(B, A)
+            self._copy_blocks(S, "Rb", j * part, part, cs, False)
+        self._check(self._lib.slm_rows_reduce(self._ctx, self._mem_ptr(partial), self.rows, self._mem_ptr(mine),
+                                              self._peer_array("gathered", slot * self.world * 32), self.world, self.rank))
+        self._after(B, A)
+        with self._torch.cuda.stream(B):
+            self._peer["hdl"].barrier(channel=0)
+        self._after(A, B)
+        self._transpose(Rb, cur, cs, True)                         # unpack: the lines of every rank -> my rows
+
     def _rows_fft(self, src, dst, inverse, block_in=0, block_out=0, u8=None):
         lut = self._dp(self._amp_lut) if u8 is not None else None
         self._check(self._lib.slm_rows_fft(self._ctx, self._mem_ptr(src), self._mem_ptr(u8), lut, self._mem_ptr(dst),
@@ -276,6 +335,7 @@ class SlabEngine(Engine):
         Y = self._peer_view("Y", self.shape, self.complex_dtype) if peer else self._mem_empty(self.shape, self.complex_dtype)
         S = self._mem_empty(blocks, self.complex_dtype)                      # exchange layout: lines (and the send side of the collectives)
         Rv = self._peer_view("Rv", blocks, self.complex_dtype) if peer else self._mem_empty(blocks, self.complex_dtype)  # receive side
+        Rb = self._peer_view("Rb", blocks, self.complex_dtype) if peer else None                                            # ... of the way back (copies)
         partial = self._mem_empty((h, 4), np.float64)
         # A = ifft2(sqrt(T))  (algorithms.py:27), unnormalised: only its phase is used.  For 8-bit targets the
         # reference computes it (and the first phasor) in complex64, so an fp64 plane borrows an fp32 engine.
@@ -305,7 +365,10 @@ class SlabEngine(Engine):
         for k in range(max_loops):
             cur = X if src is Y else Y                                        # receives the row-transformed B
             overlap = peer and getattr(self, "_parts", 1) > 1
-            if overlap:
+            by_copy = overlap and self._how == "copy"
+            if by_copy:
+                self._row_pass_and_copy(src, cur, field, S, cs)
+            elif overlap:
                 self._row_pass_and_push(src, cur, field, cs)
             else:
                 self._check(self._lib.slm_rows_gs_row_pass(self._ctx, self._mem_ptr(src), self._mem_ptr(cur), None, int(field), 0, None))
@@ -317,7 +380,10 @@ class SlabEngine(Engine):
             want_i = inten if (want_expected and (last or check_every or k == 0)) else None
             if overlap:
                 slot, self._slot = self._slot, self._slot ^ 1
-                self._fourier_and_push_back(Rv, S, Tx, state, partial, want_i, "X" if cur is X else "Y", cs, mine, slot)
+                if by_copy:
+                    self._fourier_and_copy_back(Rv, S, Rb, Tx, state, partial, want_i, cur, cs, mine, slot)
+                else:
+                    self._fourier_and_push_back(Rv, S, Tx, state, partial, want_i, "X" if cur is X else "Y", cs, mine, slot)
                 self._check(self._lib.slm_rows_close(self._ctx, self._mem_ptr(gathered[slot]), self.world, float(norm), float(hw), 0,
                                                      float(tolerance), self._mem_ptr(state), self._mem_ptr(curve)))
             else:

@@ -58,9 +58,10 @@ def _slab_worker(rank, world, port, n, loops, out_dir):
                             device_id=torch.device("cuda", rank))
     try:
         t = synthetic.noise_target((n, n), seed=6)
-        for tag, env in (("peer", {}), ("peer1", {"SLM_SLAB_PARTS": "1"}), ("coll", {"SLM_SLAB_NO_PEER": "1"})):
-            os.environ.pop("SLM_SLAB_NO_PEER", None)
-            os.environ.pop("SLM_SLAB_PARTS", None)
+        for tag, env in (("peer", {}), ("peer_store", {"SLM_SLAB_EXCHANGE": "store"}), ("peer1", {"SLM_SLAB_PARTS": "1"}),
+                         ("coll", {"SLM_SLAB_NO_PEER": "1"})):
+            for k in ("SLM_SLAB_NO_PEER", "SLM_SLAB_PARTS", "SLM_SLAB_EXCHANGE"):
+                os.environ.pop(k, None)
             os.environ.update(env)
             eng = slab.SlabEngine(n, world, rank, "fp32")
             h, e, errs = eng.gs(t[rank * (n // world):(rank + 1) * (n // world)], loops)
@@ -83,8 +84,9 @@ def test_two_gpu_slab_gs_matches_single_gpu(tmp_path):
     eng = SlabEngine(n, 1, 0, "fp32")
     h, e, errs = eng.gs(synthetic.noise_target((n, n), seed=6), loops)
     statuses = {}
-    # blocks stored straight into the peer's memory (in parts beside the passes / in one go) / NCCL all-to-all: the same bits
-    for tag in ("peer", "peer1", "coll"):
+    # copy engines beside the passes / transposing stores into the peer's memory (in parts, in one go) / NCCL all-to-all:
+    # the same bits
+    for tag in ("peer", "peer_store", "peer1", "coll"):
         r0, r1 = np.load(tmp_path / f"slab_{tag}0.npz"), np.load(tmp_path / f"slab_{tag}1.npz")
         statuses[tag] = str(r0["status"])
         np.testing.assert_array_equal(np.concatenate([r0["h"], r1["h"]]), h)
