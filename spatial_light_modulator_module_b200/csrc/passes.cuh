@@ -483,6 +483,25 @@ template <int M> SLM_DEV LineLayout line_layout(int wb, int rows, int W, long lo
 template <int M> SLM_DEV unsigned line_off(const LineLayout& L, int r) {
     return (unsigned)(r >> L.lq) * L.block_stride + L.base + (unsigned)(r & L.qmask) * M;
 }
+// f(r, offset of point r) for r < E with the block size q = 2^LQ a compile-time number, so that a thread's points are
+// (a few block bases) + immediates -- like the plain layout's.  With the run-time form above the 32 offsets of a thread
+// were formed once, kept from its loads to its stores and spilled (16384-point lines: 128 registers, one 512-thread CTA
+// per SM and a small L1 beside 135 KB of shared memory -- every spill an exposed round trip to L2).
+template <int E, int M, int LQ, class F> SLM_DEV void each_point_lq(const LineLayout& L, F f) {
+#pragma unroll
+    for (int r = 0; r < E; ++r) f(r, (unsigned)(r >> LQ) * L.block_stride + L.base + (unsigned)((r & ((1 << LQ) - 1)) * M));
+}
+template <int E, int M, class F> SLM_DEV void each_point(const LineLayout& L, F f) {
+    constexpr int LE = E >= 32 ? 5 : (E >= 16 ? 4 : 3);               // log2(E): one block holds the whole line (and the plain layout)
+    switch (L.lq) {
+        case 0: each_point_lq<E, M, 0>(L, f); break;
+        case 1: each_point_lq<E, M, 1>(L, f); break;
+        case 2: each_point_lq<E, M, 2>(L, f); break;
+        case 3: each_point_lq<E, M, (3 < LE ? 3 : LE)>(L, f); break;
+        case 4: each_point_lq<E, M, (4 < LE ? 4 : LE)>(L, f); break;
+        default: each_point_lq<E, M, LE>(L, f); break;
+    }
+}
 
 // ---- plain row transform (setup, preview, slm_fft2) --------------------------------------------------
 template <typename R, int W>
@@ -541,29 +560,29 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), (RowGeom<R, W>::MIN_
     const R* lut = static_cast<const R*>(a.lut);
     const LineLayout lay = line_layout<M>(a.block_w, a.rows, W, row, j);
     cpx<R> v[E];
-    int grey[E];
+    unsigned grey4[(E + 3) / 4];                              // the points' grey levels, four to a register (they wait through a transform)
 #pragma unroll
-    for (int r = 0; r < E; ++r) {
-        const unsigned off = line_off<M>(lay, r);
+    for (int r = 0; r < (E + 3) / 4; ++r) grey4[r] = 0u;
+    each_point<E, M>(lay, [&](int r, unsigned off) {
         v[r] = ld_plane(in + off);
-        grey[r] = ld_ro(a.T8 + off);
-    }
+        grey4[r / 4] |= (unsigned)ld_ro(a.T8 + off) << (8 * (r % 4));
+    });
     line_fft<R, W, -1, 1>(v, line, j, tw, sync);              // second half of C = fft2(B)
     R mx = 0, sa = 0, sb = 0, sc = 0;
     const R s0r = (R)(a.s0_dev ? ld_cg(a.s0_dev) : a.s0);
+    if (a.intensity) each_point<E, M>(lay, [&](int r, unsigned off) { a.intensity[off] = (double)cnorm2(v[r]); });
 #pragma unroll
     for (int r = 0; r < E; ++r) {
         const R m2 = cnorm2(v[r]);
-        const R amp = ld_ro(lut + grey[r]);
-        const R u = s0r * m2, d = u - (R)grey[r];
+        const int grey = (int)((grey4[r / 4] >> (8 * (r % 4))) & 0xffu);
+        const R amp = ld_ro(lut + grey);
+        const R u = s0r * m2, d = u - (R)grey;
         mx = fmax(mx, m2); sa += d * d; sb += d * u; sc += u * u;
-        if (a.intensity) a.intensity[line_off<M>(lay, r)] = (double)m2;
         v[r] = (m2 == (R)0) ? mk<R>(copysign(amp, v[r].x), (R)0) : cscale(v[r], amp * rsqrt_fast(m2));   // algorithms.py:33
     }
     line_fft<R, W, +1, 1>(v, line, j, tw, sync);              // first half of A = ifft2(D)
     cpx<R>* out = static_cast<cpx<R>*>(a.out);
-#pragma unroll
-    for (int r = 0; r < E; ++r) st_plane(out + line_off<M>(lay, r), v[r]);
+    each_point<E, M>(lay, [&](int r, unsigned off) { st_plane(out + off, v[r]); });
 
     // per-line reduction over its M threads
     Partial p; p.mx = (double)mx; p.a = (double)sa; p.b = (double)sb; p.c = (double)sc;
