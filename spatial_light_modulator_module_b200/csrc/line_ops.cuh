@@ -34,7 +34,8 @@ template <typename R, int L> struct ColWarpLaunch<R, L, true> {
                                         cudaStream_t s) {
         if (mode != MODE) return;
         // (CGM_GD_PIPE: tiles wait for the other tiles of their plane, which other CTAs hold -- all of them must be resident)
-        if (MODE == CGM_GD_PIPE) SLM_LAUNCH_COOP((col_warp_kernel<R, L, MODE>), grid, block, WG::SMEM, s, ga, in, out);
+        static const bool coop = !(getenv("SLM_PIPE_COOP") && getenv("SLM_PIPE_COOP")[0] == '0');     // developer switch (A/B)
+        if (MODE == CGM_GD_PIPE && coop) SLM_LAUNCH_COOP((col_warp_kernel<R, L, MODE>), grid, block, WG::SMEM, s, ga, in, out);
         else SLM_LAUNCH_PDL((col_warp_kernel<R, L, MODE>), grid, block, WG::SMEM, s, ga, in, out);
         if (MODE != CGM_COMPLEX && ga.defer_close)
             SLM_LAUNCH((close_planes_kernel<R, L, MODE>), dim3((unsigned)ga.c.B), dim3(32), 0, s, ga, ga.c.W / WG::TC);
