@@ -69,6 +69,7 @@ struct slm_ctx {
     // graphs of one loop iteration, replayed (see replay_iterations); destroyed once their last launch has run
     struct Replay { cudaGraphExec_t exec; cudaGraph_t graph; cudaEvent_t done; };
     std::vector<Replay> replays;
+    cudaStream_t capture_stream = nullptr;                // (the context's stream may be the legacy default stream, which cannot capture)
 #endif
 };
 
@@ -267,11 +268,18 @@ template <class F> static int replay_iterations(slm_ctx* c, int times, F body) {
         } else ++i;
     }
     cudaGetLastError();
-    if (enabled && !c->profiling && times >= 4 && cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+    if (enabled && !c->profiling && times >= 4 && !c->capture_stream &&
+        cudaStreamCreateWithFlags(&c->capture_stream, cudaStreamNonBlocking) != cudaSuccess) { c->capture_stream = nullptr; cudaGetLastError(); }
+    if (enabled && !c->profiling && times >= 4 && c->capture_stream &&
+        cudaStreamBeginCapture(c->capture_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        // the iteration is recorded from a stream of the context's own and launched into the caller's
         const long long before = c->launches;
+        cudaStream_t callers = c->stream;
+        c->stream = c->capture_stream;
         const int rc = body();
+        c->stream = callers;
         cudaGraph_t graph = nullptr;
-        const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+        const cudaError_t e = cudaStreamEndCapture(c->capture_stream, &graph);
         cudaGraphExec_t exec = nullptr;
         if (rc == 0 && e == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
             const long long per = c->launches - before;
@@ -288,6 +296,7 @@ template <class F> static int replay_iterations(slm_ctx* c, int times, F body) {
         c->launches = before;
         if (rc != 0 && rc != SLM_ERR_CUDA) return rc;
     }
+    cudaGetLastError();
 #endif
     for (int i = 0; i < times; ++i) SLM_TRY(body());
     return 0;
@@ -303,6 +312,7 @@ extern "C" void slm_ctx_destroy(slm_ctx* c) {
     cudaStreamSynchronize(c->stream);
 #ifndef SLM_EMULATE
     for (auto& r : c->replays) { cudaGraphExecDestroy(r.exec); cudaGraphDestroy(r.graph); cudaEventDestroy(r.done); }
+    if (c->capture_stream) cudaStreamDestroy(c->capture_stream);
 #endif
     for (void* p : c->owned) cudaFree(p);
     delete c;
