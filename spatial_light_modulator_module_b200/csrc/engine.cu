@@ -251,13 +251,15 @@ static int ensure_loops(slm_ctx* c, int max_loops) {
     return 0;
 }
 
-// `times` identical iterations of a loop: the launches of ONE iteration (issued by `body` on the context's stream)
-// are captured into a CUDA graph and the graph is launched `times` times -- one driver call per iteration instead of
-// three to five kernel launches (a cooperative one among them), which is what the HOST could not always keep up
-// with (measured on a slow box of the pool: 47.5 instead of 42.9 ms per 100 iterations of 32 planes, two-pass form
-// 63.7 instead of 45.5).  Every iteration-dependent quantity (iteration count, learning rate, scale, loop condition)
+// `times` identical iterations of a loop: the launches of up to kReplayChunk iterations (issued by `body` on the
+// context's stream) are captured into a CUDA graph and the graph is launched times / chunk times -- one driver call
+// per 20 iterations instead of three to five kernel launches per iteration, which the HOST could not always keep up
+// with (measured on a slow box of the pool: GS 43.6 instead of 32.1 ms per 100 iterations of 32 planes).  One graph
+// per iteration was tried first: the device-side start-up gap between graph launches cost the five-kernel two-pass GD
+// form more (53.4 ms) than the host saved (44.9 ms without graphs).  Every iteration-dependent quantity (iteration count, learning rate, scale, loop condition)
 // lives in device memory, so the captured arguments are the same for all iterations.
 // Falls back to plain launches when capture is not possible; SLM_NO_GRAPH=1 disables it.
+static const int kReplayChunk = 20;          // iterations per graph: a graph launch has a start-up gap of its own on the device
 template <class F> static int replay_iterations(slm_ctx* c, int times, F body) {
 #ifndef SLM_EMULATE
     static const bool enabled = !getenv("SLM_NO_GRAPH");
@@ -276,19 +278,22 @@ template <class F> static int replay_iterations(slm_ctx* c, int times, F body) {
         const long long before = c->launches;
         cudaStream_t callers = c->stream;
         c->stream = c->capture_stream;
-        const int rc = body();
+        const int chunk = times < kReplayChunk ? times : kReplayChunk;
+        int rc = 0;
+        for (int i = 0; i < chunk && rc == 0; ++i) rc = body();
         c->stream = callers;
         cudaGraph_t graph = nullptr;
         const cudaError_t e = cudaStreamEndCapture(c->capture_stream, &graph);
         cudaGraphExec_t exec = nullptr;
         if (rc == 0 && e == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
-            const long long per = c->launches - before;
-            for (int i = 0; i < times; ++i) SLM_CUDA(cudaGraphLaunch(exec, c->stream));
-            c->launches = before + per * times;
+            const long long per = (c->launches - before) / chunk;
+            for (int i = 0; i < times / chunk; ++i) SLM_CUDA(cudaGraphLaunch(exec, c->stream));
+            c->launches = before + per * (times / chunk) * chunk;
             slm_ctx::Replay r{exec, graph, nullptr};
             SLM_CUDA(cudaEventCreateWithFlags(&r.done, cudaEventDisableTiming));
             SLM_CUDA(cudaEventRecord(r.done, c->stream));
             c->replays.push_back(r);
+            for (int i = 0; i < times % chunk; ++i) SLM_TRY(body());     // the remainder: plain launches
             return 0;
         }
         if (graph) cudaGraphDestroy(graph);
