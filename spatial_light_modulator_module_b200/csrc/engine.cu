@@ -260,9 +260,13 @@ static int ensure_loops(slm_ctx* c, int max_loops) {
 // lives in device memory, so the captured arguments are the same for all iterations.
 // Falls back to plain launches when capture is not possible; SLM_NO_GRAPH=1 disables it.
 static const int kReplayChunk = 20;          // iterations per graph: a graph launch has a start-up gap of its own on the device
-template <class F> static int replay_iterations(slm_ctx* c, int times, F body) {
+template <class F> static int replay_iterations(slm_ctx* c, int batch, int times, F body) {
 #ifndef SLM_EMULATE
-    static const bool enabled = !getenv("SLM_NO_GRAPH");
+    // (small runs -- a single SLM-size plane -- are latency bound: recording and instantiating a graph costs them more
+    //  than it saves, 3.0 instead of 2.8 ms per 100-iteration hologram, and their passes overlap by programmatic
+    //  dependent launch instead; same threshold as choose_pdl)
+    static const bool on = !getenv("SLM_NO_GRAPH");
+    const bool enabled = on && (long long)batch * c->H * c->W > (1ll << 21);
     for (size_t i = 0; i < c->replays.size();) {               // retire graphs whose last launch has run
         if (cudaEventQuery(c->replays[i].done) == cudaSuccess) {
             cudaGraphExecDestroy(c->replays[i].exec); cudaGraphDestroy(c->replays[i].graph); cudaEventDestroy(c->replays[i].done);
@@ -537,7 +541,7 @@ extern "C" int slm_gs_run(slm_ctx* c, int batch, const uint8_t* T8, const void* 
         else SLM_TIMED(K_COL_PASS, c->col->col_pass(ALG_GS, ca, c->stream));
         return 0;
     };
-    SLM_TRY(replay_iterations(c, max_loops - 1, [&]() -> int {     // iterations 0 .. max_loops-2: Fourier-plane pass + SLM-plane pass
+    SLM_TRY(replay_iterations(c, batch, max_loops - 1, [&]() -> int {     // iterations 0 .. max_loops-2: Fourier-plane pass + SLM-plane pass
         SLM_TRY(fourier_step());
         SLM_TIMED(K_ROW_PASS, c->row->row_pass(ALG_GS, ra, c->stream));
         return 0;
@@ -618,7 +622,7 @@ extern "C" int slm_gd_run(slm_ctx* c, int batch, const uint8_t* T8, const void* 
         }
         return 0;
     };
-    SLM_TRY(replay_iterations(c, max_loops - 1, [&]() -> int {     // iterations 0 .. max_loops-2: Fourier-plane step + SLM-plane pass
+    SLM_TRY(replay_iterations(c, batch, max_loops - 1, [&]() -> int {     // iterations 0 .. max_loops-2: Fourier-plane step + SLM-plane pass
         SLM_TRY(fourier_step());
         SLM_TIMED(K_ROW_PASS, c->row->row_pass(ALG_GD, ra, c->stream));
         return 0;

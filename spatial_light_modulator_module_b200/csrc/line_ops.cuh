@@ -34,11 +34,9 @@ template <typename R, int L> struct ColWarpLaunch<R, L, true> {
                                         cudaStream_t s) {
         if (mode != MODE) return;
         // (CGM_GD_PIPE: tiles wait for the other tiles of their plane, which other CTAs hold -- all of them must be resident)
-        // A cooperative launch guarantees what the form needs -- every CTA resident -- but costs host time per launch and,
-        // inside a graph, device time (67 k instead of 75 k iterations/s): the grid is at most one CTA per SM (shared
-        // memory allows no second one), so on a device this process has to itself the plain launch is resident as a whole
-        // anyway; a time-out in the kernel turns the exception into an error instead of a hang.  SLM_PIPE_COOP=1 insists.
-        static const bool coop = getenv("SLM_PIPE_COOP") && getenv("SLM_PIPE_COOP")[0] == '1';
+        // (SLM_PIPE_COOP=0: plain launch -- the grid is at most one CTA per SM, so on a device the process has to itself it
+        //  is resident as a whole anyway; the kernel's time-out turns the exception into an error instead of a hang)
+        static const bool coop = !(getenv("SLM_PIPE_COOP") && getenv("SLM_PIPE_COOP")[0] == '0');
         if (MODE == CGM_GD_PIPE && coop) SLM_LAUNCH_COOP((col_warp_kernel<R, L, MODE>), grid, block, WG::SMEM, s, ga, in, out);
         else SLM_LAUNCH_PDL((col_warp_kernel<R, L, MODE>), grid, block, WG::SMEM, s, ga, in, out);
         if (MODE != CGM_COMPLEX && ga.defer_close)
