@@ -70,6 +70,11 @@ struct slm_ctx {
     struct Replay { cudaGraphExec_t exec; cudaGraph_t graph; cudaEvent_t done; };
     std::vector<Replay> replays;
     cudaStream_t capture_stream = nullptr;                // (the context's stream may be the legacy default stream, which cannot capture)
+    // whole loops of small runs, kept per argument set (see replay_iterations)
+    struct Kept { std::string key; cudaGraphExec_t exec; cudaGraph_t graph; long long launches; unsigned long long stamp; };
+    std::vector<Kept> kept;
+    std::vector<std::string> seen;                        // argument sets met once (the last few)
+    unsigned long long kept_clock = 0;
 #endif
 };
 
@@ -260,39 +265,68 @@ static int ensure_loops(slm_ctx* c, int max_loops) {
 // lives in device memory, so the captured arguments are the same for all iterations.
 // Falls back to plain launches when capture is not possible; SLM_NO_GRAPH=1 disables it.
 static const int kReplayChunk = 20;          // iterations per graph: a graph launch has a start-up gap of its own on the device
-template <class F> static int replay_iterations(slm_ctx* c, int batch, int times, F body) {
+
 #ifndef SLM_EMULATE
-    // (small runs -- a single SLM-size plane -- are latency bound: recording and instantiating a graph costs them more
-    //  than it saves, 3.0 instead of 2.8 ms per 100-iteration hologram, and their passes overlap by programmatic
-    //  dependent launch instead; same threshold as choose_pdl)
+// Record `n` iterations (issued by `body` on the context's stream) into an instantiated graph.  The iterations are
+// recorded from a stream of the context's own (the caller's may be the legacy default stream, which cannot capture).
+// Returns false -- with the context untouched -- when the driver refuses; launches_out: kernels in the graph.
+template <class F> static bool record_iterations(slm_ctx* c, int n, F& body, cudaGraph_t* graph, cudaGraphExec_t* exec, long long* launches_out,
+                                                 int* rc_out) {
+    *rc_out = 0;
+    cudaGetLastError();
+    if (!c->capture_stream && cudaStreamCreateWithFlags(&c->capture_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        c->capture_stream = nullptr; cudaGetLastError(); return false;
+    }
+    if (cudaStreamBeginCapture(c->capture_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return false; }
+    const long long before = c->launches;
+    cudaStream_t callers = c->stream;
+    c->stream = c->capture_stream;
+    int rc = 0;
+    for (int i = 0; i < n && rc == 0; ++i) rc = body();
+    c->stream = callers;
+    *graph = nullptr; *exec = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(c->capture_stream, graph);
+    *launches_out = c->launches - before;
+    c->launches = before;
+    if (rc == 0 && e == cudaSuccess && *graph && cudaGraphInstantiate(exec, *graph, 0) == cudaSuccess) return true;
+    if (*graph) cudaGraphDestroy(*graph);
+    cudaGetLastError();                                           // (e.g. an attribute the driver cannot capture): plain launches
+    if (rc != 0 && rc != SLM_ERR_CUDA) *rc_out = rc;
+    return false;
+}
+#endif
+
+// `times` identical iterations of a loop.  Every iteration-dependent quantity (iteration count, learning rate, scale,
+// loop condition) lives in device memory, so the launches of all iterations of a run have the same arguments
+//  and can be replayed from a CUDA graph instead of being launched one by one:
+//   * LARGE runs (batches): up to kReplayChunk iterations are recorded and the graph is launched times / chunk times --
+//     one driver call per 20 iterations instead of three to five launches per iteration, which the HOST could not
+//     always keep up with (a slow box of the pool: GS 43.6 instead of 32.1 ms, GD 50.4 instead of 41.9 ms per 100
+//     iterations of 32 planes).  One graph per iteration was tried first: the device-side start-up gap between graph
+//     launches cost the five-kernel two-pass GD form more (53.4 ms) than the host saved (44.9 ms without graphs).
+//   * SMALL runs (one SLM-size plane: latency bound, ~200 launches in under 3 ms): recording a graph per run costs more
+//     than it saves (3.0 instead of 2.8 ms), so the whole loop is recorded once per distinct argument set -- `key`: the
+//     bytes of every launch argument -- when that set is seen the SECOND time, kept (four per context), and later runs
+//     are ONE graph launch.  The drop-in calls meet this in practice: holograms of one shape made one after the other
+//     get the same buffers from the allocator.
+// Falls back to plain launches whenever capture is not possible; SLM_NO_GRAPH=1 disables all of it.
+template <class F> static int replay_iterations(slm_ctx* c, int batch, int times, const std::string& key, F body) {
+#ifndef SLM_EMULATE
     static const bool on = !getenv("SLM_NO_GRAPH");
-    const bool enabled = on && (long long)batch * c->H * c->W > (1ll << 21);
-    for (size_t i = 0; i < c->replays.size();) {               // retire graphs whose last launch has run
+    for (size_t i = 0; i < c->replays.size();) {               // retire one-shot graphs whose last launch has run
         if (cudaEventQuery(c->replays[i].done) == cudaSuccess) {
             cudaGraphExecDestroy(c->replays[i].exec); cudaGraphDestroy(c->replays[i].graph); cudaEventDestroy(c->replays[i].done);
             c->replays.erase(c->replays.begin() + i);
         } else ++i;
     }
     cudaGetLastError();
-    if (enabled && !c->profiling && times >= 4 && !c->capture_stream &&
-        cudaStreamCreateWithFlags(&c->capture_stream, cudaStreamNonBlocking) != cudaSuccess) { c->capture_stream = nullptr; cudaGetLastError(); }
-    if (enabled && !c->profiling && times >= 4 && c->capture_stream &&
-        cudaStreamBeginCapture(c->capture_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-        // the iteration is recorded from a stream of the context's own and launched into the caller's
-        const long long before = c->launches;
-        cudaStream_t callers = c->stream;
-        c->stream = c->capture_stream;
+    const bool large = (long long)batch * c->H * c->W > (1ll << 21);
+    if (on && !c->profiling && times >= 4 && large) {
         const int chunk = times < kReplayChunk ? times : kReplayChunk;
-        int rc = 0;
-        for (int i = 0; i < chunk && rc == 0; ++i) rc = body();
-        c->stream = callers;
-        cudaGraph_t graph = nullptr;
-        const cudaError_t e = cudaStreamEndCapture(c->capture_stream, &graph);
-        cudaGraphExec_t exec = nullptr;
-        if (rc == 0 && e == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
-            const long long per = (c->launches - before) / chunk;
+        cudaGraph_t graph; cudaGraphExec_t exec; long long launches = 0; int rc = 0;
+        if (record_iterations(c, chunk, body, &graph, &exec, &launches, &rc)) {
             for (int i = 0; i < times / chunk; ++i) SLM_CUDA(cudaGraphLaunch(exec, c->stream));
-            c->launches = before + per * (times / chunk) * chunk;
+            c->launches += launches * (times / chunk);
             slm_ctx::Replay r{exec, graph, nullptr};
             SLM_CUDA(cudaEventCreateWithFlags(&r.done, cudaEventDisableTiming));
             SLM_CUDA(cudaEventRecord(r.done, c->stream));
@@ -300,12 +334,42 @@ template <class F> static int replay_iterations(slm_ctx* c, int batch, int times
             for (int i = 0; i < times % chunk; ++i) SLM_TRY(body());     // the remainder: plain launches
             return 0;
         }
-        if (graph) cudaGraphDestroy(graph);
-        cudaGetLastError();                                       // capture refused (e.g. an attribute the driver cannot capture): plain launches
-        c->launches = before;
-        if (rc != 0 && rc != SLM_ERR_CUDA) return rc;
+        if (rc) return rc;
+    } else if (on && !c->profiling && times >= 4 && times <= 512 && !key.empty()) {
+        for (auto& k : c->kept) {
+            if (k.key == key) {                                           // seen before and recorded: one launch
+                SLM_CUDA(cudaGraphLaunch(k.exec, c->stream));
+                c->launches += k.launches;
+                k.stamp = ++c->kept_clock;
+                return 0;
+            }
+        }
+        bool met = false;
+        for (auto& k : c->seen) met = met || k == key;
+        if (met) {                                                        // second sighting: record the whole loop and keep it
+            cudaGraph_t graph; cudaGraphExec_t exec; long long launches = 0; int rc = 0;
+            if (record_iterations(c, times, body, &graph, &exec, &launches, &rc)) {
+                if (c->kept.size() >= 4) {                                // drop the least recently used (not in flight: launches are stream ordered,
+                    size_t old = 0;                                       //  and destroying an exec waits for nothing it still needs)
+                    for (size_t i = 1; i < c->kept.size(); ++i) if (c->kept[i].stamp < c->kept[old].stamp) old = i;
+                    SLM_CUDA(cudaStreamSynchronize(c->stream));
+                    cudaGraphExecDestroy(c->kept[old].exec); cudaGraphDestroy(c->kept[old].graph);
+                    c->kept.erase(c->kept.begin() + old);
+                }
+                SLM_CUDA(cudaGraphLaunch(exec, c->stream));
+                c->launches += launches;
+                c->kept.push_back({key, exec, graph, launches, ++c->kept_clock});
+                return 0;
+            }
+            if (rc) return rc;
+        } else {
+            if (c->seen.size() >= 4) c->seen.erase(c->seen.begin());
+            c->seen.push_back(key);
+        }
     }
     cudaGetLastError();
+#else
+    (void)batch; (void)key;
 #endif
     for (int i = 0; i < times; ++i) SLM_TRY(body());
     return 0;
@@ -321,6 +385,7 @@ extern "C" void slm_ctx_destroy(slm_ctx* c) {
     cudaStreamSynchronize(c->stream);
 #ifndef SLM_EMULATE
     for (auto& r : c->replays) { cudaGraphExecDestroy(r.exec); cudaGraphDestroy(r.graph); cudaEventDestroy(r.done); }
+    for (auto& k : c->kept) { cudaGraphExecDestroy(k.exec); cudaGraphDestroy(k.graph); }
     if (c->capture_stream) cudaStreamDestroy(c->capture_stream);
 #endif
     for (void* p : c->owned) cudaFree(p);
@@ -541,7 +606,12 @@ extern "C" int slm_gs_run(slm_ctx* c, int batch, const uint8_t* T8, const void* 
         else SLM_TIMED(K_COL_PASS, c->col->col_pass(ALG_GS, ca, c->stream));
         return 0;
     };
-    SLM_TRY(replay_iterations(c, batch, max_loops - 1, [&]() -> int {     // iterations 0 .. max_loops-2: Fourier-plane pass + SLM-plane pass
+    std::string key("gs");                                          // every argument the loop's launches are made of
+    RowArgs ra_key = ra;
+    ra_key.hologram = nullptr;                                      // (only the final pass -- outside the loop -- writes the hologram)
+    key.append(reinterpret_cast<const char*>(&ra_key), sizeof ra_key).append(reinterpret_cast<const char*>(&ca), sizeof ca);
+    key.append(reinterpret_cast<const char*>(&batch), sizeof batch);
+    SLM_TRY(replay_iterations(c, batch, max_loops - 1, key, [&]() -> int {     // iterations 0 .. max_loops-2: Fourier-plane pass + SLM-plane pass
         SLM_TRY(fourier_step());
         SLM_TIMED(K_ROW_PASS, c->row->row_pass(ALG_GS, ra, c->stream));
         return 0;
@@ -622,7 +692,12 @@ extern "C" int slm_gd_run(slm_ctx* c, int batch, const uint8_t* T8, const void* 
         }
         return 0;
     };
-    SLM_TRY(replay_iterations(c, batch, max_loops - 1, [&]() -> int {     // iterations 0 .. max_loops-2: Fourier-plane step + SLM-plane pass
+    std::string key(fused ? "gdf" : (pipe ? "gdp" : "gd2"));
+    RowArgs ra_key = ra;
+    ra_key.hologram = nullptr;                                      // (only the final pass -- outside the loop -- writes the hologram)
+    key.append(reinterpret_cast<const char*>(&ra_key), sizeof ra_key).append(reinterpret_cast<const char*>(&ca), sizeof ca);
+    key.append(reinterpret_cast<const char*>(&batch), sizeof batch);
+    SLM_TRY(replay_iterations(c, batch, max_loops - 1, key, [&]() -> int {     // iterations 0 .. max_loops-2: Fourier-plane step + SLM-plane pass
         SLM_TRY(fourier_step());
         SLM_TIMED(K_ROW_PASS, c->row->row_pass(ALG_GD, ra, c->stream));
         return 0;
