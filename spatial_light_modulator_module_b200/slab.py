@@ -95,7 +95,16 @@ class SlabEngine(Engine):
             comm_ctx = C.c_void_p()
             _ffi.check(self._lib, self._lib.slm_rows_create(C.byref(comm_ctx), self._device_index, self.rows, self.n,
                                                             _PREC[self.precision], C.c_void_p(comm_stream.cuda_stream)))
-            self._peer = {"buf": buf, "hdl": hdl, "ptrs": ptrs, "offs": offs, "comm_stream": comm_stream, "comm_ctx": comm_ctx}
+            # further streams (and contexts) so that the copies to different peers run on different copy engines at once
+            lanes = []
+            for _ in range(min(self.world - 1, int(os.environ.get("SLM_SLAB_COPY_LANES", "4"))) - 1):
+                st = torch.cuda.Stream(self._dev)
+                cx = C.c_void_p()
+                _ffi.check(self._lib, self._lib.slm_rows_create(C.byref(cx), self._device_index, self.rows, self.n,
+                                                                _PREC[self.precision], C.c_void_p(st.cuda_stream)))
+                lanes.append((st, cx))
+            self._peer = {"buf": buf, "hdl": hdl, "ptrs": ptrs, "offs": offs, "comm_stream": comm_stream, "comm_ctx": comm_ctx,
+                          "lanes": lanes}
             parts = int(os.environ.get("SLM_SLAB_PARTS", "4"))
             self._parts = parts if parts > 1 and self.rows % (32 * parts) == 0 else 1
             # how the blocks travel when a pass is split in parts: "copy" -- packed by a local transposing kernel, then moved
@@ -255,17 +264,24 @@ class SlabEngine(Engine):
         """comm stream: my blocks for every peer -> the peer's buffer `dst_name`, block `self.rank`.  rows_part: the part is
         a range of slab rows i (way out: [q][c][i in part] -- h runs of `count` elements); else a range of lines c (way
         back: [q][c in part][i] -- one contiguous run)."""
-        h, ctx = self.rows, self._peer["comm_ctx"]
+        h = self.rows
+        B = self._peer["comm_stream"]
+        lanes = [(B, self._peer["comm_ctx"])] + self._peer["lanes"]     # copies to different peers on different streams: several
+        for st, _ in lanes[1:]:                                          # copy engines at once; all of them start behind B ...
+            self._after(st, B)
         base = self._mem_ptr(src_buf).value
         dst_off = self._peer["offs"][dst_name]
         for d in range(1, self.world + 1):                         # start with the neighbour: the ranks do not all hit rank 0 first
             q = (self.rank + d) % self.world
+            ctx = lanes[d % len(lanes)][1]
             src = base + (q * h * h + (first if rows_part else first * h)) * cs
             dst = self._peer["ptrs"][q] + dst_off + (self.rank * h * h + (first if rows_part else first * h)) * cs
             if rows_part:
                 self._check(self._lib.slm_copy2d_async(ctx, C.c_void_p(dst), h * cs, C.c_void_p(src), h * cs, count * cs, h))
             else:
                 self._check(self._lib.slm_copy2d_async(ctx, C.c_void_p(dst), count * h * cs, C.c_void_p(src), count * h * cs, count * h * cs, 1))
+        for st, _ in lanes[1:]:                                          # ... and B goes on behind all of them
+            self._after(B, st)
 
     def _pack_ptrs(self, S):
         """peer-pointer table that makes slm_transpose_blocks_peer write block q of the LOCAL buffer S (it writes block
@@ -449,6 +465,8 @@ class SlabEngine(Engine):
     def close(self):
         if self._peer is not None and self._peer.get("comm_ctx") is not None and getattr(self, "_ctx", None):
             self._lib.slm_ctx_destroy(self._peer["comm_ctx"])
+            for _, cx in self._peer.get("lanes", []):
+                self._lib.slm_ctx_destroy(cx)
         self._peer = None
         super().close()
 
