@@ -1,5 +1,6 @@
-"""Developer tool: GD iterations/s at 32 x 1024^2 (device resident) under a few engine switches given as NAME=VALUE
-pairs separated by commas on the command line, e.g.  python profiles/ab_gd.py "" SLM_PIPE_CTAS=128 SLM_GD_FORM=two_pass
+"""Developer tool: GD iterations/s at 32 x 1024^2 (device resident; AB_SIZE / AB_HEIGHT / AB_BATCH / AB_LOOPS change the
+workload) under a few engine switches given as NAME=VALUE pairs separated by commas on the command line, e.g.
+python profiles/ab_gd.py "" SLM_PIPE_CTAS=128 SLM_GD_FORM=two_pass
 Each variant runs in a child process (the switches are read once per process)."""
 import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -9,7 +10,9 @@ sys.path.insert(0, %r)
 from spatial_light_modulator_module_b200 import host_logic as hl, synthetic
 from spatial_light_modulator_module_b200.engine import Engine
 alg = sys.argv[1]
-shape, batch, loops = (1024, 1024), 32, 100
+import os
+n = int(os.environ.get("AB_SIZE", "1024"))
+shape, batch, loops = (int(os.environ.get("AB_HEIGHT", n)), n), int(os.environ.get("AB_BATCH", "32")), int(os.environ.get("AB_LOOPS", "100"))
 eng = Engine(shape, "fp32", batch)
 dev = torch.device("cuda", 0)
 t = torch.from_numpy(np.stack([synthetic.noise_target(shape, seed=i) for i in range(batch)])).to(dev)
@@ -17,6 +20,7 @@ x0 = torch.from_numpy(np.exp(2j * np.pi * np.random.default_rng(0).random((batch
 x = torch.empty_like(x0)
 during, _ = hl.learning_rate_schedule(0.005, 0, loops)
 norms = np.full(batch, 255.0)
+print("", end="")
 def step():
     if alg == "gd":
         x.copy_(x0); r, _ = eng.gd(t, x, during, loops, want_expected=False, norms=norms)
