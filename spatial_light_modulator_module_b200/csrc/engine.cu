@@ -51,6 +51,7 @@ struct slm_ctx {
     void* lut = nullptr;
     float* lut32 = nullptr;
     double lut_host[256];                                 // the table the device copies hold (upload_lut)
+    float lut_host_f[256];                                // ... narrowed: staging for the copies (lives as long as the context)
     bool lut_valid = false;
     unsigned* mt_buf = nullptr;                           // [624 state in][625 state out] of slm_mt19937_uniform
     int loops_cap = 0, tiles = 0;
@@ -250,6 +251,13 @@ static int ensure_loops(slm_ctx* c, int max_loops) {
     int cap = c->loops_cap ? c->loops_cap : 256;
     while (cap < max_loops) cap *= 2;
     SLM_CUDA(cudaStreamSynchronize(c->stream));
+    for (void* old : {(void*)c->err_curve, (void*)c->lr}) {           // the smaller buffers are not needed any more
+        if (!old) continue;
+        for (size_t i = 0; i < c->owned.size(); ++i)
+            if (c->owned[i] == old) { c->owned.erase(c->owned.begin() + i); break; }
+        cudaFree(old);
+    }
+    c->err_curve = nullptr; c->lr = nullptr;
     SLM_TRY(dev_alloc(c, (void**)&c->err_curve, (size_t)c->max_batch * cap * sizeof(double)));
     SLM_TRY(dev_alloc(c, (void**)&c->lr, (size_t)cap * sizeof(double)));
     c->loops_cap = cap;
@@ -475,14 +483,14 @@ static int check_batch(slm_ctx* c, int batch, const char* who) {
 // host LUT (double[256]) -> device R[256] and float[256]
 static int upload_lut(slm_ctx* c, const double* lut) {
     if (c->lut_valid && memcmp(c->lut_host, lut, sizeof c->lut_host) == 0) return 0;     // unchanged since the last run: no copy, no sync
+    // (a copy from pageable memory is staged by the driver before the call returns, and the staging arrays are the
+    //  context's own: no synchronisation -- GD and GS alternate their tables in error_evolution_curves)
     memcpy(c->lut_host, lut, sizeof c->lut_host);
     c->lut_valid = true;
-    float f[256]; double d[256];
-    for (int i = 0; i < 256; ++i) { f[i] = (float)lut[i]; d[i] = lut[i]; }
-    SLM_CUDA(cudaMemcpyAsync(c->lut32, f, sizeof f, cudaMemcpyHostToDevice, c->stream));
-    if (c->prec == PREC_F64) SLM_CUDA(cudaMemcpyAsync(c->lut, d, sizeof d, cudaMemcpyHostToDevice, c->stream));
-    else SLM_CUDA(cudaMemcpyAsync(c->lut, f, sizeof f, cudaMemcpyHostToDevice, c->stream));
-    SLM_CUDA(cudaStreamSynchronize(c->stream));     // the staging arrays live on this stack frame
+    for (int i = 0; i < 256; ++i) c->lut_host_f[i] = (float)lut[i];
+    SLM_CUDA(cudaMemcpyAsync(c->lut32, c->lut_host_f, sizeof c->lut_host_f, cudaMemcpyHostToDevice, c->stream));
+    if (c->prec == PREC_F64) SLM_CUDA(cudaMemcpyAsync(c->lut, c->lut_host, sizeof c->lut_host, cudaMemcpyHostToDevice, c->stream));
+    else SLM_CUDA(cudaMemcpyAsync(c->lut, c->lut_host_f, sizeof c->lut_host_f, cudaMemcpyHostToDevice, c->stream));
     return 0;
 }
 
