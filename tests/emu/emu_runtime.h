@@ -70,7 +70,8 @@ struct State {
     unsigned char* smem = nullptr;
     void (*body)(void*) = nullptr;
     void* body_arg = nullptr;
-    unsigned long progress = 0;
+    unsigned long progress = 0;      // barriers completed, mbarrier arrivals, global atomics, threads finished ...
+    unsigned long weak = 0;          // warp rendezvous: a polling warp produces these for ever, so they only postpone the verdict
     std::vector<unsigned char> smem_store;
 };
 // The CTA whose fibres are running.  Ordinary launches run one CTA at a time on `solo`; a cooperative launch
@@ -112,7 +113,7 @@ inline void sync_warp() {
     unsigned w = s.cur->tid / 32;
     WarpSlot& ws = s.warps[w];
     unsigned gen = ws.gen;
-    s.progress++;
+    s.weak++;
     if (++ws.count == warp_lanes(w)) { ws.count = 0; ws.gen++; return; }
     while (ws.gen == gen) yield();
 }
@@ -183,10 +184,12 @@ inline void sweep_cta(State& s) {
 template <class F> void run_cta(dim3 bidx, dim3 grid, dim3 block, size_t smem_bytes, F& f) {
     State& s = S();
     setup_cta(s, bidx, grid, block, smem_bytes, f);
+    unsigned long idle = 0;
     while (s.alive) {
-        unsigned long before = s.progress;
+        unsigned long before = s.progress, weak_before = s.weak;
         sweep_cta(s);
-        if (s.alive && s.progress == before) { fprintf(stderr, "emu: deadlock in CTA (%u,%u)\n", bidx.x, bidx.y); abort(); }
+        if (s.progress != before) { idle = 0; continue; }
+        if (s.alive && (s.weak == weak_before || ++idle > 200000)) { fprintf(stderr, "emu: deadlock in CTA (%u,%u)\n", bidx.x, bidx.y); abort(); }
     }
 }
 
@@ -203,19 +206,22 @@ template <class F> void launch_coop(dim3 grid, dim3 block, size_t smem_bytes, F 
     while (pool.size() < grid.x) pool.push_back(new State);
     State* const saved = current();
     for (unsigned x = 0; x < grid.x; ++x) { current() = pool[x]; setup_cta(*pool[x], dim3(x, 1, 1), grid, block, smem_bytes, f); }
+    unsigned long idle = 0;
     for (;;) {
-        unsigned long alive = 0, moved = 0;
+        unsigned long alive = 0, moved = 0, weak = 0;
         for (unsigned x = 0; x < grid.x; ++x) {
             State& s = *pool[x];
             if (!s.alive) continue;
             current() = &s;
-            const unsigned long before = s.progress;
+            const unsigned long before = s.progress, weak_before = s.weak;
             sweep_cta(s);
             moved += s.progress - before;
+            weak += s.weak - weak_before;
             alive += s.alive;
         }
         if (!alive) break;
-        if (!moved) { fprintf(stderr, "emu: deadlock in a cooperative grid of %u CTAs\n", grid.x); abort(); }
+        if (moved) { idle = 0; continue; }
+        if (!weak || ++idle > 200000) { fprintf(stderr, "emu: deadlock in a cooperative grid of %u CTAs\n", grid.x); abort(); }
     }
     current() = saved;
 }
