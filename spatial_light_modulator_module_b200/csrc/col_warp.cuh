@@ -225,7 +225,6 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS(32, 1) close_planes_kernel(ColGroupArgs ga, in
     const ColArgs& a = ga.c;
     const int b = blockIdx.x, lane = threadIdx.x;
     griddep_wait();
-    if (MODE == CGM_GD_PIPE && b == 0 && lane == 0) a.fused_count[(size_t)a.max_planes + 1] = 0u;    // the pass's tile counter
     PlaneStats* st = a.stats + b;
     if (!ga.all_planes && ld_cg(&st->done) != 0) return;         // the pass skipped this plane
     const Partial* plane_partials = a.partial + (size_t)b * tiles;
@@ -298,7 +297,9 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
             // max |F|^2 to its plane (atomic max, then the plane's arrival count) -- kept off the compute warps' path: a
             // round trip to L2 is a quarter of a tile's transform; (ii) the sums of a finished tile, as in the other modes.
             // (Watching the planes' arrival counts here as well, to spare group 1 its polling, made both duties late:
-            //  measured 0.251 instead of 0.238 ms per pass.)
+            //  measured 0.251 instead of 0.238 ms per pass.  Handing the tiles out on demand from a device counter instead
+            //  of the fixed order -- in case some CTAs were simply slower -- changed nothing: 0.2422 / 0.2445 against
+            //  0.2423 / 0.2444 ms; the CTAs drift apart by jitter, not by speed.)
             float* const fmx = reinterpret_cast<float*>(raw + G::OFF_FMX);
             unsigned kf = 0, kd = 0;             // next tile to hand its max over / to publish
             bool fend = false;                   // group 0 has reached the stop marker
@@ -424,21 +425,9 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
             }
             return p;
         };
-        // The tile after tile g for this CTA.  Fixed order: g + gridDim.x.  CGM_GD_PIPE with the planes closed behind the pass
-        // (ga.dynamic_tiles): the next tile nobody has claimed yet -- every plane is a barrier among the CTAs holding its
-        // tiles, so the pass runs at the pace of the slowest CTA of each step; handing the tiles out on demand lets the
-        // faster CTAs take more of them.  (The closing kernel re-arms the counter.)
-        unsigned* const tile_counter = a.fused_count + (size_t)a.max_planes + 1;
-        const bool dynamic_tiles = PIPE && ga.dynamic_tiles;
-        auto next_tile = [&](long long g) -> long long {
-            if (!dynamic_tiles) return g + gridDim.x;
-            unsigned v = 0;
-            if (lane == 0) v = atomic_add_u32(tile_counter, 1u);
-            return (long long)gridDim.x + shfl_idx(v, 0);
-        };
         // -> descriptor of the first tile at or after the candidate whose plane is still iterating (g = -1: none)
         auto resolve = [&](Peek p) {
-            while (p.g < total && p.done) p = peek(next_tile(p.g));       // finished planes rest (tolerance > 0 only)
+            while (p.g < total && p.done) p = peek(p.g + gridDim.x);      // finished planes rest (tolerance > 0 only)
             TileDesc d; d.g = p.g < total ? p.g : -1; d.scale = p.scale; d.imax = p.imax; d.norm = p.norm;
             return d;
         };
@@ -477,9 +466,8 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
             sync_warp();
             post(s, cur);
             ++k;
-            if (cur.g < 0) ++stops;
-            else if (!dynamic_tiles || k < (unsigned)NBUF) cur = resolve(peek(next_tile(cur.g)));   // (on demand: no tile is held back)
-            if (!dynamic_tiles) prefetch(cur);
+            if (cur.g < 0) ++stops; else cur = resolve(peek(cur.g + gridDim.x));
+            prefetch(cur);
         }
         // retire tile kd (store it), then reuse its buffer for item kd + NBUF
         for (unsigned kd = 0; kd < k - (unsigned)stops; ++kd) {              // k - stops = tiles issued so far
@@ -493,21 +481,8 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
                 tile_store(tm_out, tile_buf(s), (long long)b * H, H, (long long)tile * ROWB, ROWB, (int)sizeof(R));
                 tile_store_commit();
             }
-            if (stops < STOPS && dynamic_tiles) {
-                // Tiles on demand: the next one is claimed only now that this slot is certain to come free (its tile is
-                // done; the store and the publisher need nothing from other CTAs).  A tile claimed earlier and held back
-                // for want of a buffer could belong to the very plane the buffers' tiles are waiting for.
-                cur = resolve(peek(next_tile(0)));
-                prefetch(cur);
-                stage_grey(s, cur);
-                if (HAS_STATS) mbar_wait(bar(taken, s), par);
-                if (lane == 0) tile_store_wait_read();
-                sync_warp();
-                post(s, cur);
-                ++k;
-                if (cur.g < 0) ++stops;
-            } else if (stops < STOPS) {
-                const Peek ahead = peek(cur.g < 0 ? total : next_tile(cur.g));    // in flight during the staging below
+            if (stops < STOPS) {
+                const Peek ahead = peek(cur.g < 0 ? total : cur.g + gridDim.x);   // in flight during the staging below
                 stage_grey(s, cur);                                       // the group is through this slot's grey rows
                 if (HAS_STATS) mbar_wait(bar(taken, s), par);            // the publisher has this slot's descriptor and sums
                 SLM_STAMP(lane == 0, kd, 11);

@@ -229,8 +229,6 @@ static int launch_group(slm_ctx* c, int mode, int batch, const ColArgs* loop, co
     // keep the in-kernel closing, which costs no extra launch
     ga.defer_close = (mode != CGM_COMPLEX && mode != CGM_GD_FUSED && !getenv("SLM_NO_DEFER_CLOSE") &&
                       (long long)batch * (c->W / c->col->cols_per_cta) > 4LL * c->persist_ctas) ? 1 : 0;
-    static const bool fixed_order = getenv("SLM_PIPE_FIXED_ORDER") != nullptr;             // developer switch (A/B measurements)
-    ga.dynamic_tiles = (mode == CGM_GD_PIPE && ga.defer_close && !fixed_order) ? 1 : 0;
 #ifdef SLM_TRACE
     if (mode == g_trace_mode) { ga.trace = g_trace; g_trace_mode = -1; }      // trace the next launch of that mode only
 #endif
@@ -430,7 +428,7 @@ extern "C" int slm_ctx_create(slm_ctx** out, int device, int H, int W, int max_b
     A((void**)&c->stats, (size_t)max_batch * sizeof(PlaneStats));
     A((void**)&c->partial, (size_t)max_batch * tmax * sizeof(Partial));
     A((void**)&c->counter, (size_t)max_batch * sizeof(unsigned));
-    A((void**)&c->fused, (3 * (size_t)max_batch + 4) * sizeof(unsigned));
+    A((void**)&c->fused, 3 * (size_t)max_batch * sizeof(unsigned));
     A((void**)&c->norm, (size_t)max_batch * sizeof(double));
     A(&c->lut, 256 * real_size(precision));
     A((void**)&c->lut32, 256 * sizeof(float));
@@ -441,7 +439,7 @@ extern "C" int slm_ctx_create(slm_ctx** out, int device, int H, int W, int max_b
     if (!rc) rc = ensure_loops(c, 256);
     if (!rc) rc = setup_groups(c);
     if (!rc && cudaMemset(c->counter, 0, (size_t)max_batch * sizeof(unsigned)) != cudaSuccess) rc = fail(SLM_ERR_CUDA, "cudaMemset(counter)");
-    if (!rc && cudaMemset(c->fused, 0, (3 * (size_t)max_batch + 4) * sizeof(unsigned)) != cudaSuccess) rc = fail(SLM_ERR_CUDA, "cudaMemset(fused)");
+    if (!rc && cudaMemset(c->fused, 0, 3 * (size_t)max_batch * sizeof(unsigned)) != cudaSuccess) rc = fail(SLM_ERR_CUDA, "cudaMemset(fused)");
     if (!rc && cudaMemset(c->stats, 0, (size_t)max_batch * sizeof(PlaneStats)) != cudaSuccess) rc = fail(SLM_ERR_CUDA, "cudaMemset(stats)");
     if (rc) { std::string keep = g_err; slm_ctx_destroy(c); g_err = keep; return rc; }
     *out = c;
@@ -510,7 +508,7 @@ static int begin_run(slm_ctx* c, int batch, const double* norm, int max_loops) {
     choose_pdl(c, batch);
     SLM_TRY(ensure_loops(c, max_loops));
     SLM_CUDA(cudaMemsetAsync(c->stats, 0, (size_t)batch * sizeof(PlaneStats), c->stream));
-    if (c->fused) SLM_CUDA(cudaMemsetAsync(c->fused, 0, (3 * (size_t)c->max_batch + 4) * sizeof(unsigned), c->stream));
+    if (c->fused) SLM_CUDA(cudaMemsetAsync(c->fused, 0, 3 * (size_t)c->max_batch * sizeof(unsigned), c->stream));
     if (norm) SLM_CUDA(cudaMemcpyAsync(c->norm, norm, (size_t)batch * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     return 0;
 }

@@ -67,8 +67,7 @@ struct ColArgs {
     int skip_forward;        // col_pass_kernel<GD>: X already holds the column-transformed field (max pass with `keep`)
     unsigned* fused_max;     // CGM_GD_FUSED: [B] bit pattern of the running max |F|^2 of the plane (0 between launches)
     unsigned* fused_count;   // CGM_GD_FUSED: [B] tiles of the plane that have contributed (0 between launches)
-    int max_planes;          // stride of the two arrays above; fused_count[max_planes] is the pass's time-out flag,
-                             // fused_count[max_planes + 1] the tile counter of CGM_GD_PIPE (0 between launches)
+    int max_planes;          // stride of the two arrays above; fused_count[max_planes] is the pass's time-out flag
 };
 
 // ---- warp-specialised persistent column kernel (col_groups.cuh) ---------------------------------------
@@ -92,7 +91,6 @@ struct ColGroupArgs {
     int defer_close;         // 1: the pass only stores its tiles' partial sums; a one-warp-per-plane kernel launched behind it
                              // closes the planes' iteration (warp-per-column kernel, large batches: keeps fences and atomics
                              // out of the tile pipeline)
-    int dynamic_tiles;       // CGM_GD_PIPE with defer_close: tiles are claimed from a device counter instead of a fixed order
     double scale;            // CGM_COMPLEX: output scale
     unsigned long long* trace;   // -DSLM_TRACE builds: [ctas][64 tiles][16 events] globaltimer stamps, else null
     ColArgs c;               // loop arguments; B, W, stats, partial, counter, norm, tw are used by every mode
