@@ -168,6 +168,9 @@ int slm_transpose_blocks_peer(slm_ctx* ctx, const void* in, const void* const* p
 /* Strided device-to-device copy on the context's stream (cudaMemcpy2DAsync): `rows` runs of width_bytes.  dst may be
  * peer memory; the copy engines move the blocks while the SMs compute (the slab path's overlapped exchange). */
 int slm_copy2d_async(slm_ctx* ctx, void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows);
+/* n such copies of one geometry (one block per peer) in one call. */
+int slm_copy2d_multi(slm_ctx* ctx, int n, void* const* dst, const void* const* src, size_t dst_pitch, size_t src_pitch,
+                     size_t width_bytes, size_t rows);
 
 /* error_evolution and its length per plane (algorithms.py:25,39,93) of the last run.
  * err: host double[batch][max_loops]; iters: host int[batch].  Synchronises the stream. */

@@ -48,6 +48,7 @@ SIGNATURES = {
     "slm_rows_close": (_i, [_vp, _vp, _i, _d, _d, _i, _d, _vp, _vp]),
     "slm_transpose_blocks": (_i, [_vp, _vp, _vp, _i, _i, _i, _i]),
     "slm_copy2d_async": (_i, [_vp, _vp, C.c_size_t, _vp, C.c_size_t, C.c_size_t, C.c_size_t]),
+    "slm_copy2d_multi": (_i, [_vp, _i, _vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t]),
     "slm_transpose_blocks_peer": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i]),
     "slm_read_curves": (_i, [_vp, _i, _i, _dp, _ip]),
     "slm_expected_outcome": (_i, [_vp, _i, _vp, _dp, _vp]),

@@ -986,6 +986,13 @@ extern "C" int slm_copy2d_async(slm_ctx* c, void* dst, size_t dst_pitch, const v
     return 0;
 }
 
+extern "C" int slm_copy2d_multi(slm_ctx* c, int n, void* const* dst, const void* const* src, size_t dst_pitch, size_t src_pitch,
+                                size_t width_bytes, size_t rows) {
+    if (!c || n < 0 || (n && (!dst || !src))) return fail(SLM_ERR_ARG, "slm_copy2d_multi: bad argument");
+    for (int i = 0; i < n; ++i) SLM_TRY(slm_copy2d_async(c, dst[i], dst_pitch, src[i], src_pitch, width_bytes, rows));
+    return 0;
+}
+
 extern "C" int slm_transpose_blocks(slm_ctx* c, const void* in, void* out, int rows, int W, int elem_bytes, int from_exchange) {
     if (!c || !in || !out || in == out) return fail(SLM_ERR_ARG, "slm_transpose_blocks: bad argument");
     if (rows < 32 || rows % 32 || W % rows) return fail(SLM_ERR_SHAPE, "slm_transpose_blocks: rows must be a multiple of 32 dividing W");

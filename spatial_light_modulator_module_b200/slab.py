@@ -268,21 +268,28 @@ class SlabEngine(Engine):
         back: [q][c in part][i] -- one contiguous run)."""
         h = self.rows
         B = self._peer["comm_stream"]
-        lanes = [(B, self._peer["comm_ctx"])] + self._peer["lanes"]     # copies to different peers on different streams: several
-        for st, _ in lanes[1:]:                                          # copy engines at once; all of them start behind B ...
+        lanes = [(B, self._peer["comm_ctx"])] + self._peer["lanes"]     # (optionally copies to different peers on different streams)
+        for st, _ in lanes[1:]:
             self._after(st, B)
         base = self._mem_ptr(src_buf).value
         dst_off = self._peer["offs"][dst_name]
+        off = (first if rows_part else first * h)
+        per_lane = [([], []) for _ in lanes]
         for d in range(1, self.world + 1):                         # start with the neighbour: the ranks do not all hit rank 0 first
             q = (self.rank + d) % self.world
-            ctx = lanes[d % len(lanes)][1]
-            src = base + (q * h * h + (first if rows_part else first * h)) * cs
-            dst = self._peer["ptrs"][q] + dst_off + (self.rank * h * h + (first if rows_part else first * h)) * cs
+            dsts, srcs = per_lane[d % len(lanes)]
+            srcs.append(base + (q * h * h + off) * cs)
+            dsts.append(self._peer["ptrs"][q] + dst_off + (self.rank * h * h + off) * cs)
+        for (_, ctx), (dsts, srcs) in zip(lanes, per_lane):
+            if not dsts:
+                continue
+            n = len(dsts)
+            da, sa = (C.c_void_p * n)(*dsts), (C.c_void_p * n)(*srcs)
             if rows_part:
-                self._check(self._lib.slm_copy2d_async(ctx, C.c_void_p(dst), h * cs, C.c_void_p(src), h * cs, count * cs, h))
+                self._check(self._lib.slm_copy2d_multi(ctx, n, da, sa, h * cs, h * cs, count * cs, h))
             else:
-                self._check(self._lib.slm_copy2d_async(ctx, C.c_void_p(dst), count * h * cs, C.c_void_p(src), count * h * cs, count * h * cs, 1))
-        for st, _ in lanes[1:]:                                          # ... and B goes on behind all of them
+                self._check(self._lib.slm_copy2d_multi(ctx, n, da, sa, count * h * cs, count * h * cs, count * h * cs, 1))
+        for st, _ in lanes[1:]:
             self._after(B, st)
 
     def _pack_ptrs(self, S):
@@ -409,7 +416,7 @@ class SlabEngine(Engine):
                 self._close(partial, mine, gathered, norm, hw, False, tolerance, state, curve)
                 self._exchange_back(S, Rv, cur, cs, "X" if cur is X else "Y") # D with the columns inverse-transformed
             src, field, done_iters = cur, 0, k + 1
-            if check_every or k == 0:                                         # (k == 0: an all-zero target ends the loop at once, algorithms.py:29)
+            if check_every or (k == 0 and not norm > 0):                      # (an all-zero target ends the loop at once: 0/0, algorithms.py:29,37)
                 st = self.to_host(state)
                 if st[3] != 0.0:
                     break
