@@ -48,6 +48,20 @@ template <typename R, int H> struct ColWarpGeom {
     static_assert(!OK || SMEM <= 232448, "shared memory budget");
 };
 
+// Per-plane state of the one-pass GD forms in global memory: one 64-bit word per plane, low half = bit pattern of the
+// running max |F|^2, high half = tiles that have contributed -- so that ONE load tells a waiting tile both whether its
+// plane is complete and what the max is (a round trip to L2 less on its critical path).  Contributors update the max,
+// fence, then the count; word [max_planes] is the passes' time-out flag.
+SLM_DEV unsigned* plane_max_word(const ColArgs& a, int b) { return a.fused_max + 2 * (size_t)b; }
+SLM_DEV unsigned* plane_count_word(const ColArgs& a, int b) { return a.fused_max + 2 * (size_t)b + 1; }
+SLM_DEV unsigned* plane_timeout_flag(const ColArgs& a) { return a.fused_max + 2 * (size_t)a.max_planes; }
+// -> true when every tile of the plane has contributed; max_bits then holds the plane's max
+SLM_DEV bool plane_complete(const ColArgs& a, int b, int tiles, unsigned& max_bits) {
+    const unsigned long long w = ld_acquire_u64(reinterpret_cast<const unsigned long long*>(plane_max_word(a, b)));
+    max_bits = (unsigned)w;
+    return (unsigned)(w >> 32) >= (unsigned)tiles;
+}
+
 // What the sequencer tells the other warps about the tile in a buffer.
 struct TileDesc { long long g; double scale, imax, norm; };      // g < 0: no more tiles
 
@@ -205,9 +219,9 @@ SLM_DEV void close_plane(const ColArgs& a, int b, const Partial& tot, double s0,
     } else {
         err = tot.a / hw;                                // algorithms.py:92
         if (MODE == CGM_GD_FUSED || MODE == CGM_GD_PIPE) {   // every tile of the plane has used the max: record and re-arm
-            const double pm = (double)__uint_as_float(ld_cg(a.fused_max + b));
+            const double pm = (double)__uint_as_float(ld_cg(plane_max_word(a, b)));
             st->imax = pm; st->scale = norm / pm;
-            a.fused_max[b] = 0u; a.fused_count[b] = 0u;
+            *plane_max_word(a, b) = 0u; *plane_count_word(a, b) = 0u;
         }
     }
     const int it = st->iters;
@@ -334,9 +348,9 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
                         float mm = fmx[s * (TC + 2)];
 #pragma unroll
                         for (int i = 1; i < TC; ++i) mm = fmax(mm, fmx[s * (TC + 2) + i]);
-                        atomic_max_u32(a.fused_max + b, __float_as_uint(mm));       // |F|^2 >= 0: ordered like its bit pattern
+                        atomic_max_u32(plane_max_word(a, b), __float_as_uint(mm));  // |F|^2 >= 0: ordered like its bit pattern
                         fence_device();
-                        atomic_add_u32(a.fused_count + b, 1u);
+                        atomic_add_u32(plane_count_word(a, b), 1u);
                     }
                     ++kf;
                 }
@@ -578,11 +592,12 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
                 // the plane's other tiles: counted already, or being transformed on other SMs right now (cooperative
                 // launch: every CTA is resident).  The time-out only guards against a broken launch.
                 const long long t0 = clock_now();
-                while (ld_acquire(a.fused_count + b) < (unsigned)tiles) {
+                unsigned max_bits;
+                while (!plane_complete(a, b, tiles, max_bits)) {
                     spin_pause();
-                    if (clock_now() - t0 > (1ll << 32)) { atomic_max_u32(a.fused_count + (size_t)a.max_planes, 1u); break; }
+                    if (clock_now() - t0 > (1ll << 32)) { atomic_max_u32(plane_timeout_flag(a), 1u); break; }
                 }
-                fmx[s * (TC + 2) + TC] = __uint_as_float(ld_cg(a.fused_max + b));
+                fmx[s * (TC + 2) + TC] = __uint_as_float(max_bits);
             }
             sync_named(10, G::GROUP_THREADS);
             SLM_STAMP(t == G::GROUP_THREADS, k, 6);
@@ -668,17 +683,18 @@ col_warp_kernel(ColGroupArgs ga, const SLM_GRID_CONSTANT TileMap tm_in, const SL
                 float mm = fmx[0];
 #pragma unroll
                 for (int i = 1; i < TC; ++i) mm = fmax(mm, fmx[i]);
-                atomic_max_u32(a.fused_max + b, __float_as_uint(mm));       // |F|^2 >= 0: ordered like its bit pattern
+                atomic_max_u32(plane_max_word(a, b), __float_as_uint(mm));  // |F|^2 >= 0: ordered like its bit pattern
                 fence_device();
-                atomic_add_u32(a.fused_count + b, 1u);
+                atomic_add_u32(plane_count_word(a, b), 1u);
                 // the plane's other tiles are in flight on other SMs; should they not be (the CTAs of this launch not all
                 // resident: a foreign kernel holding SMs for good), give up after ~2 s with the error flag set instead of
                 // hanging the device
                 const long long t0 = clock_now();
-                while (ld_acquire(a.fused_count + b) < (unsigned)tiles) {
-                    if (clock_now() - t0 > (1ll << 32)) { atomic_max_u32(a.fused_count + (size_t)a.max_planes, 1u); break; }
+                unsigned max_bits;
+                while (!plane_complete(a, b, tiles, max_bits)) {
+                    if (clock_now() - t0 > (1ll << 32)) { atomic_max_u32(plane_timeout_flag(a), 1u); break; }
                 }
-                fmx[TC] = __uint_as_float(ld_cg(a.fused_max + b));
+                fmx[TC] = __uint_as_float(max_bits);
             }
             sync_named(9 + grp, G::GROUP_THREADS);
             plane_max = (double)fmx[TC];

@@ -44,7 +44,7 @@ struct slm_ctx {
     PlaneStats* stats = nullptr;
     Partial* partial = nullptr;
     unsigned* counter = nullptr;
-    unsigned* fused = nullptr;                            // [3][max_batch]: plane max bits, tile count of CGM_GD_FUSED, [0] of the third row: time-out flag
+    unsigned* fused = nullptr;                            // [max_batch] pairs {plane max bits, tile count} of the one-pass GD forms + time-out flag
     int fused_ctas = 0;                                   // grid of the fused GD column pass (0: two passes)
     bool pipe_ok = false;                                 // CGM_GD_PIPE may be used (warp-per-column kernel, a plane's tiles fit the CTAs' buffers)
     double *err_curve = nullptr, *lr = nullptr, *norm = nullptr;
@@ -234,7 +234,7 @@ static int launch_group(slm_ctx* c, int mode, int batch, const ColArgs* loop, co
 #endif
     ga.c.B = batch; ga.c.W = c->W; ga.c.stats = c->stats; ga.c.partial = c->partial; ga.c.counter = c->counter;
     ga.c.norm = c->norm; ga.c.tw = c->tw_col;
-    ga.c.fused_max = c->fused; ga.c.fused_count = c->fused + c->max_batch; ga.c.max_planes = c->max_batch;
+    ga.c.fused_max = c->fused; ga.c.max_planes = c->max_batch;
     int ctas = mode == CGM_GD_FUSED ? c->fused_ctas : c->persist_ctas;
     if (mode == CGM_GD_PIPE) {
         static const char* pc = getenv("SLM_PIPE_CTAS");         // developer switch (A/B measurements)
@@ -1016,7 +1016,7 @@ extern "C" int slm_read_curves(slm_ctx* c, int batch, int max_loops, double* err
     SLM_CUDA(cudaMemcpyAsync(st.data(), c->stats, (size_t)batch * sizeof(PlaneStats), cudaMemcpyDeviceToHost, c->stream));
     if (err) SLM_CUDA(cudaMemcpyAsync(err, c->err_curve, (size_t)batch * max_loops * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     unsigned timed_out = 0;
-    if (c->fused) SLM_CUDA(cudaMemcpyAsync(&timed_out, c->fused + 2 * (size_t)c->max_batch, sizeof timed_out, cudaMemcpyDeviceToHost, c->stream));
+    if (c->fused) SLM_CUDA(cudaMemcpyAsync(&timed_out, c->fused + 2 * (size_t)c->max_batch, sizeof timed_out, cudaMemcpyDeviceToHost, c->stream));   // (the flag behind the pairs)
     SLM_CUDA(cudaStreamSynchronize(c->stream));
     if (timed_out) return fail(SLM_ERR_CUDA, "the fused Fourier-plane pass timed out waiting for the tiles of a plane (its CTAs were not all "
                                              "resident: is another kernel holding SMs?); set SLM_NO_FUSED_GD=1");

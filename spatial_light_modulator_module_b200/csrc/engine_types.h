@@ -65,9 +65,9 @@ struct ColArgs {
     double inv_hw;
     const void* tw;          // complex<R> [H] column twiddles
     int skip_forward;        // col_pass_kernel<GD>: X already holds the column-transformed field (max pass with `keep`)
-    unsigned* fused_max;     // CGM_GD_FUSED: [B] bit pattern of the running max |F|^2 of the plane (0 between launches)
-    unsigned* fused_count;   // CGM_GD_FUSED: [B] tiles of the plane that have contributed (0 between launches)
-    int max_planes;          // stride of the two arrays above; fused_count[max_planes] is the pass's time-out flag
+    unsigned* fused_max;     // one-pass GD forms: [max_planes] pairs {bit pattern of the plane's running max |F|^2, tiles that have
+                             // contributed} (8-byte aligned, 0 between launches) + the time-out flag behind them (col_warp.cuh)
+    int max_planes;
 };
 
 // ---- warp-specialised persistent column kernel (col_groups.cuh) ---------------------------------------

@@ -267,6 +267,7 @@ inline unsigned atomic_inc_wrap(unsigned* p, unsigned limit) { unsigned o = *p; 
 inline unsigned atomic_max_u32(unsigned* p, unsigned v) { emu::S().progress++; unsigned o = *p; if (v > o) *p = v; return o; }
 inline unsigned atomic_add_u32(unsigned* p, unsigned v) { emu::S().progress++; unsigned o = *p; *p = o + v; return o; }
 inline unsigned ld_acquire(const unsigned* p) { return *p; }
+inline unsigned long long ld_acquire_u64(const unsigned long long* p) { return *p; }
 inline long long clock_now() { return 0; }
 inline void spin_pause() { emu::yield(); }          // a wait on another CTA's progress: let the other fibres / CTAs run
 }  // namespace slm
