@@ -559,6 +559,12 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), (RowGeom<R, W>::MIN_
     const cpx<R>* in = static_cast<const cpx<R>*>(a.in);
     const R* lut = static_cast<const R*>(a.lut);
     const LineLayout lay = line_layout<M>(a.block_w, a.rows, W, row, j);
+    // the amplitude table in shared memory, the scale in a register: asked for here, needed after the first transform
+    // (one CTA per SM and nothing to hide a global load behind)
+    SLM_STATIC_SMEM R lut_s[256];
+    for (int i = t; i < 256; i += G::THREADS) lut_s[i] = ld_ro(lut + i);
+    const R s0r = (R)(a.s0_dev ? ld_cg(a.s0_dev) : a.s0);
+    sync_cta();
     cpx<R> v[E];
     unsigned grey4[(E + 3) / 4];                              // the points' grey levels, four to a register (they wait through a transform)
 #pragma unroll
@@ -569,13 +575,12 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), (RowGeom<R, W>::MIN_
     });
     line_fft<R, W, -1, 1>(v, line, j, tw, sync);              // second half of C = fft2(B)
     R mx = 0, sa = 0, sb = 0, sc = 0;
-    const R s0r = (R)(a.s0_dev ? ld_cg(a.s0_dev) : a.s0);
     if (a.intensity) each_point<E, M>(lay, [&](int r, unsigned off) { a.intensity[off] = (double)cnorm2(v[r]); });
 #pragma unroll
     for (int r = 0; r < E; ++r) {
         const R m2 = cnorm2(v[r]);
         const int grey = (int)((grey4[r / 4] >> (8 * (r % 4))) & 0xffu);
-        const R amp = ld_ro(lut + grey);
+        const R amp = lut_s[grey];
         const R u = s0r * m2, d = u - (R)grey;
         mx = fmax(mx, m2); sa += d * d; sb += d * u; sc += u * u;
         v[r] = (m2 == (R)0) ? mk<R>(copysign(amp, v[r].x), (R)0) : cscale(v[r], amp * rsqrt_fast(m2));   // algorithms.py:33
