@@ -63,6 +63,7 @@ def parse():
     p.add_argument("--cpu-loops", type=int, default=40, help="iterations of the CPU baseline sample")
     p.add_argument("--only", default="", help="comma-separated sections (default: all): " + ",".join(ALL_SECTIONS))
     p.add_argument("--movie-frames", type=int, default=1024)
+    p.add_argument("--movie-batch", type=int, default=32, help="frames per device batch of config3")
     p.add_argument("--config4-targets", type=int, default=256)
     p.add_argument("--slab-size", type=int, default=16384)
     p.add_argument("--workload", default="batch", choices=["batch", "slab"],
@@ -607,13 +608,19 @@ def run_config3(h, a):
         src = None if "trap_dots" in kw else frames
 
         def once():
-            return ghs.sequence_holograms(src, loops, precision="fp32", batch=32, gather=True, **kw)
+            return ghs.sequence_holograms(src, loops, precision="fp32", batch=a.movie_batch, gather=True, **kw)
         s, out = h.wall_steps(once, 2, 2)          # (two warm-ups: the result of call k is alive while call k+1 allocates its own)
         per_frame = shape[0] * shape[1] * (1 if kw["output"] == "uint8" else 8)
         rec[name] = {"holograms_per_s": frames_n / s, "iterations_per_s": frames_n * loops / s, "seconds": s,
                      "h2d_bytes": 0 if src is None else int(frames.nbytes), "d2h_bytes": frames_n * per_frame,
                      "gathered_bytes": 0 if h.world == 1 else frames_n * per_frame * (h.world - 1) // h.world,
                      "final_error_frame0": float(out[2][0][-1]) if env_rank()[0] == 0 else None}
+    # the loop of the same workload alone, device resident, with its kernels' rooflines
+    peak, peak_src = measured_peak()
+    dev_rec, st = batched_loop_record(h, a, "gs", "fp32", shape, 32, loops, 3, 3, peak, peak_src)
+    st["eng"].close()
+    dev_rec["workload"] = f"gerchberg_saxton {shape[0]}x{shape[1]} (the SLM shape), batch 32/GPU, {loops} iterations, fp32, device resident (noise targets)"
+    rec["device_resident_loop"] = dev_rec
     rec["note"] = ("timed region: host uint8 frames -> device, 50 iterations per frame, mask add + quantisation (uint8 variants), device-to-device "
                    "gather on rank 0 (NCCL) and the read-back into page-locked host memory; float64 results are bounded by rank 0's PCIe link "
                    "(6 MiB per frame), uint8 SLM frames are what display_holograms.py:253-266 consumes")
