@@ -63,7 +63,7 @@ def parse():
     p.add_argument("--cpu-loops", type=int, default=40, help="iterations of the CPU baseline sample")
     p.add_argument("--only", default="", help="comma-separated sections (default: all): " + ",".join(ALL_SECTIONS))
     p.add_argument("--movie-frames", type=int, default=1024)
-    p.add_argument("--movie-batch", type=int, default=64, help="frames per device batch of config3 (64: +5 % over 32)")
+    p.add_argument("--movie-batch", type=int, default=0, help="frames per device batch of config3 (0: the driver's own choice)")
     p.add_argument("--config4-targets", type=int, default=256)
     p.add_argument("--slab-size", type=int, default=16384)
     p.add_argument("--workload", default="batch", choices=["batch", "slab"],
@@ -608,7 +608,7 @@ def run_config3(h, a):
         src = None if "trap_dots" in kw else frames
 
         def once():
-            return ghs.sequence_holograms(src, loops, precision="fp32", batch=a.movie_batch, gather=True, **kw)
+            return ghs.sequence_holograms(src, loops, precision="fp32", batch=a.movie_batch or None, gather=True, **kw)
         s, out = h.wall_steps(once, 2, 2)          # (two warm-ups: the result of call k is alive while call k+1 allocates its own)
         per_frame = shape[0] * shape[1] * (1 if kw["output"] == "uint8" else 8)
         rec[name] = {"holograms_per_s": frames_n / s, "iterations_per_s": frames_n * loops / s, "seconds": s,

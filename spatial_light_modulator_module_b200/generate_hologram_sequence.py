@@ -27,7 +27,7 @@ def _dist():
 
 
 def sequence_holograms(frames, max_loops: int, tolerance: float = 0.0, precision: str = "fp32",
-                       batch: int = 64, want_expected: bool = False, engine_factory: Optional[Callable] = None,
+                       batch: Optional[int] = None, want_expected: bool = False, engine_factory: Optional[Callable] = None,
                        gather: bool = True, inc_amp=None, warm_start: bool = False, output: str = "float64",
                        mask=None, ct2pi=256, trap_dots=None, on_batch: Optional[Callable] = None):
     """GS holograms of ``frames`` (uint8 [F,H,W], a host array or a device tensor); ``inc_amp``: illumination amplitude
@@ -74,7 +74,11 @@ def sequence_holograms(frames, max_loops: int, tolerance: float = 0.0, precision
     n_local = hi - lo
     blocks = [hl.shard_range(n_frames, r, world) for r in range(world)]
     n_max = max(h - l for l, h in blocks)
-    batch = max(1, min(batch, max(n_max, 1)))
+    if batch is None:
+        # 64 frames per launch sequence are 5 % faster than 32, but a rank wants at least four batches so that the gather
+        # and the read-back of one batch hide behind the iterations of the next
+        batch = min(64, max(16, n_max // 4))
+    batch = max(1, min(int(batch), max(n_max, 1)))
     if engine_factory is None:
         from .engine import get_engine
         eng = get_engine(shape, precision, batch)
@@ -260,7 +264,7 @@ def generate_hologram_sequence(args):
 
     _, _, errors, _ = sequence_holograms(
         frames, int(args.max_loops), float(args.tolerance), getattr(args, "precision", None) or
-        os.environ.get("SLM_PRECISION", "fp32"), int(getattr(args, "batch", 64)), bool(args.preview), gather=False,
+        os.environ.get("SLM_PRECISION", "fp32"), getattr(args, "batch", None), bool(args.preview), gather=False,
         inc_amp=inc, on_batch=write)
     plot_error_evolution([list(e) for e in errors])
     return errors
@@ -292,7 +296,7 @@ def build_parser():
     p.add_argument("-tol", "--tolerance", metavar="FLOAT", default=0, type=float, help="stop when the error falls to this value")
     p.add_argument("-loops", "--max_loops", metavar="INT", default=5, type=int, help="upper bound on the number of iterations")
     p.add_argument("-p", "--preview", action="store_true", help="also write the expected images of the holograms")
-    p.add_argument("--batch", type=int, default=64, help="frames per device batch")
+    p.add_argument("--batch", type=int, default=None, help="frames per device batch (default: chosen from the number of frames)")
     p.add_argument("--precision", default=None, choices=["fp32", "fp64"], help="engine arithmetic (default fp32)")
     return p
 
