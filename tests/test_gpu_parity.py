@@ -236,6 +236,60 @@ def test_gs_invariants_1024():
     assert set(map(tuple, np.argwhere(t == 255))) == set(zip(*np.unravel_index(top, t.shape)))
 
 
+def test_graph_replay_gives_the_same_results():
+    """Loops are replayed from CUDA graphs: a small run is launched plainly the first time, recorded the second time its
+    arguments are seen and replayed from the kept graph afterwards; a large batch records 20 iterations per graph.  Same
+    bits and the same launch count every time, and the same as with SLM_NO_GRAPH=1 (child process)."""
+    import os, subprocess, sys, tempfile
+    import torch
+    shape = (1024, 1024)
+    t = synthetic.noise_target(shape, seed=4)
+    x0 = hl.host_initial_guess("random", shape, 42).astype(np.complex64)
+    during, _ = hl.learning_rate_schedule(0.005, 0, 12)
+    eng = make_engine(shape, "fp32", 8)
+    td = torch.from_numpy(t[None]).cuda()
+    x0d = torch.from_numpy(x0[None]).cuda()
+    x = torch.empty_like(x0d)
+    runs = []
+    for rep in range(4):                       # same device buffers every time: plain, recorded, replayed, replayed
+        x.copy_(x0d)
+        n0 = eng.launch_count()
+        res, _ = eng.gd(td, x, during, 12, norms=np.array([float(t.max())]))
+        runs.append((res.errors[0].copy(), eng.to_host(res.hologram).copy(), eng.launch_count() - n0))
+        g = eng.gs(td, 12, norms=np.array([float(t.max())]))
+        runs[-1] += (g.errors[0].copy(), eng.to_host(g.hologram).copy())
+        del res, g
+    for r in runs[1:]:
+        np.testing.assert_array_equal(r[0], runs[0][0])
+        np.testing.assert_array_equal(r[1], runs[0][1])
+        assert r[2] == runs[0][2]
+        np.testing.assert_array_equal(r[3], runs[0][3])
+        np.testing.assert_array_equal(r[4], runs[0][4])
+    # a batch (graphs of 20 iterations + a remainder launched plainly) against the same batch without graphs
+    tb = np.stack([synthetic.noise_target(shape, seed=10 + i) for i in range(8)])
+    during50, _ = hl.learning_rate_schedule(0.005, 0, 50)
+    xb = np.stack([x0] * 8)
+    res, _ = eng.gd(tb, xb, during50, 50)
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "from spatial_light_modulator_module_b200.engine import Engine\n"
+        "from spatial_light_modulator_module_b200 import synthetic, host_logic as hl\n"
+        "shape=(1024,1024); eng=Engine(shape,'fp32',8)\n"
+        "tb=np.stack([synthetic.noise_target(shape,seed=10+i) for i in range(8)])\n"
+        "x0=hl.host_initial_guess('random',shape,42).astype(np.complex64)\n"
+        "during,_=hl.learning_rate_schedule(0.005,0,50)\n"
+        "r,_=eng.gd(tb,np.stack([x0]*8),during,50)\n"
+        "np.savez(sys.argv[1], e=np.array(r.errors), h=eng.to_host(r.hologram))\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "plain.npz")
+        subprocess.run([sys.executable, "-c", code, path], check=True, env={**os.environ, "SLM_NO_GRAPH": "1"}, timeout=600)
+        plain = dict(np.load(path))
+    np.testing.assert_array_equal(np.array(res.errors), plain["e"])
+    np.testing.assert_array_equal(eng.to_host(res.hologram), plain["h"])
+    eng.close()
+
+
 def test_batched_equals_single_1024():
     eng = make_engine((768, 1024), "fp32", 4)
     frames = synthetic.movie_frames(4)
