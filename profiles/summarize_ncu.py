@@ -41,9 +41,14 @@ def main(path):
             kernels.append(cur)
         elif cur is not None:
             cur["rows"].append(r)
+    seen = set()
     for kd in kernels:
         if not kd["rows"]:
             continue
+        fingerprint = (kd["name"], tuple(tuple(r[:4]) for r in kd["rows"][:40]))       # (ncu lists a launch's source page more than once)
+        if fingerprint in seen:
+            continue
+        seen.add(fingerprint)
         h = kd["rows"][0]
         data = [r for r in kd["rows"][1:] if len(r) >= len(h) - 2]
         i_s, i_src = h.index("# Samples"), h.index("Source")
