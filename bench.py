@@ -550,9 +550,13 @@ def run_b200(a):
     cpu = None
     if "cpu" in only and rank == 0:
         v, dt = cpu_port_iterations_per_s(a.alg, shape, min(a.cpu_loops, a.loops), 1)
+        cores = os.cpu_count() or 1
+        v_all, dt_all = cpu_port_iterations_per_s(a.alg, shape, min(a.cpu_loops, a.loops), cores)
         cpu = {"value": v, "unit": "iterations/s", "cores": 1, "kind": "port",
                "sample": f"1 hologram x {min(a.cpu_loops, a.loops)} iterations of oracle/numpy_port.py ({dt:.1f} s), "
-                         f"scipy.fft workers=1 as in the reference; host has {os.cpu_count()} cores"}
+                         f"scipy.fft workers=1 as in the reference; host has {cores} cores",
+               "all_cores": {"value": v_all, "cores": cores, "sample": f"the same with scipy.fft workers={cores} ({dt_all:.1f} s); numpy's "
+                                                                       "elementwise work stays on one core"}}
     line["cpu_baseline"] = cpu
     line["configs"] = configs
     if rank == 0:
