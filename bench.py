@@ -22,7 +22,8 @@ warm-up, max over ranks):
               and gathered on rank 0 inside the timed region (strong scaling)
     config4   compare_error_evolution_algorithms shape: 256 targets x 2048^2, GD then GS, 50 iterations, all 512 curves
               (targets sharded over the ranks)
-    config5   one 16384^2 GS hologram, 20 iterations, slab-decomposed over the ranks (1 GPU: the same code, world = 1)
+    config5   one 16384^2 GS hologram, 20 iterations, slab-decomposed over the ranks (1 GPU: the same code, world = 1);
+              config5_gd: the same plane through gradient descent
     size_4096 GD and GS at 4096^2 (the upper end of the north star's range)
 
 `--impl reference` times the CPU implementation (the oracle's numpy restatement of the reference, scipy.fft with all
@@ -518,6 +519,7 @@ def run_b200(a):
         configs["config4"] = run_config4(h, a, local_rank, peak)
     if "config5" in only:
         configs["config5"] = run_config5(h, a.slab_size, 20, "fp32", 2, 1, peak)
+        configs["config5_gd"] = run_config5(h, a.slab_size, 20, "fp32", 2, 1, peak, alg="gd")
 
     # ---- end to end through the drop-in API with host buffers, every rank at once -------------------------------------
     if "e2e" in only:
@@ -667,35 +669,46 @@ def run_config4(h, a, local_rank, peak):
             "gd_curve0_decreasing": bool(gd[0][-1] < gd[0][0]) if len(gd) else None}
 
 
-def run_config5(h, n, loops, precision, steps, warmup, peak):
-    """BASELINE configs[4]: one n x n GS hologram, slab-decomposed over the ranks (strong scaling)."""
+def run_config5(h, n, loops, precision, steps, warmup, peak, alg="gs"):
+    """BASELINE configs[4]: one n x n GS hologram, slab-decomposed over the ranks (strong scaling); ``alg="gd"``: the
+    same plane through gradient descent (algorithms.py:60-112), whose Fourier plane is passed twice per iteration."""
     import torch
+    from spatial_light_modulator_module_b200 import host_logic as hl
     from spatial_light_modulator_module_b200.slab import SlabEngine
     rank, world = env_rank()[0], h.world
     rows = n // world
     eng = SlabEngine(n, world, rank, precision)
     slab = eng._mem_upload((np.random.default_rng(100 + rank).random((rows, n)) * 255).astype(np.uint8))   # resident in HBM
     state = {}
+    if alg == "gd":
+        u = eng._mem_upload(np.random.default_rng(200 + rank).random((rows, n)))
+        x0 = eng._mem_empty((rows, n), eng.complex_dtype)
+        eng._check(eng._lib.slm_random_phasor(eng._ctx, eng._mem_ptr(u), eng._mem_ptr(x0), rows * n, 1.0))
+        del u
+        run = lambda k: eng.gd(slab, x0, hl.learning_rate_schedule(0.005, 0, k)[0], k, want_expected=False, on_device=True)
+    else:
+        run = lambda k: eng.gs(slab, k, want_expected=False, on_device=True)
 
     def step():
-        state["out"] = eng.gs(slab, loops, want_expected=False, on_device=True)
+        state["out"] = run(loops)
         return state["out"][0]
     for _ in range(warmup):
-        eng.gs(slab, 2, want_expected=False, on_device=True)
+        state["out"] = run(2)                      # (kept alive like a timed step's result: see Harness.time_steps)
     n0 = eng.launch_count()
-    ms, _, _ = h.time_steps(step, 0, steps)
+    ms, step_ms, _ = h.time_steps(step, 0, steps)
     launches = eng.launch_count() - n0
     errs = state["out"][2]
-    c = 8 if precision == "fp32" else 16
-    it_bytes = (8 * c + 4) * n * n
+    it_bytes = survey_bytes_per_px(alg, precision) * n * n          # SURVEY 8(d)'s four-pass model (the exchanges are not in it)
     per_it = ms * 1e-3 / (steps * loops)
     eng.close()
     del slab
     torch.cuda.empty_cache()
-    return {"workload": f"gerchberg_saxton, one {n}x{n} uint8 noise target, {loops} iterations incl. setup and the final hologram, rows split over "
-                        f"{world} GPU(s), 2 all-to-alls + 1 all-reduce per iteration (BASELINE.json configs[4])",
-            "value": 1.0 / per_it, "unit": "iterations/s", "scaling": "strong", "ms_per_hologram": ms / steps, "gpu_launches": int(launches),
-            "final_error": float(errs[-1]), "iterations": len(errs),
+    what = ("gerchberg_saxton", "2 all-to-alls + 1 all-reduce", "BASELINE.json configs[4]") if alg == "gs" else \
+        ("gradient_descent", "2 all-to-alls + 2 all-reduces", "the plane of configs[4] through the other algorithm")
+    return {"workload": f"{what[0]}, one {n}x{n} uint8 noise target, {loops} iterations incl. setup and the final hologram, rows split over "
+                        f"{world} GPU(s), {what[1]} per iteration ({what[2]})",
+            "value": 1.0 / per_it, "unit": "iterations/s", "scaling": "strong", "ms_per_hologram": ms / steps, "step_ms": step_ms,
+            "gpu_launches": int(launches), "final_error": float(errs[-1]), "iterations": len(errs),
             "iteration_roofline": {"survey_bytes_per_iteration": it_bytes, "achieved_gbs_per_gpu": it_bytes / per_it / 1e9 / world,
                                    "frac": it_bytes / per_it / 1e9 / world / peak, "peak": peak, "unit": "GB/s per GPU"}}
 

@@ -149,10 +149,26 @@ int slm_rows_reduce(slm_ctx* ctx, const double* partial, int rows, double* out4,
                     int n_peers, int self);
 /* Close one GS iteration of the distributed plane from every rank's four numbers (gathered: device double[world][4],
  * rank order): scale = norm / max (algorithms.py:37), error (algorithms.py:38,162) appended to err_curve (device),
- * loop condition (algorithms.py:29).  state: device double[4] = {scale (in: the one the pass used; out: the new one),
- * last error, iterations done, loop-ended flag}.  prepass != 0: only the scale (exact scale of iteration 0). */
-int slm_rows_close(slm_ctx* ctx, const double* gathered, int world, double norm, double hw, int prepass, double tolerance,
+ * loop condition (algorithms.py:29).  state: device double[8] = {scale (in: the one the pass used; out: the new one),
+ * last error, iterations done, loop-ended flag, max |C|^2, -, -, -}.  form 0: a GS iteration; 1: only scale and max (the
+ * exact scale of GS iteration 0, the max pass of a GD iteration); 2: a GD iteration (error = sum (output - T)^2 / HW). */
+int slm_rows_close(slm_ctx* ctx, const double* gathered, int world, double norm, double hw, int form, double tolerance,
                    double* state, double* err_curve);
+/* Gradient descent (algorithms.py:60-112) on the distributed plane, same exchange as GS:
+ *   slm_rows_reset           zero the context's loop state before a run;
+ *   slm_rows_gd_row_pass     SLM-plane pass on this rank's rows: finish ifft2 along the rows (in: lines back from the exchange),
+ *                            dEdX + update of x in place with lr_dev[iteration] (:87-91,179-185), x/|x| and the row half of fft2
+ *                            (:84) into out; first != 0: no update yet (the run's first pass); final_pass != 0: the last update,
+ *                            then angle(x) into hologram (:111) instead of a transform;
+ *   slm_rows_gd_fourier_pass stage 0: finish fft2 along the received lines, keep the transform (out), max |F|^2 per line into
+ *                            partial[.][0] (:84-86); stage 1 (after slm_rows_close form 1 has put norm/max and max into state):
+ *                            output, error sum into partial[.][1], mask * F * (output - T), first half of ifft2 (:85-88,92);
+ *                            intensity (nullable): |F|^2 of the lines (expected outcome = that * norm / max);
+ *   slm_rows_close           form 1 after stage 0, form 2 after stage 1 (error curve, iteration count, loop condition). */
+int slm_rows_reset(slm_ctx* ctx);
+int slm_rows_gd_row_pass(slm_ctx* ctx, const void* in, void* x, void* out, const double* lr_dev, int first, int final_pass, double* hologram);
+int slm_rows_gd_fourier_pass(slm_ctx* ctx, const void* in, void* out, int block_w, const uint8_t* target_u8, const double* mask_lut,
+                             double norm, const double* state_dev, double* partial, double* intensity, int stage);
 /* row slab [rows][W] <-> exchange layout [W/rows][rows][rows] (each block transposed); elem_bytes 1, 8 or 16. */
 int slm_transpose_blocks(slm_ctx* ctx, const void* in, void* out, int rows, int W, int elem_bytes, int from_exchange);
 

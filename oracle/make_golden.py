@@ -87,9 +87,24 @@ def benched_path_fixtures(alg):
          hologram_sha=np.array(sha(holo)), seed=np.array(0))
 
 
+def slab_fixtures(alg):
+    """Round 2: one 8192 x 8192 plane (lines only the slab path holds) through the reference's GD and GS -- the error
+    curves and a 64x64-strided subsample of hologram / expected.  Minutes of numpy time and ~10 GB of memory."""
+    n = 8192
+    sub = (slice(None, None, 64), slice(None, None, 64))
+    t = synthetic.traps_target((n, n), [(1000, 2000), (6000, 5000), (4096, 700)])
+    holo, exp, errs = quiet(alg.gradient_descent, t, ns(max_loops=5))
+    save("gd_traps_8192_slab", errors=np.array(errs), hologram_sub=holo[sub], expected_sub=exp[sub], hologram_sha=np.array(sha(holo)))
+    holo, exp, errs = quiet(alg.gerchberg_saxton, t, ns(max_loops=6))
+    save("gs_traps_8192_slab", errors=np.array(errs), hologram_sub=holo[sub], expected_sub=exp[sub], hologram_sha=np.array(sha(holo)))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     alg = reference_loader.load("algorithms")
+    if "--slab" in sys.argv:                     # only the 8192^2 fixtures of the slab path
+        slab_fixtures(alg)
+        return
     if "--benched-path" in sys.argv:             # only the round-2 fixtures (the others are unchanged)
         benched_path_fixtures(alg)
         return

@@ -60,7 +60,7 @@ for mode in ("copy", "store", "peer1", "coll"):
             if rank == 0: print(f"    {name}: {e0.elapsed_time(e1)/5:.3f} ms per exchange ({rows*n*cs*(world-1)/world/1e6/(e0.elapsed_time(e1)/5)*1e-3*1e3:.0f} GB/s to the peers)")
         # the passes alone (engine stream), then passes + copies together
         Tx = eng._peer_view("Tx", (world, rows, rows), np.uint8)
-        state = eng._mem_upload(np.array([1.0, 0.0, 0.0, 0.0])); partial = eng._mem_empty((rows, 4), np.float64)
+        state = eng._mem_upload(np.array([1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0])); partial = eng._mem_empty((rows, 4), np.float64)
         Y = eng._peer_view("Y", eng.shape, np.complex64)
         torch.cuda.synchronize(); dist.barrier()
         e0.record()

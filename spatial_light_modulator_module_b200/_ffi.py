@@ -46,6 +46,9 @@ SIGNATURES = {
     "slm_rows_gs_row_pass_part": (_i, [_vp, _vp, _vp, _i, _i, _i]),
     "slm_rows_reduce": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i]),
     "slm_rows_close": (_i, [_vp, _vp, _i, _d, _d, _i, _d, _vp, _vp]),
+    "slm_rows_reset": (_i, [_vp]),
+    "slm_rows_gd_row_pass": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "slm_rows_gd_fourier_pass": (_i, [_vp, _vp, _vp, _i, _vp, _dp, _d, _vp, _vp, _vp, _i]),
     "slm_transpose_blocks": (_i, [_vp, _vp, _vp, _i, _i, _i, _i]),
     "slm_copy2d_async": (_i, [_vp, _vp, C.c_size_t, _vp, C.c_size_t, C.c_size_t, C.c_size_t]),
     "slm_copy2d_multi": (_i, [_vp, _i, _vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t]),

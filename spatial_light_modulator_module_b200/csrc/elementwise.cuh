@@ -286,22 +286,32 @@ SLM_GLOBAL void rows_reduce_kernel(const double* partial, int rows, double* out,
 // gathered[world][4] -> the plane's max and sums (rank order: the same bits on every rank); closes the iteration like
 // close_plane<GS>: state[0] = scale (in: the one the pass used, out: norm / max), state[1] = error, state[2] = iterations
 // done (as a double), state[3] = loop-ended flag.  prepass: only the scale (exact scale of iteration 0).
-SLM_GLOBAL void rows_close_kernel(const double* gathered, int world, double norm, double hw, int prepass, int as_float,
-                                  double tolerance, double* state, double* err_curve) {
+// form: 0 GS iteration; 1 only the scale and the max (GS iteration 0's exact scale; the max pass of every GD iteration,
+// algorithms.py:86); 2 GD iteration: error = sum (output - T)^2 / HW (algorithms.py:92), scale and max stay.  `stats`
+// (nullable): the context's PlaneStats, which the GD SLM-plane pass reads (iteration count -> learning rate, loop ended).
+SLM_GLOBAL void rows_close_kernel(const double* gathered, int world, double norm, double hw, int form, int as_float,
+                                  double tolerance, double* state, double* err_curve, PlaneStats* stats) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double mx = 0, a = 0, b = 0, c = 0;
     for (int r = 0; r < world; ++r) {
         mx = fmax(mx, gathered[4 * r]); a += gathered[4 * r + 1]; b += gathered[4 * r + 2]; c += gathered[4 * r + 3];
     }
-    const double s = norm / mx;                                   // algorithms.py:37
-    if (prepass) { state[0] = s; return; }
-    const double s0u = as_float ? (double)(float)state[0] : state[0];          // the scale the kernel used
-    const double dl = s0u != 0.0 ? s / s0u - 1.0 : 0.0;
-    const double err = (a + 2.0 * dl * b + dl * dl * c) / hw;     // algorithms.py:38,162
+    if (form == 1) { state[0] = norm / mx; state[4] = mx; return; }
+    double err;
+    if (form == 0) {
+        const double s = norm / mx;                               // algorithms.py:37
+        const double s0u = as_float ? (double)(float)state[0] : state[0];      // the scale the kernel used
+        const double dl = s0u != 0.0 ? s / s0u - 1.0 : 0.0;
+        err = (a + 2.0 * dl * b + dl * dl * c) / hw;              // algorithms.py:38,162
+        state[0] = s; state[4] = mx;
+    } else {
+        err = a / hw;                                             // algorithms.py:92
+    }
     const int k = (int)state[2];
     err_curve[k] = err;
-    state[0] = s; state[1] = err; state[2] = (double)(k + 1);
-    state[3] = !(err > tolerance) ? 1.0 : 0.0;                    // loop condition, algorithms.py:29
+    state[1] = err; state[2] = (double)(k + 1);
+    state[3] = !(err > tolerance) ? 1.0 : 0.0;                    // loop condition, algorithms.py:29,83
+    if (stats) { stats->err = err; stats->iters = k + 1; stats->done = !(err > tolerance); }
 }
 
 // complex<R> <-> complex128 / real conversions at the boundary (numpy hands over complex128)

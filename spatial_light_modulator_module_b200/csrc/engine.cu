@@ -935,13 +935,48 @@ extern "C" int slm_rows_reduce(slm_ctx* c, const double* partial, int rows, doub
     return 0;
 }
 
-extern "C" int slm_rows_close(slm_ctx* c, const double* gathered, int world, double norm, double hw, int prepass, double tolerance,
+extern "C" int slm_rows_close(slm_ctx* c, const double* gathered, int world, double norm, double hw, int form, double tolerance,
                               double* state, double* err_curve) {
-    if (!c || !gathered || !state || world < 1 || (!prepass && !err_curve)) return fail(SLM_ERR_ARG, "slm_rows_close: bad argument");
+    if (!c || !gathered || !state || world < 1 || form < 0 || form > 2 || (form != 1 && !err_curve)) return fail(SLM_ERR_ARG, "slm_rows_close: bad argument");
     SLM_CUDA(cudaSetDevice(c->device));
-    { LaunchTimer t_(c, K_ELEMENTWISE); SLM_LAUNCH(rows_close_kernel, dim3(1), dim3(32), 0, c->stream, gathered, world, norm, hw, prepass,
-                                                    c->prec == PREC_F32 ? 1 : 0, tolerance, state, err_curve); }
+    { LaunchTimer t_(c, K_ELEMENTWISE); SLM_LAUNCH(rows_close_kernel, dim3(1), dim3(32), 0, c->stream, gathered, world, norm, hw, form,
+                                                    c->prec == PREC_F32 ? 1 : 0, tolerance, state, err_curve, form == 2 ? c->stats : nullptr); }
     SLM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int slm_rows_reset(slm_ctx* c) {
+    if (!c) return fail(SLM_ERR_ARG, "slm_rows_reset: null context");
+    SLM_CUDA(cudaSetDevice(c->device));
+    SLM_CUDA(cudaMemsetAsync(c->stats, 0, sizeof(PlaneStats), c->stream));
+    return 0;
+}
+
+extern "C" int slm_rows_gd_row_pass(slm_ctx* c, const void* in, void* x, void* out, const double* lr_dev, int first, int final_pass,
+                                    double* hologram) {
+    if (!c || !x || !lr_dev || (!first && !in) || (final_pass ? !hologram : !out)) return fail(SLM_ERR_ARG, "slm_rows_gd_row_pass: bad argument");
+    SLM_CUDA(cudaSetDevice(c->device));
+    RowArgs ra{};
+    ra.B = 1; ra.H = c->H; ra.Y = in; ra.field = in; ra.X = out; ra.x = x; ra.lr = lr_dev; ra.stats = c->stats; ra.hologram = hologram;
+    ra.inv_hw = 1.0 / ((double)c->W * (double)c->W);              // scipy's ifft2 normalisation of the WHOLE (square) plane, algorithms.py:87-89
+    ra.tw = c->tw_row; ra.final_pass = final_pass;
+    ra.source = first ? ROW_FROM_FIELD : ROW_FROM_Y;
+    SLM_TIMED(K_ROW_PASS, c->row->row_pass(ALG_GD, ra, c->stream));
+    return 0;
+}
+
+extern "C" int slm_rows_gd_fourier_pass(slm_ctx* c, const void* in, void* out, int block_w, const uint8_t* target_u8, const double* mask_lut,
+                                        double norm, const double* state_dev, double* partial, double* intensity, int stage) {
+    if (!c || !in || !out || !partial || (stage != 0 && stage != 1)) return fail(SLM_ERR_ARG, "slm_rows_gd_fourier_pass: bad argument");
+    if (stage == 1 && (!target_u8 || !mask_lut || !state_dev)) return fail(SLM_ERR_ARG, "slm_rows_gd_fourier_pass: the gradient stage needs target, table and state");
+    if (!block_width_ok(c, block_w))
+        return fail(SLM_ERR_SHAPE, "slm_rows_gd_fourier_pass: the exchange block width must be a power-of-two multiple of the line's thread count");
+    SLM_CUDA(cudaSetDevice(c->device));
+    if (stage == 1) SLM_TRY(upload_lut(c, mask_lut));
+    RowFourierArgs fa{};
+    fa.rows = c->H; fa.block_w = block_w; fa.in = in; fa.out = out; fa.T8 = target_u8; fa.lut = c->lut; fa.partial = partial; fa.intensity = intensity;
+    fa.tw = c->tw_row; fa.mode = stage == 0 ? RF_GD_MAX : RF_GD_POST; fa.norm = norm; fa.state = state_dev;
+    SLM_TIMED(stage == 0 ? K_COL_STATS : K_COL_PASS, c->row->row_fourier(fa, c->stream));
     return 0;
 }
 

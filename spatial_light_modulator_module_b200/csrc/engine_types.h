@@ -137,6 +137,11 @@ struct PlainColArgs {
     const void* tw;
 };
 
+enum RowFourierMode {
+    RF_GS = 0,               // GS: finish fft2, amplitude replacement + error sums, start ifft2 (algorithms.py:31-38)
+    RF_GD_MAX = 1,           // GD: finish fft2 (kept, written to `out`), max |F|^2 per line (algorithms.py:84-86)
+    RF_GD_POST = 2,          // GD: on the kept transform: output, error sum, mask*F*(output-T), start ifft2 (algorithms.py:85-88,92)
+};
 // ---- Fourier-plane step on ROWS of a transposed slab (slab-decomposed 2-D transform, slab.cuh) -----------
 struct RowFourierArgs {
     int rows;                // local lines (columns of the global plane owned by this rank)
@@ -148,6 +153,9 @@ struct RowFourierArgs {
     double s0;               // scale of the previous iteration (algorithms.py:37) ...
     const double* s0_dev;    // ... or, when not null, where it lies in device memory (loop state kept on the device)
     int row0, nrows;         // the lines [row0, row0 + nrows) only (nrows == 0: all) -- chunks that overlap the exchange
+    int mode;                // RowFourierMode
+    double norm;             // RF_GD_POST: amax(T) (algorithms.py:74)
+    const double* state;     // RF_GD_POST: device loop state {norm/max, error, iterations, ended, max} (slm_rows_close)
     double* partial;         // device [rows][4]: max |C|^2, sum r^2, sum r*u, sum u^2 per line
     double* intensity;       // device double, same layout, or null: |C|^2 (final expected_outcome, unscaled)
     const void* tw;

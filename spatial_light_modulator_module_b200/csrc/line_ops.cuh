@@ -103,7 +103,9 @@ template <typename R, int L> struct RowLaunch {
         cudaFuncSetAttribute(row_pass_kernel<R, L, ALG_GD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
         cudaFuncSetAttribute(row_pass_kernel<R, L, ALG_GD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
         cudaFuncSetAttribute(row_plain_kernel<R, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
-        cudaFuncSetAttribute(row_fourier_kernel<R, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
+        cudaFuncSetAttribute(row_fourier_kernel<R, L, RF_GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
+        cudaFuncSetAttribute(row_fourier_kernel<R, L, RF_GD_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
+        cudaFuncSetAttribute(row_fourier_kernel<R, L, RF_GD_POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RG::SMEM);
     }
     static int row_pass(int alg, const RowArgs& a, cudaStream_t s) {
         const dim3 grid((unsigned)((long long)a.B * a.H / RG::NR)), block(RG::THREADS);
@@ -123,7 +125,9 @@ template <typename R, int L> struct RowLaunch {
     }
     static int row_fourier(const RowFourierArgs& a, cudaStream_t s) {
         const dim3 grid((unsigned)((a.nrows ? a.nrows : a.rows) / RG::NR)), block(RG::THREADS);
-        SLM_LAUNCH((row_fourier_kernel<R, L>), grid, block, RG::SMEM, s, a);
+        if (a.mode == RF_GD_MAX) SLM_LAUNCH((row_fourier_kernel<R, L, RF_GD_MAX>), grid, block, RG::SMEM, s, a);
+        else if (a.mode == RF_GD_POST) SLM_LAUNCH((row_fourier_kernel<R, L, RF_GD_POST>), grid, block, RG::SMEM, s, a);
+        else SLM_LAUNCH((row_fourier_kernel<R, L, RF_GS>), grid, block, RG::SMEM, s, a);
         return check();
     }
 };

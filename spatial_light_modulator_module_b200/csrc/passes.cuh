@@ -545,11 +545,12 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), 1) row_plain_kernel(
 // Same arithmetic as col_pass_tile<GS>; a line here is one COLUMN of the global plane, held by this rank
 // after the all-to-all.  Per-line partial sums go to `partial`; the ranks' totals are combined by the
 // caller (NCCL all-reduce), which also closes the iteration (scale, error).
-template <typename R, int W>
+template <typename R, int W, int MODE>
 SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), (RowGeom<R, W>::MIN_CTAS)) row_fourier_kernel(RowFourierArgs a) {
     using G = RowGeom<R, W>;
     using P = FftPlan<W>;
     constexpr int E = P::E, M = P::M;
+    constexpr bool HAS_T = MODE != RF_GD_MAX;                 // needs the target's grey levels and a table
     SLM_DYN_SMEM(raw);
     const int t = threadIdx.x, rr = t / M, j = t % M;
     const long long row = (long long)a.row0 + (long long)blockIdx.x * G::NR + rr;
@@ -559,11 +560,12 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), (RowGeom<R, W>::MIN_
     const cpx<R>* in = static_cast<const cpx<R>*>(a.in);
     const R* lut = static_cast<const R*>(a.lut);
     const LineLayout lay = line_layout<M>(a.block_w, a.rows, W, row, j);
-    // the amplitude table in shared memory, the scale in a register: asked for here, needed after the first transform
+    // the table in shared memory, the loop's scalars in registers: asked for here, needed after the first transform
     // (one CTA per SM and nothing to hide a global load behind)
     SLM_STATIC_SMEM R lut_s[256];
-    for (int i = t; i < 256; i += G::THREADS) lut_s[i] = ld_ro(lut + i);
-    const R s0r = (R)(a.s0_dev ? ld_cg(a.s0_dev) : a.s0);
+    if (HAS_T) for (int i = t; i < 256; i += G::THREADS) lut_s[i] = ld_ro(lut + i);
+    const R s0r = MODE == RF_GS ? (R)(a.s0_dev ? ld_cg(a.s0_dev) : a.s0) : (R)0;
+    const double gd_scale = MODE == RF_GD_POST ? ld_cg(a.state) : 0.0, gd_max = MODE == RF_GD_POST ? ld_cg(a.state + 4) : 0.0;
     sync_cta();
     cpx<R> v[E];
     unsigned grey4[(E + 3) / 4];                              // the points' grey levels, four to a register (they wait through a transform)
@@ -571,21 +573,33 @@ SLM_GLOBAL void SLM_LAUNCH_BOUNDS((RowGeom<R, W>::THREADS), (RowGeom<R, W>::MIN_
     for (int r = 0; r < (E + 3) / 4; ++r) grey4[r] = 0u;
     each_point<E, M>(lay, [&](int r, unsigned off) {
         v[r] = ld_plane(in + off);
-        grey4[r / 4] |= (unsigned)ld_ro(a.T8 + off) << (8 * (r % 4));
+        if (HAS_T) grey4[r / 4] |= (unsigned)ld_ro(a.T8 + off) << (8 * (r % 4));
     });
-    line_fft<R, W, -1, 1>(v, line, j, tw, sync);              // second half of C = fft2(B)
+    if (MODE != RF_GD_POST) line_fft<R, W, -1, 1>(v, line, j, tw, sync);      // second half of C = fft2(B) / of med_output
     R mx = 0, sa = 0, sb = 0, sc = 0;
-    if (a.intensity) each_point<E, M>(lay, [&](int r, unsigned off) { a.intensity[off] = (double)cnorm2(v[r]); });
+    if (MODE != RF_GD_MAX && a.intensity) each_point<E, M>(lay, [&](int r, unsigned off) { a.intensity[off] = (double)cnorm2(v[r]); });
+    const R gdk = (R)gd_scale;                                // GD fp32: output = |F|^2 * (norm / max), like the column kernels
 #pragma unroll
     for (int r = 0; r < E; ++r) {
         const R m2 = cnorm2(v[r]);
         const int grey = (int)((grey4[r / 4] >> (8 * (r % 4))) & 0xffu);
-        const R amp = lut_s[grey];
-        const R u = s0r * m2, d = u - (R)grey;
-        mx = fmax(mx, m2); sa += d * d; sb += d * u; sc += u * u;
-        v[r] = (m2 == (R)0) ? mk<R>(copysign(amp, v[r].x), (R)0) : cscale(v[r], amp * rsqrt_fast(m2));   // algorithms.py:33
+        if (MODE == RF_GS) {
+            const R amp = lut_s[grey];
+            const R u = s0r * m2, d = u - (R)grey;
+            mx = fmax(mx, m2); sa += d * d; sb += d * u; sc += u * u;
+            v[r] = (m2 == (R)0) ? mk<R>(copysign(amp, v[r].x), (R)0) : cscale(v[r], amp * rsqrt_fast(m2));   // algorithms.py:33
+        } else if (MODE == RF_GD_MAX) {
+            mx = fmax(mx, m2);                                                 // amax(output_unnormed), algorithms.py:86
+        } else {
+            R I;                                                               // output, algorithms.py:86
+            if (sizeof(R) == 8) I = (R)(((double)m2 * a.norm) / gd_max);
+            else I = m2 * gdk;
+            const R d = I - (R)grey;
+            sa += d * d;                                                       // algorithms.py:92
+            v[r] = cscale(cscale(v[r], lut_s[grey]), d);                       // mask * med_output * (output - T), :88
+        }
     }
-    line_fft<R, W, +1, 1>(v, line, j, tw, sync);              // first half of A = ifft2(D)
+    if (MODE != RF_GD_MAX) line_fft<R, W, +1, 1>(v, line, j, tw, sync);       // first half of A = ifft2(D) / of dEdF
     cpx<R>* out = static_cast<cpx<R>*>(a.out);
     each_point<E, M>(lay, [&](int r, unsigned off) { st_plane(out + off, v[r]); });
 

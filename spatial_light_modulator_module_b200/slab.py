@@ -376,7 +376,7 @@ class SlabEngine(Engine):
             field_kind = 2
         hw = float(n) * float(n)
         # loop state on the device: {scale, last error, iterations done, loop ended}, the error curve, the ranks' sums
-        state = self._mem_upload(np.array([1.0, 0.0, 0.0, 0.0]))
+        state = self._mem_upload(np.array([1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0]))
         curve = self._mem_empty((max_loops,), np.float64)
         mine = self._mem_empty((4,), np.float64)
         # (two slots used in turn: a rank may run one closing step ahead of a peer that is still reading the previous one)
@@ -445,7 +445,8 @@ class SlabEngine(Engine):
         return (holo if on_device else self.to_host(holo)), expected, errors
 
     def _close(self, partial, mine, gathered, norm, hw, prepass, tolerance, state, curve):
-        """this rank's sums -> every rank -> scale / error / loop condition in `state` (all on the device)"""
+        """this rank's sums -> every rank -> scale / error / loop condition in `state` (all on the device); ``prepass``:
+        the form of slm_rows_close (False / 0: GS iteration, True / 1: scale and max only, 2: GD iteration)"""
         peer = self._peer is not None
         slot, self._slot = self._slot, self._slot ^ 1
         self._check(self._lib.slm_rows_reduce(self._ctx, self._mem_ptr(partial), self.rows, self._mem_ptr(mine),
@@ -457,6 +458,107 @@ class SlabEngine(Engine):
             self._all_gather4(mine, gathered[slot])
         self._check(self._lib.slm_rows_close(self._ctx, self._mem_ptr(gathered[slot]), self.world, float(norm), float(hw), int(prepass),
                                              float(tolerance), self._mem_ptr(state), self._mem_ptr(curve)))
+
+    # ---- gradient descent on the distributed plane (algorithms.py:60-112) ------------------------------------------------
+    def gd(self, target_slab, x0_slab, lr_schedule, max_loops: int, tolerance: float = 0.0, white_attention=1,
+           want_expected: bool = True, on_device: bool = False):
+        """``target_slab``: this rank's uint8 rows [rows, N] (host array or device buffer); ``x0_slab``: this rank's rows of the complex initial guess
+        (host array; make_initial_guess draws the plane row-major, so rank p's rows are a contiguous part of the stream).
+        Returns ``(hologram_slab, expected_slab or None, error_evolution)`` like :meth:`gs`.  Same exchange as GS (stores into
+        peer memory or collectives), two Fourier-plane passes per iteration: the plane's max is needed before the gradient
+        (algorithms.py:86), and here it lives on several devices."""
+        if max_loops < 1:
+            raise UnboundLocalError("cannot access local variable 'output' where it is not associated with a value")
+        if self._mem_is_device(target_slab):
+            T = target_slab
+            if tuple(T.shape) != self.shape or self._mem_np_dtype(T) != np.uint8:
+                raise ValueError(f"target slab must be uint8 {self.shape}")
+            local_max = float(self.to_host(T.max() if hasattr(T, "is_cuda") else np.asarray(T).max()))
+        else:
+            t = np.ascontiguousarray(target_slab)
+            if t.dtype != np.uint8 or t.shape != self.shape:
+                raise ValueError(f"target slab must be uint8 {self.shape}")
+            T, local_max = self._mem_upload(t), float(t.max())
+        x_on_device = self._mem_is_device(x0_slab)
+        x0 = x0_slab if x_on_device else np.asarray(x0_slab)
+        if tuple(x0.shape) != self.shape or (x_on_device and not str(x0.dtype).endswith(np.dtype(self.complex_dtype).name)):
+            raise ValueError(f"x0 slab must have shape {self.shape} (a device buffer: in the engine's complex type)")
+        lr = np.ascontiguousarray(lr_schedule, dtype=np.float64)
+        if lr.shape != (max_loops,):
+            raise ValueError("lr_schedule must have max_loops entries")
+        h, n, cs = self.rows, self.n, np.dtype(self.complex_dtype).itemsize
+        norm = float(self._all_reduce(np.array([local_max]), "max")[0])
+        peer = self._peer is not None
+        blocks = (self.world, h, h)
+        Tx_send = None if peer else self._mem_empty(blocks, np.uint8)
+        Tx = self._peer_view("Tx", blocks, np.uint8) if peer else self._mem_empty(blocks, np.uint8)
+        self._exchange(T, Tx_send, Tx, 1, "Tx")
+        X = self._peer_view("X", self.shape, self.complex_dtype) if peer else self._mem_empty(self.shape, self.complex_dtype)
+        Y = self._peer_view("Y", self.shape, self.complex_dtype) if peer else self._mem_empty(self.shape, self.complex_dtype)
+        S = self._mem_empty(blocks, self.complex_dtype)
+        Rv = self._peer_view("Rv", blocks, self.complex_dtype) if peer else self._mem_empty(blocks, self.complex_dtype)
+        if x_on_device:                                                   # (the row pass updates x in place: work on a copy)
+            x = self._mem_empty(self.shape, self.complex_dtype)
+            self._copy(x0, x)
+        else:
+            x = self._mem_upload(x0.astype(self.complex_dtype))
+        lr_dev = self._mem_upload(lr)
+        mask_lut = hl.gd_mask_lut(white_attention)
+        partial = self._mem_empty((h, 4), np.float64)
+        state = self._mem_upload(np.array([1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0]))
+        curve = self._mem_empty((max_loops,), np.float64)
+        mine = self._mem_empty((4,), np.float64)
+        gathered = self._peer_view("gathered", (2, self.world, 4), np.float64) if peer else self._mem_empty((2, self.world, 4), np.float64)
+        self._slot = 0
+        inten = self._mem_empty(blocks, np.float64) if want_expected else None
+        hw = float(n) * float(n)
+        check_every = tolerance > 0
+        self._check(self._lib.slm_rows_reset(self._ctx))
+        done_iters = 0
+        for k in range(max_loops):
+            # SLM-plane pass: the update of the previous iteration (none yet at k = 0), x/|x|, rows of fft2
+            self._check(self._lib.slm_rows_gd_row_pass(self._ctx, self._mem_ptr(Y), self._mem_ptr(x), self._mem_ptr(X), self._mem_ptr(lr_dev),
+                                                       int(k == 0), 0, None))
+            self._exchange(X, S, Rv, cs, "Rv")
+            # the plane's max (the transform is kept in S), then the gradient step on it
+            self._check(self._lib.slm_rows_gd_fourier_pass(self._ctx, self._mem_ptr(Rv), self._mem_ptr(S), h, None, None, norm, None,
+                                                           self._mem_ptr(partial), None, 0))
+            self._close(partial, mine, gathered, norm, hw, 1, tolerance, state, curve)
+            last = k == max_loops - 1
+            want_i = inten if (want_expected and (last or check_every or k == 0)) else None
+            self._check(self._lib.slm_rows_gd_fourier_pass(self._ctx, self._mem_ptr(S), self._mem_ptr(S), h, self._mem_ptr(Tx), self._dp(mask_lut),
+                                                           norm, self._mem_ptr(state), self._mem_ptr(partial), self._mem_ptr(want_i), 1))
+            self._close(partial, mine, gathered, norm, hw, 2, tolerance, state, curve)
+            self._exchange_back(S, Rv, Y, cs, "Y")
+            done_iters = k + 1
+            if check_every or (k == 0 and not norm > 0):
+                if self.to_host(state)[3] != 0.0:
+                    break
+        errors = [np.float64(e) for e in self.to_host(curve)[:done_iters]]
+        for i, e in enumerate(errors):
+            if not (e > tolerance):
+                errors = errors[:i + 1]
+                break
+        st = self.to_host(state)
+        holo = self._mem_empty(self.shape, np.float64)
+        self._check(self._lib.slm_rows_gd_row_pass(self._ctx, self._mem_ptr(Y), self._mem_ptr(x), None, self._mem_ptr(lr_dev), 0, 1,
+                                                   self._mem_ptr(holo)))
+        expected = None
+        if want_expected:
+            exp_slab = self._mem_empty(self.shape, np.float64)
+            if self.world == 1:
+                self._transpose(inten, exp_slab, 8, True)
+            else:
+                recv_i = self._mem_empty(blocks, np.float64)
+                self._all_to_all(inten, recv_i)
+                self._transpose(recv_i, exp_slab, 8, True)
+            if on_device:
+                exp_slab *= norm                                              # output_unnormed * norm / amax, algorithms.py:86
+                exp_slab /= float(st[4])
+                expected = exp_slab
+            else:
+                expected = self.to_host(exp_slab) * norm / float(st[4])
+        return (holo if on_device else self.to_host(holo)), expected, errors
 
     def _setup_field(self, T, X, S, Rv, peer_recv=None, peer_slab=None):
         """A = ifft2(amplitude) of the distributed target into the row slab X (this engine's precision)."""
@@ -497,5 +599,44 @@ def gerchberg_saxton_slab(target, max_loops: int, tolerance: float = 0.0, precis
     eng = (engine_factory or SlabEngine)(n, world, rank, precision)
     try:
         return eng.gs(slab, max_loops, tolerance, want_expected)
+    finally:
+        eng.close()
+
+
+def gradient_descent_slab(target, max_loops: int, learning_rate: float = 0.005, unsettle: int = 0, tolerance: float = 0.0,
+                          white_attention=1, initial_guess: str = "random", random_seed: int = 42, precision: str = "fp32",
+                          want_expected: bool = True, engine_factory=None):
+    """GD hologram (algorithms.py:60-112) of one large square uint8 ``target`` on all ranks of the default process group;
+    the arguments are the reference's ``args`` fields of the same names.  ``initial_guess``: the random families of make_initial_guess
+    (algorithms.py:115-153; the MT19937 stream is drawn row-major for the whole plane, every rank keeps its own rows) --
+    "fourier" is not offered here.  Returns this rank's row slab of (hologram, expected), the error curve and the learning rate the
+    reference would leave in ``args.learning_rate``."""
+    try:
+        import torch.distributed as dist
+        world, rank = (dist.get_world_size(), dist.get_rank()) if dist.is_available() and dist.is_initialized() else (1, 0)
+    except Exception:
+        world, rank = 1, 0
+    target = np.asarray(target)
+    n = target.shape[1]
+    lo, hi = rank * (n // world), (rank + 1) * (n // world)
+    if target.shape[0] != n:
+        raise ValueError("gradient_descent_slab takes the whole plane (the initial guess is drawn for all of it)")
+    if initial_guess == "fourier":
+        raise ValueError('initial_guess "fourier" is not available on the slab path')
+    during, after = hl.learning_rate_schedule(learning_rate, unsettle, int(max_loops))
+    eng = (engine_factory or SlabEngine)(n, world, rank, precision)
+    try:
+        if initial_guess in ("random", "zeros"):
+            # the MT19937 stream continued on the device (Engine.python_random_uniform); every rank draws the plane's
+            # stream up to the end of its own rows and keeps those
+            u = eng.python_random_uniform(random_seed, (hi, n))
+            x0 = eng._mem_empty(eng.shape, eng.complex_dtype)
+            eng._check(eng._lib.slm_random_phasor(eng._ctx, eng._mem_ptr(u[lo:hi]), eng._mem_ptr(x0), (hi - lo) * n,
+                                                  100.0 if initial_guess == "zeros" else 1.0))
+            del u
+        else:
+            x0 = hl.host_initial_guess(initial_guess, (n, n), random_seed)[lo:hi]
+        h, e, errs = eng.gd(target[lo:hi], x0, during, int(max_loops), float(tolerance), white_attention, want_expected)
+        return h, e, errs, after[len(errs)]
     finally:
         eng.close()

@@ -98,6 +98,53 @@ def test_two_gpu_slab_gs_matches_single_gpu(tmp_path):
     eng.close()
 
 
+def _slab_gd_worker(rank, world, port, n, loops, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from spatial_light_modulator_module_b200 import host_logic as hl, slab, synthetic
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        t = synthetic.noise_target((n, n), seed=6)
+        x0 = hl.host_initial_guess("random", (n, n), 11)
+        during, _ = hl.learning_rate_schedule(0.005, 1, loops)
+        lo, hi = rank * (n // world), (rank + 1) * (n // world)
+        for tag, env in (("peer", {}), ("coll", {"SLM_SLAB_NO_PEER": "1"})):
+            os.environ.pop("SLM_SLAB_NO_PEER", None)
+            os.environ.update(env)
+            eng = slab.SlabEngine(n, world, rank, "fp32")
+            h, e, errs = eng.gd(t[lo:hi], x0[lo:hi], during, loops, white_attention=2.0)
+            np.savez(os.path.join(out_dir, f"slabgd_{tag}{rank}.npz"), h=h, e=e, errs=np.array(errs))
+            eng.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_slab_gd_matches_single_gpu(tmp_path):
+    """GD on one 2048^2 plane over 2 GPUs (peer-memory exchange and collectives) against one GPU: the same bits."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from spatial_light_modulator_module_b200 import host_logic as hl, synthetic
+    from spatial_light_modulator_module_b200.slab import SlabEngine
+    n, loops = 2048, 5
+    mp.spawn(_slab_gd_worker, args=(2, free_port(), n, loops, str(tmp_path)), nprocs=2, join=True)
+    eng = SlabEngine(n, 1, 0, "fp32")
+    during, _ = hl.learning_rate_schedule(0.005, 1, loops)
+    h, e, errs = eng.gd(synthetic.noise_target((n, n), seed=6), hl.host_initial_guess("random", (n, n), 11), during, loops,
+                        white_attention=2.0)
+    for tag in ("peer", "coll"):
+        r0, r1 = np.load(tmp_path / f"slabgd_{tag}0.npz"), np.load(tmp_path / f"slabgd_{tag}1.npz")
+        np.testing.assert_array_equal(np.concatenate([r0["h"], r1["h"]]), h)
+        np.testing.assert_allclose(np.concatenate([r0["e"], r1["e"]]), e, rtol=1e-12)
+        np.testing.assert_array_equal(r0["errs"], r1["errs"])
+        assert np.max(np.abs(r0["errs"] - np.array(errs)) / np.array(errs)) < 1e-12
+    eng.close()
+
+
 def _frames_worker(rank, world, port, n_frames, out_dir):
     sys.path.insert(0, ROOT)
     import torch

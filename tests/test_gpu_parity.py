@@ -505,6 +505,57 @@ def test_slab_gs_single_rank_equals_plane_engine(precision):
     eng.close(); ref.close()
 
 
+@pytest.mark.parametrize("precision,n", [("fp32", 512), ("fp64", 1024), ("fp32", 2048), ("fp64", 2048)])
+def test_slab_gd_single_rank_equals_plane_engine(precision, n):
+    """GD on the slab path (algorithms.py:60-112 with the plane's max found in a pass of its own) against the ordinary
+    engine and the oracle; a tolerance ends both loops on the same iteration."""
+    from oracle import numpy_port as P
+    from spatial_light_modulator_module_b200 import host_logic as hl
+    from spatial_light_modulator_module_b200.slab import SlabEngine
+    loops = 6
+    t = synthetic.noise_target((n, n), seed=8)
+    x0 = hl.host_initial_guess("random", (n, n), 42)
+    during, _ = hl.learning_rate_schedule(0.01, 1, loops)
+    ref = make_engine((n, n), precision, 1)
+    r, _ = ref.gd(t, x0.copy(), during, loops)
+    eng = SlabEngine(n, 1, 0, precision)
+    h, e, errs = eng.gd(t, x0, during, loops)
+    # the ordinary engine's Fourier-plane forms order the scale (norm / max) and the transform's butterflies differently:
+    # equal to rounding, not to the bit
+    f64 = precision == "fp64"
+    ref_h_np, ref_e_np, ref_errs, _ = P.gd_run(t, loops, learning_rate=0.01, unsettle=1)
+    for other_h, other_e, other_errs in ((ref.to_host(r.hologram)[0], ref.to_host(r.expected)[0], r.errors[0]),
+                                         (ref_h_np, ref_e_np, np.array(ref_errs))):
+        assert np.abs(np.angle(np.exp(1j * (h - other_h)))).max() < (1e-9 if f64 else 5e-3)
+        np.testing.assert_allclose(e, other_e, rtol=1e-9 if f64 else 1e-3, atol=1e-9 if f64 else 1e-2)
+        assert np.max(np.abs(np.array(errs) - other_errs) / other_errs) < (1e-10 if f64 else 1e-4)
+    stop_at = float(0.5 * (errs[1] + errs[2]))
+    h2, _, errs2 = eng.gd(t, x0, during, loops, tolerance=stop_at)
+    assert len(errs2) == 3 and errs2 == errs[:3]
+    eng.close(); ref.close()
+
+
+def _golden_slab(name):
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+
+
+def test_slab_gd_8192_vs_reference_golden():
+    """GD on a plane only the slab path holds as lines, against the reference's own run (oracle/make_golden.py --slab):
+    the error curve (which RISES first on this sparse target, as the reference's does), hologram and expected samples."""
+    from spatial_light_modulator_module_b200 import algorithms, slab
+    g = _golden_slab("gd_traps_8192_slab")
+    n = 8192
+    t = synthetic.traps_target((n, n), [(1000, 2000), (6000, 5000), (4096, 700)])
+    h, e, errs, _ = slab.gradient_descent_slab(t, 5, learning_rate=0.005, precision="fp32")
+    assert np.all(np.abs(h) <= np.pi) and abs(e.max() - 255.0) < 1e-9
+    assert abs(algorithms.error_f(e, t, t.size) - errs[-1]) < 1e-5 * errs[-1]
+    assert np.max(np.abs(np.array(errs) - g["errors"]) / g["errors"]) < 2e-4
+    sub = (slice(None, None, 64), slice(None, None, 64))
+    assert np.abs(np.angle(np.exp(1j * (h[sub] - g["hologram_sub"])))).max() < 5e-3
+    np.testing.assert_allclose(e[sub], g["expected_sub"], rtol=2e-3, atol=2e-2)
+
+
 def test_slab_gs_8192_invariants():
     """A plane only the slab path can hold as lines (8192 points): GS on a trap target converges to a fixed
     point, |hologram| <= pi, max(expected) == max(target), error == error_f(expected, target)."""
@@ -517,6 +568,11 @@ def test_slab_gs_8192_invariants():
     assert np.all(np.abs(h) <= np.pi) and abs(e.max() - 255.0) < 1e-9
     assert abs(algorithms.error_f(e, t, t.size) - errs[-1]) < 1e-5 * errs[-1]
     assert abs(errs[-1] - errs[-2]) < 1e-4 * errs[-1]
+    g = _golden_slab("gs_traps_8192_slab")                     # the reference's own run of this case
+    assert np.max(np.abs(np.array(errs) - g["errors"]) / g["errors"]) < 2e-4
+    sub = (slice(None, None, 64), slice(None, None, 64))
+    print("8192 GS hologram vs reference, max circular distance:", np.abs(np.angle(np.exp(1j * (h[sub] - g["hologram_sub"])))).max())
+    np.testing.assert_allclose(e[sub], g["expected_sub"], rtol=2e-3, atol=2e-2)
     eng.close()
 
 

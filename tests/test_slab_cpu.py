@@ -105,3 +105,94 @@ def test_two_rank_slab_gs_matches_single_rank(tmp_path):
     np.testing.assert_array_equal(r0["errs"], r1["errs"])                     # every rank closes the loop identically
     assert np.max(np.abs(r0["errs"] - np.array(errs)) / np.array(errs)) < 1e-12
     eng.close()
+
+
+# ---- gradient descent on the distributed plane -------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_slab_gd_single_rank_equals_plane_engine_and_oracle(precision):
+    """world = 1: GD on the slab path (two Fourier-plane passes per iteration, loop state on the device) against the
+    ordinary engine -- the same arithmetic per element, the error sums in another order -- and against the oracle."""
+    from oracle import numpy_port as P
+    from spatial_light_modulator_module_b200 import host_logic as hl, synthetic
+    from tests.emu.emu_engine import EmuEngine, EmuSlabEngine
+    n, loops = 256, 5
+    t = synthetic.noise_target((n, n), seed=8)
+    x0 = hl.host_initial_guess("random", (n, n), 42)
+    during, _ = hl.learning_rate_schedule(0.01, 1, loops)             # (with one doubling of the learning rate on the way)
+    ref = EmuEngine((n, n), precision, 1)
+    r, _ = ref.gd(t, x0.copy(), during, loops)
+    eng = EmuSlabEngine(n, 1, 0, precision)
+    h, e, errs = eng.gd(t, x0, during, loops)
+    np.testing.assert_array_equal(h, ref.to_host(r.hologram)[0])
+    np.testing.assert_allclose(e, ref.to_host(r.expected)[0], rtol=1e-12)
+    assert np.max(np.abs(np.array(errs) - r.errors[0]) / r.errors[0]) < (1e-6 if precision == "fp32" else 1e-12)
+    ref_h, ref_e, ref_errs, _ = P.gd_run(t, loops, learning_rate=0.01, unsettle=1)
+    tol = 1e-9 if precision == "fp64" else 1e-4
+    assert np.max(np.abs(np.array(errs) - np.array(ref_errs)) / np.array(ref_errs)) < tol
+    # a tolerance ends the loop where the reference does (algorithms.py:83)
+    stop_at = float(0.5 * (errs[1] + errs[2]))
+    h2, _, errs2 = eng.gd(t, x0, during, loops, tolerance=stop_at)
+    assert len(errs2) == 3 and errs2 == errs[:3]
+    r2, _ = ref.gd(t, x0.copy(), during[:3], 3)
+    np.testing.assert_array_equal(h2, ref.to_host(r2.hologram)[0])
+    # device-resident target and guess (what bench.py hands over): the same result, the guess left as it was
+    xd = eng._mem_upload(x0.astype(eng.complex_dtype))
+    h3, _, errs3 = eng.gd(eng._mem_upload(t), xd, during, loops, want_expected=False)
+    np.testing.assert_array_equal(h3, h)
+    assert errs3 == errs
+    np.testing.assert_array_equal(eng.to_host(xd), x0.astype(eng.complex_dtype))
+    eng.close(); ref.close()
+
+
+def _gd_worker(rank, world, port, n, loops, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from spatial_light_modulator_module_b200 import host_logic as hl, synthetic
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        t = synthetic.shapes_target((n, n))
+        x0 = hl.host_initial_guess("random", (n, n), 7)
+        during, _ = hl.learning_rate_schedule(0.005, 0, loops)
+        lo, hi = rank * (n // world), (rank + 1) * (n // world)
+        eng = _slab_factory(n, world, rank, "fp64")
+        h, e, errs = eng.gd(t[lo:hi], x0[lo:hi], during, loops, white_attention=2.5)
+        np.savez(os.path.join(out_dir, f"gd{rank}.npz"), h=h, e=e, errs=np.array(errs))
+        eng.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_slab_gd_matches_single_rank(tmp_path):
+    from spatial_light_modulator_module_b200 import host_logic as hl, synthetic
+    from tests.emu.emu_engine import EmuSlabEngine
+    n, loops = 256, 4
+    mp.spawn(_gd_worker, args=(2, free_port(), n, loops, str(tmp_path)), nprocs=2, join=True)
+    t = synthetic.shapes_target((n, n))
+    x0 = hl.host_initial_guess("random", (n, n), 7)
+    during, _ = hl.learning_rate_schedule(0.005, 0, loops)
+    eng = EmuSlabEngine(n, 1, 0, "fp64")
+    h, e, errs = eng.gd(t, x0, during, loops, white_attention=2.5)
+    r0, r1 = np.load(tmp_path / "gd0.npz"), np.load(tmp_path / "gd1.npz")
+    np.testing.assert_array_equal(np.concatenate([r0["h"], r1["h"]]), h)
+    np.testing.assert_allclose(np.concatenate([r0["e"], r1["e"]]), e, rtol=1e-12)
+    np.testing.assert_array_equal(r0["errs"], r1["errs"])
+    assert np.max(np.abs(r0["errs"] - np.array(errs)) / np.array(errs)) < 1e-12
+    eng.close()
+
+
+def test_gradient_descent_slab_entry_point():
+    """The reference-style entry (learning rate, unsettle, initial guess by name) against the oracle's GD."""
+    from oracle import numpy_port as P
+    from spatial_light_modulator_module_b200 import slab, synthetic
+    n, loops = 256, 6
+    t = synthetic.noise_target((n, n), seed=3)
+    h, e, errs, lr_after = slab.gradient_descent_slab(t, loops, learning_rate=0.01, unsettle=2, precision="fp64",
+                                                      engine_factory=_slab_factory)
+    ref_h, ref_e, ref_errs, ref_lr = P.gd_run(t, loops, learning_rate=0.01, unsettle=2)
+    assert np.max(np.abs(np.array(errs) - np.array(ref_errs)) / np.array(ref_errs)) < 1e-9
+    assert lr_after == ref_lr
+    d = np.abs(np.angle(np.exp(1j * (h - ref_h))))
+    assert d.max() < 1e-6
+    np.testing.assert_allclose(e, ref_e, rtol=1e-7, atol=1e-9)
+    with pytest.raises(ValueError):
+        slab.gradient_descent_slab(t, loops, initial_guess="fourier", engine_factory=_slab_factory)
