@@ -289,8 +289,14 @@ template <class F> static bool record_iterations(slm_ctx* c, int n, F& body, cud
     const long long before = c->launches;
     cudaStream_t callers = c->stream;
     c->stream = c->capture_stream;
+    // Recorded without programmatic dependent launch: in a graph the kernels follow each other without the host in
+    // between, and a dependent kernel that starts early only takes SM slots from the tail of its predecessor
+    // (measured, one 1024^2 plane x 100 iterations from a kept graph: GD 2.39 ms without, 2.67 ms with; GS 2.11 / 2.30).
+    const bool pdl = tl_pdl;
+    tl_pdl = false;
     int rc = 0;
     for (int i = 0; i < n && rc == 0; ++i) rc = body();
+    tl_pdl = pdl;
     c->stream = callers;
     *graph = nullptr; *exec = nullptr;
     const cudaError_t e = cudaStreamEndCapture(c->capture_stream, graph);
@@ -600,8 +606,17 @@ extern "C" int slm_gs_run(slm_ctx* c, int batch, const uint8_t* T8, const void* 
         ra.source = src; ra.A32 = c->Y; ra.field = c->Y;
     }
     SLM_TIMED(K_ROW_PASS, c->row->row_pass(ALG_GS, ra, c->stream));
+    // Fewer tiles than SMs (one SLM-size plane): the persistent tile pipeline of the column-group kernels has nothing to
+    // pipeline, and the plain column kernel -- one CTA per tile, CTA-wide transforms -- has the shorter latency
+    // (measured per 100 iterations of one 1024^2 plane: 1.91 against 2.11 ms; 512^2 x 20: 0.35 against 0.39 ms; from
+    // two planes on the pipeline wins).  Decided per CONTEXT (its largest batch), not per run: the two kernels round
+    // differently, and a plane's result must not depend on how many planes share its batch (the tail of a movie).  One
+    // kernel family per run also because the expected outcome below takes its maximum with the arithmetic that made
+    // the transform.  SLM_GS_GROUPS=1 keeps the pipeline (tests compare contexts of different sizes bit for bit).
+    const bool groups = c->use_groups && ((long long)c->max_batch * (c->W / c->col->cols_per_cta) > c->persist_ctas || getenv("SLM_GS_GROUPS"));
     // exact scale of iteration 0 so the one-pass error of later iterations is well conditioned
-    SLM_TRY(run_stats(c, batch));
+    if (groups) SLM_TRY(run_stats(c, batch));
+    else SLM_TIMED(K_COL_STATS, c->col->col_plain(stats_args(c, batch, OUT_STATS, nullptr), c->stream));
 
     ColArgs ca{};
     ca.B = batch; ca.W = c->W; ca.X = c->X; ca.Y = c->Y; ca.T8 = T8; ca.Treal = Treal; ca.plane2 = amp_real;
@@ -610,7 +625,7 @@ extern "C" int slm_gs_run(slm_ctx* c, int batch, const uint8_t* T8, const void* 
     ca.inv_hw = ra.inv_hw; ca.tw = c->tw_col;
     ra.source = ROW_FROM_Y;
     auto fourier_step = [&]() -> int {
-        if (c->use_groups) SLM_TRY(launch_group(c, CGM_GS, batch, &ca, &c->map_y, 0, 1.0));
+        if (groups) SLM_TRY(launch_group(c, CGM_GS, batch, &ca, &c->map_y, 0, 1.0));
         else SLM_TIMED(K_COL_PASS, c->col->col_pass(ALG_GS, ca, c->stream));
         return 0;
     };
@@ -629,7 +644,7 @@ extern "C" int slm_gs_run(slm_ctx* c, int batch, const uint8_t* T8, const void* 
     SLM_TIMED(K_ROW_PASS, c->row->row_pass(ALG_GS, ra, c->stream));
     if (expected_out) {
         PlainColArgs ia = stats_args(c, batch, OUT_INTENSITY_GS, expected_out);
-        if (c->use_groups) {
+        if (groups) {
             // C = fft2(B) of the last iteration once more, by the SAME kernel arithmetic that took its max, kept in X;
             // the intensity pass then only scales |C|^2 (max(expected_outcome) == norm like the reference's, :36-37)
             SLM_TRY(launch_group(c, CGM_STATS_KEEP, batch, nullptr, &c->map_x, 0, 1.0, 1));

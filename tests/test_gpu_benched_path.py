@@ -106,10 +106,10 @@ def test_gd_large_batch_tolerance_stops_planes_independently(precision):
 # ---- GS, batch >= 8 --------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("precision", ["fp32", "fp64"])
 @pytest.mark.parametrize("shape", [(1024, 1024), (768, 1024)])
-def test_gs_large_batch_teacher_forced_and_single_runs(shape, precision):
+def test_gs_large_batch_teacher_forced_and_single_runs(shape, precision, monkeypatch):
     """Ten GS iterations, each started on the device from the oracle's state entering it (GS free-running is chaotic
     on dense targets), all eight planes in one batch; then a free-running batch against single-plane
-    runs, bit for bit."""
+    runs in the same context, bit for bit; a context made for one plane (plain column kernel) within tolerances."""
     batch, steps = 8, 10
     tol = pc.TOL[precision]
     t = plane_targets(shape, batch)
@@ -142,6 +142,17 @@ def test_gs_large_batch_teacher_forced_and_single_runs(shape, precision):
         np.testing.assert_array_equal(r1.errors[0], res.errors[b])
         np.testing.assert_array_equal(eng.to_host(r1.hologram)[0], holo[b])
         np.testing.assert_array_equal(eng.to_host(r1.expected)[0], exp[b])
+    # a context for ONE plane takes the plain column kernel (shorter latency, another rounding): the same iteration;
+    # SLM_GS_GROUPS=1 keeps it on the pipeline kernels and gives the batch's bits
+    one = make_engine(shape, precision, 1)
+    r1 = one.gs(t[3], 10)
+    assert abs(r1.errors[0][0] - res.errors[3][0]) <= tol["err"] * res.errors[3][0]
+    assert abs(r1.errors[0][1] - res.errors[3][1]) <= (1e-2 if precision == "fp32" else 1e-8) * res.errors[3][1]   # (chaotic growth)
+    monkeypatch.setenv("SLM_GS_GROUPS", "1")
+    r1 = one.gs(t[3], 10)
+    np.testing.assert_array_equal(r1.errors[0], res.errors[3])
+    np.testing.assert_array_equal(one.to_host(r1.hologram)[0], holo[3])
+    one.close()
     eng.close()
 
 

@@ -42,7 +42,13 @@ def test_native_library_is_the_compute_path():
     eng = make_engine((128, 128), "fp32", 1)
     n0 = eng.launch_count()
     eng.gs(synthetic.noise_target((128, 128)), 3)
-    assert eng.launch_count() - n0 == 2 + 1 + 1 + 3 + 2 + 1 + 2   # setup(2), row, max pre-pass, 3 col, 2 row, final row, intensity (transform kept + scaling)
+    # setup(2), row, max pre-pass, 3 col, 2 row, final row, intensity (a context for ONE plane: plain column kernels, 1 launch)
+    assert eng.launch_count() - n0 == 2 + 1 + 1 + 3 + 2 + 1 + 1
+    eng.close()
+    eng = make_engine((1024, 1024), "fp32", 2)                    # the tile pipeline: intensity = transform kept + scaling
+    n0 = eng.launch_count()
+    eng.gs(synthetic.noise_target((1024, 1024)), 3)
+    assert eng.launch_count() - n0 == 2 + 1 + 1 + 3 + 2 + 1 + 2
     eng.close()
 
 
@@ -410,7 +416,7 @@ def test_sequence_warm_start(precision):
     from spatial_light_modulator_module_b200 import generate_hologram_sequence as ghs
     frames = synthetic.movie_frames(4, rescale_parameter=0.2)
     holos, _, errors, _ = ghs.sequence_holograms(frames, 6, precision=precision, warm_start=True, gather=False)
-    eng = make_engine(frames.shape[1:], precision, 1)
+    eng = make_engine(frames.shape[1:], precision, 2)     # (a context for more than one plane, like the driver's: same kernels, same bits)
     phasor = None
     for i in range(4):
         r = eng.gs(frames[i], 6, phasor0=phasor)
