@@ -700,6 +700,7 @@ def run_config5(h, n, loops, precision, steps, warmup, peak, alg="gs"):
     errs = state["out"][2]
     it_bytes = survey_bytes_per_px(alg, precision) * n * n          # SURVEY 8(d)'s four-pass model (the exchanges are not in it)
     per_it = ms * 1e-3 / (steps * loops)
+    eng_info = argparse.Namespace(enqueue_s=getattr(eng, "enqueue_s", 0.0))
     eng.close()
     del slab
     torch.cuda.empty_cache()
@@ -709,6 +710,7 @@ def run_config5(h, n, loops, precision, steps, warmup, peak, alg="gs"):
                         f"{world} GPU(s), {what[1]} per iteration ({what[2]})",
             "value": 1.0 / per_it, "unit": "iterations/s", "scaling": "strong", "ms_per_hologram": ms / steps, "step_ms": step_ms,
             "gpu_launches": int(launches), "final_error": float(errs[-1]), "iterations": len(errs),
+            "host_enqueue_ms": round(1e3 * getattr(eng_info, "enqueue_s", 0.0), 3),
             "iteration_roofline": {"survey_bytes_per_iteration": it_bytes, "achieved_gbs_per_gpu": it_bytes / per_it / 1e9 / world,
                                    "frac": it_bytes / per_it / 1e9 / world / peak, "peak": peak, "unit": "GB/s per GPU"}}
 

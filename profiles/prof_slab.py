@@ -11,7 +11,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 for mode in ("copy", "store", "peer1", "coll"):
     for k in ("SLM_SLAB_NO_PEER", "SLM_SLAB_PARTS", "SLM_SLAB_EXCHANGE"):
         os.environ.pop(k, None)
-    os.environ.update({"copy": {}, "store": {"SLM_SLAB_EXCHANGE": "store"}, "peer1": {"SLM_SLAB_PARTS": "1"}, "coll": {"SLM_SLAB_NO_PEER": "1"}}[mode])
+    os.environ.update({"copy": {"SLM_SLAB_PARTS": "4"}, "store": {"SLM_SLAB_PARTS": "4", "SLM_SLAB_EXCHANGE": "store"}, "peer1": {}, "coll": {"SLM_SLAB_NO_PEER": "1"}}[mode])
     eng = SlabEngine(n, world, rank, "fp32")
     rows = n // world
     slab = eng._mem_upload((np.random.default_rng(100 + rank).random((rows, n)) * 255).astype(np.uint8))

@@ -1006,12 +1006,13 @@ extern "C" int slm_transpose_blocks_peer(slm_ctx* c, const void* in, const void*
     SLM_TRY(peer_ptrs(peers, n_peers, &pp, "slm_transpose_blocks_peer"));
     // a part: rows [first, first + count) of the slab on the way out, lines [first, first + count) on the way back
     const int i0 = from_exchange ? 0 : first, c0 = from_exchange ? first : 0;
-    const dim3 grid((from_exchange ? rows : count) / 32, (from_exchange ? count : rows) / 32, W / rows), block(256);
+    const int n_x = (from_exchange ? rows : count) / 32;
+    const dim3 grid(n_x * (W / rows), (from_exchange ? count : rows) / 32, 1), block(256);             // x: (tile, destination), destination fastest
     {
         LaunchTimer t_(c, K_ELEMENTWISE);
-        if (elem_bytes == 16) SLM_LAUNCH((transpose_blocks_peer_kernel<cpx<double>>), grid, block, 0, c->stream, static_cast<const cpx<double>*>(in), pp, rows, W, from_exchange, self, i0, c0);
-        else if (elem_bytes == 8) SLM_LAUNCH((transpose_blocks_peer_kernel<double>), grid, block, 0, c->stream, static_cast<const double*>(in), pp, rows, W, from_exchange, self, i0, c0);
-        else if (elem_bytes == 1) SLM_LAUNCH((transpose_blocks_peer_kernel<unsigned char>), grid, block, 0, c->stream, static_cast<const unsigned char*>(in), pp, rows, W, from_exchange, self, i0, c0);
+        if (elem_bytes == 16) SLM_LAUNCH((transpose_blocks_peer_kernel<cpx<double>>), grid, block, 0, c->stream, static_cast<const cpx<double>*>(in), pp, rows, W, from_exchange, self, i0, c0, n_x);
+        else if (elem_bytes == 8) SLM_LAUNCH((transpose_blocks_peer_kernel<double>), grid, block, 0, c->stream, static_cast<const double*>(in), pp, rows, W, from_exchange, self, i0, c0, n_x);
+        else if (elem_bytes == 1) SLM_LAUNCH((transpose_blocks_peer_kernel<unsigned char>), grid, block, 0, c->stream, static_cast<const unsigned char*>(in), pp, rows, W, from_exchange, self, i0, c0, n_x);
         else return fail(SLM_ERR_ARG, "slm_transpose_blocks_peer: elem_bytes must be 1, 8 or 16");
     }
     SLM_CUDA(cudaGetLastError());

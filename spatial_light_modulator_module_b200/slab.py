@@ -29,6 +29,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import time
 from typing import List, Optional, Tuple
 
 import numpy as np
@@ -107,7 +108,12 @@ class SlabEngine(Engine):
                 lanes.append((st, cx))
             self._peer = {"buf": buf, "hdl": hdl, "ptrs": ptrs, "offs": offs, "comm_stream": comm_stream, "comm_ctx": comm_ctx,
                           "lanes": lanes}
-            parts = int(os.environ.get("SLM_SLAB_PARTS", "4"))
+            # A pass can be cut in parts whose blocks travel (second stream) while the next part is computed.  Measured at
+            # 16384^2 with the stores of the exchange spread over all peers (elementwise.cuh): one part -- pass, then ONE
+            # storing kernel, then the barrier -- is as fast or faster at every size of the group (2 GPUs 227 = 227, 4 GPUs
+            # 414 against 400, 8 GPUs 736 against 732 (stores in parts) / 575 (copy engines) iterations/s): what the overlap
+            # hides it takes back as memory contention, events and small kernels.  So one part is the default.
+            parts = int(os.environ.get("SLM_SLAB_PARTS", "1"))
             self._parts = parts if parts > 1 and self.rows % (32 * parts) == 0 else 1
             # how the blocks travel when a pass is split in parts: "copy" -- packed by a local transposing kernel, then moved
             # by the COPY ENGINES into the peers' memory while the SMs go on with the next part (the passes hold the whole
@@ -387,6 +393,7 @@ class SlabEngine(Engine):
             inten = self._mem_empty(blocks, np.float64)
         check_every = tolerance > 0                                           # the host must see every error to stop the loop
         src, field, done_iters = A0, field_kind, 0
+        t_loop = time.perf_counter()
         for k in range(max_loops):
             cur = X if src is Y else Y                                        # receives the row-transformed B
             overlap = peer and getattr(self, "_parts", 1) > 1
@@ -420,6 +427,7 @@ class SlabEngine(Engine):
                 st = self.to_host(state)
                 if st[3] != 0.0:
                     break
+        self.enqueue_s = time.perf_counter() - t_loop                        # host time to issue the loop (measurements: is the host the bound?)
         errors = [np.float64(e) for e in self.to_host(curve)[:done_iters]]
         for i, e in enumerate(errors):                                        # tolerance <= 0: the loop ran on; cut where the reference stops
             if not (e > tolerance):

@@ -58,7 +58,7 @@ def _slab_worker(rank, world, port, n, loops, out_dir):
                             device_id=torch.device("cuda", rank))
     try:
         t = synthetic.noise_target((n, n), seed=6)
-        for tag, env in (("peer", {}), ("peer_store", {"SLM_SLAB_EXCHANGE": "store"}), ("peer1", {"SLM_SLAB_PARTS": "1"}),
+        for tag, env in (("peer", {"SLM_SLAB_PARTS": "4"}), ("peer_store", {"SLM_SLAB_PARTS": "4", "SLM_SLAB_EXCHANGE": "store"}), ("peer1", {}),
                          ("coll", {"SLM_SLAB_NO_PEER": "1"})):
             for k in ("SLM_SLAB_NO_PEER", "SLM_SLAB_PARTS", "SLM_SLAB_EXCHANGE"):
                 os.environ.pop(k, None)
