@@ -692,8 +692,11 @@ def run_config5(h, n, loops, precision, steps, warmup, peak, alg="gs"):
     def step():
         state["out"] = run(loops)
         return state["out"][0]
-    for _ in range(warmup):
-        state["out"] = run(2)                      # (kept alive like a timed step's result: see Harness.time_steps)
+    # Warm-up: twice at least, results kept alive like a timed step's -- a step allocates its result before the previous
+    # one is released, so the allocator needs TWO result blocks, and a fresh 1 GB cudaMalloc with peer mappings in place
+    # costs ~100 ms (seen as a first timed step of 188 instead of 90 ms on 2 GPUs).
+    for _ in range(max(warmup, 2)):
+        state["out"] = run(2)
     n0 = eng.launch_count()
     ms, step_ms, _ = h.time_steps(step, 0, steps)
     launches = eng.launch_count() - n0
