@@ -627,9 +627,10 @@ def run_config3(h, a):
     st["eng"].close()
     dev_rec["workload"] = f"gerchberg_saxton {shape[0]}x{shape[1]} (the SLM shape), batch 32/GPU, {loops} iterations, fp32, device resident (noise targets)"
     rec["device_resident_loop"] = dev_rec
-    rec["note"] = ("timed region: host uint8 frames -> device, 50 iterations per frame, mask add + quantisation (uint8 variants), device-to-device "
-                   "gather on rank 0 (NCCL) and the read-back into page-locked host memory; float64 results are bounded by rank 0's PCIe link "
-                   "(6 MiB per frame), uint8 SLM frames are what display_holograms.py:253-266 consumes")
+    rec["note"] = ("timed region: host uint8 frames -> device, 50 iterations per frame, mask add + quantisation (uint8 variants) and the gather: "
+                   "rank 0's result arrays lie in host memory shared by the ranks of the node, every rank reads its own frames back into them "
+                   "over its own PCIe link (shared_host.py; SLM_GATHER=device: device-to-device gather on rank 0 over NCCL, then ONE link); "
+                   "uint8 SLM frames are what display_holograms.py:253-266 consumes, float64 holograms what the reference saves (6 MiB per frame)")
     return rec
 
 

@@ -50,10 +50,13 @@ def sequence_holograms(frames, max_loops: int, tolerance: float = 0.0, precision
     host memory (this rank's own frames; with a gather, rank 0 receives every rank's), while later batches iterate.
 
     Under an initialised process group every rank passes the SAME ``frames`` and computes only its contiguous block.
-    With ``gather`` the finished frames travel device to device to rank 0 (``torch.distributed.gather`` per batch:
-    NCCL over NVLink on GPUs), which alone reads them back -- batch k is gathered and read back while batch k+1
-    iterates -- and the full movie is returned on rank 0 (other ranks return their own block's error curves and empty
-    arrays).  Returns ``(holograms [n,H,W] float64 | uint8, expected or None, errors list, (lo, hi))``.
+    With ``gather`` the full movie is returned on rank 0 (other ranks return their own block's error curves and empty
+    arrays).  ``gather=True`` picks the way: all ranks on ONE node (and no ``on_batch``) -- rank 0's result arrays lie
+    in shared host memory which every rank maps, page-locks and reads its own frames back into, each over its own
+    PCIe link (``shared_host.py``; "host"); otherwise, or as ``gather="device"``, the finished frames travel device to
+    device to rank 0 (``torch.distributed.gather`` per batch: NCCL over NVLink on GPUs), which alone reads them back.
+    Either way batch k is read back while batch k+1 iterates.
+    Returns ``(holograms [n,H,W] float64 | uint8, expected or None, errors list, (lo, hi))``.
     """
     if output not in ("float64", "uint8"):
         raise ValueError("output must be 'float64' or 'uint8'")
@@ -85,12 +88,26 @@ def sequence_holograms(frames, max_loops: int, tolerance: float = 0.0, precision
     else:
         eng = engine_factory(shape, precision, batch)
     out_dtype = np.float64 if output == "float64" else np.uint8
+    if gather not in (True, False, "host", "device"):
+        raise ValueError("gather must be True, False, 'host' or 'device'")
     collect = bool(dist and world > 1 and gather)
     root = rank == 0
+    shared = None                                         # the result arrays in host memory shared by the ranks of one node
+    if collect and warm_start:
+        raise ValueError("warm_start chains the frames of a block: gather=False only")
+    if collect and gather != "device" and on_batch is None and n_frames > 0:
+        from . import shared_host
+        want = os.environ.get("SLM_GATHER", "host" if gather == "host" or shared_host.same_node(dist) else "device")
+        if want == "host":
+            specs = [((n_frames,) + shape, out_dtype)] + ([((n_frames,) + shape, np.float64)] if want_expected else [])
+            shared = shared_host.shared_results(dist, specs, (lo, hi))
     n_host = n_frames if (collect and root) else (0 if collect else n_local)
     base = 0 if collect else lo                           # global index of holos[0]
-    holos = eng.host_empty((n_host,) + shape, out_dtype)
-    exps = eng.host_empty((n_host,) + shape, np.float64) if want_expected else None
+    if shared is not None:
+        holos, exps = shared[0], (shared[1] if want_expected else None)
+    else:
+        holos = eng.host_empty((n_host,) + shape, out_dtype)
+        exps = eng.host_empty((n_host,) + shape, np.float64) if want_expected else None
     errors: List[np.ndarray] = []
     writer = _Writer(on_batch)
 
@@ -138,11 +155,13 @@ def sequence_holograms(frames, max_loops: int, tolerance: float = 0.0, precision
         for jobs, a, b in pending:
             writer.put(jobs, a, b, holos[a - base:b - base], exps[a - base:b - base] if want_expected else None)
         pending = []
-        if not collect:
-            jobs = [eng.to_host_into(finish(res), holos[s:e])]
-            if want_expected:
-                jobs.append(eng.to_host_into(res.expected, exps[s:e]))
-            pending.append((jobs, lo + s, lo + e))
+        if not collect or shared is not None:
+            off = lo if shared is not None else 0         # (shared arrays hold the whole movie: this rank fills its own rows)
+            if e > s:
+                jobs = [eng.to_host_into(finish(res), holos[off + s:off + e])]
+                if want_expected:
+                    jobs.append(eng.to_host_into(res.expected, exps[off + s:off + e]))
+                pending.append((jobs, lo + s, lo + e))
             continue
         # gather this batch of every rank on rank 0's device; rank 0 reads the blocks back
         parts = [(finish(res) if res is not None else None, holos)]
@@ -160,11 +179,14 @@ def sequence_holograms(frames, max_loops: int, tolerance: float = 0.0, precision
         pending = [(jobs, a, b) for (a, b), jobs in by_block.items()]
     for jobs, a, b in pending:
         writer.put(jobs, a, b, holos[a - base:b - base], exps[a - base:b - base] if want_expected else None)
-    writer.close()
+    writer.close()                                        # (every copy of this rank has landed)
     if collect:
-        errors = _gather_curves(dist, n_frames, errors, max_loops)
+        errors = _gather_curves(dist, n_frames, errors, max_loops)      # also the point where rank 0 knows the others are done
         if root:
             lo, hi = 0, n_frames
+        elif shared is not None:                          # like the device gather: only rank 0 holds the movie
+            holos = np.empty((0,) + shape, out_dtype)
+            exps = np.empty((0,) + shape, np.float64) if want_expected else None
     return holos, exps, errors, (lo, hi)
 
 

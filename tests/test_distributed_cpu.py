@@ -23,25 +23,34 @@ def _factory(shape, precision, batch):
     return EmuEngine(shape, precision, batch)
 
 
-def _worker(rank, world, port, n_frames, out_dir):
+def _worker(rank, world, port, n_frames, out_dir, gather):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
-    from spatial_light_modulator_module_b200 import generate_hologram_sequence as ghs
+    from spatial_light_modulator_module_b200 import generate_hologram_sequence as ghs, shared_host
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
-        holos, exps, errors, (lo, hi) = ghs.sequence_holograms(_frames(n_frames), 5, precision="fp64", batch=2,
-                                                               want_expected=True, engine_factory=_factory)
+        run = lambda: ghs.sequence_holograms(_frames(n_frames), 5, precision="fp64", batch=2, want_expected=True,   # noqa: E731
+                                             engine_factory=_factory, gather=gather)
+        first = run()
+        kept = first[0].copy()
+        holos, exps, errors, (lo, hi) = run()            # (the first result is still alive: rank 0 must not hand its memory out again)
+        np.testing.assert_array_equal(first[0], kept)
+        pool_while_alive = len(shared_host._POOL)
+        del first
+        third = run()                                    # ... and now it may
+        np.testing.assert_array_equal(third[0], holos)
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), holos=holos, exps=exps, lo=lo, hi=hi,
-                 errors=np.array([np.asarray(e) for e in errors]))
+                 errors=np.array([np.asarray(e) for e in errors]), pool=np.array([pool_while_alive, len(shared_host._POOL)]))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_frames", [5, 4])
-def test_two_rank_movie_matches_single_process(tmp_path, n_frames):
+@pytest.mark.parametrize("n_frames,gather", [(5, True), (4, "host"), (5, "device")])
+def test_two_rank_movie_matches_single_process(tmp_path, n_frames, gather):
+    """gather: through host memory shared by the ranks of one node (the default there) or device to device."""
     from spatial_light_modulator_module_b200 import generate_hologram_sequence as ghs
     port = free_port()
-    mp.spawn(_worker, args=(2, port, n_frames, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, n_frames, str(tmp_path), gather), nprocs=2, join=True)
     ref_h, ref_e, ref_err, (lo, hi) = ghs.sequence_holograms(_frames(n_frames), 5, precision="fp64", batch=3,
                                                             want_expected=True, engine_factory=_factory)
     assert (lo, hi) == (0, n_frames)
@@ -53,7 +62,9 @@ def test_two_rank_movie_matches_single_process(tmp_path, n_frames):
     np.testing.assert_array_equal(r0["errors"], np.array(ref_err))
     lo1, hi1 = int(r1["lo"]), int(r1["hi"])                           # rank 1 computed its own block ...
     assert (lo1, hi1) == ((n_frames + 1) // 2, n_frames)
-    assert r1["holos"].shape[0] == 0                                  # ... and sent it device to device: nothing read back
+    assert r1["holos"].shape[0] == 0                                  # ... and holds none of the movie
+    # shared host memory: two segments per result set (holograms, expected); two sets while the first result lived, and no more after
+    assert list(r0["pool"]) == ([0, 0] if gather == "device" else [4, 4])
     np.testing.assert_array_equal(r1["errors"], np.array(ref_err)[lo1:hi1])
 
 

@@ -156,17 +156,21 @@ def _frames_worker(rank, world, port, n_frames, out_dir):
     try:
         mask = synthetic.random_mask((768, 1024), seed=2)
         dots = synthetic.movie_frame_dots(n_frames, rescale_parameter=5.0)
-        frames, _, errors, (lo, hi) = ghs.sequence_holograms(None, 6, precision="fp32", batch=3, output="uint8", mask=mask, ct2pi=256,
-                                                             trap_dots=(dots, n_frames, (768, 1024)))
-        if rank == 0:
-            np.savez(os.path.join(out_dir, "frames0.npz"), frames=frames, lo=lo, hi=hi)
+        for how in ("device", "host"):                 # NCCL gather onto rank 0's device / host memory shared by the ranks
+            frames, _, errors, (lo, hi) = ghs.sequence_holograms(None, 6, precision="fp32", batch=3, output="uint8", mask=mask, ct2pi=256,
+                                                                 trap_dots=(dots, n_frames, (768, 1024)), gather=how)
+            if rank == 0:
+                import torch as _t
+                np.savez(os.path.join(out_dir, f"frames0_{how}.npz"), frames=frames, lo=lo, hi=hi,
+                         pinned=_t.from_numpy(frames[hi // 2:]).is_pinned() if how == "host" else False)
     finally:
         dist.destroy_process_group()
 
 
-def test_two_gpu_uint8_frames_gathered_device_to_device(tmp_path):
-    """Config 3's output format: device-rasterised trap targets, GS, mask add + quantisation, NCCL gather of the 8-bit
-    frames onto rank 0 -- equal to quantising the single-GPU float64 holograms."""
+def test_two_gpu_uint8_frames_gathered(tmp_path):
+    """Config 3's output format: device-rasterised trap targets, GS, mask add + quantisation, the 8-bit frames gathered
+    on rank 0 both ways (NCCL onto its device; read back by every rank into shared host memory) -- equal to quantising
+    the single-GPU float64 holograms."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -175,8 +179,9 @@ def test_two_gpu_uint8_frames_gathered_device_to_device(tmp_path):
     n = 7
     mp.spawn(_frames_worker, args=(2, free_port(), n, str(tmp_path)), nprocs=2, join=True)
     ref_h, _, _, _ = ghs.sequence_holograms(synthetic.movie_frames(n, rescale_parameter=5.0), 6, precision="fp32", batch=4)
-    r0 = np.load(tmp_path / "frames0.npz")
-    assert (int(r0["lo"]), int(r0["hi"])) == (0, n) and r0["frames"].dtype == np.uint8
     mask = synthetic.random_mask((768, 1024), seed=2)
-    for i in range(n):
-        np.testing.assert_array_equal(r0["frames"][i], dh.hologram_to_grey(ref_h[i], mask, 256))
+    for how in ("device", "host"):
+        r0 = np.load(tmp_path / f"frames0_{how}.npz")
+        assert (int(r0["lo"]), int(r0["hi"])) == (0, n) and r0["frames"].dtype == np.uint8
+        for i in range(n):
+            np.testing.assert_array_equal(r0["frames"][i], dh.hologram_to_grey(ref_h[i], mask, 256))
