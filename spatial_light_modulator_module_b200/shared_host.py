@@ -69,12 +69,12 @@ def shared_results(dist, specs, my_rows, page_lock=True):
             for n in sizes:
                 e = _free_entry(n, entries)
                 if e is None:
+                    # A tmpfs that is too small must fail HERE, not with SIGBUS in a copy.  (Not posix_fallocate: the pages
+                    # should be first touched -- page-locked -- by the rank that fills them, on ITS memory node.)
+                    st = os.statvfs("/dev/shm")
+                    if n > 0.8 * st.f_bavail * st.f_frsize:
+                        raise OSError("not enough room in /dev/shm")
                     shm = shared_memory.SharedMemory(create=True, size=n)
-                    try:                                  # reserve the pages now: a tmpfs that is too small must fail HERE, not with SIGBUS in a copy
-                        os.posix_fallocate(shm._fd, 0, n)
-                    except Exception:
-                        shm.close(); shm.unlink()
-                        raise
                     e = {"name": shm.name, "shm": shm, "nbytes": n, "owner": True, "holder": None, "locked": set()}
                     _POOL.append(e)
                 entries.append(e)

@@ -162,7 +162,7 @@ def _frames_worker(rank, world, port, n_frames, out_dir):
             if rank == 0:
                 import torch as _t
                 np.savez(os.path.join(out_dir, f"frames0_{how}.npz"), frames=frames, lo=lo, hi=hi,
-                         pinned=_t.from_numpy(frames[hi // 2:]).is_pinned() if how == "host" else False)
+                         pinned=_t.from_numpy(frames[:1]).is_pinned())           # (rank 0 page-locks the rows it fills itself)
     finally:
         dist.destroy_process_group()
 
@@ -183,5 +183,6 @@ def test_two_gpu_uint8_frames_gathered(tmp_path):
     for how in ("device", "host"):
         r0 = np.load(tmp_path / f"frames0_{how}.npz")
         assert (int(r0["lo"]), int(r0["hi"])) == (0, n) and r0["frames"].dtype == np.uint8
+        assert bool(r0["pinned"])                                     # page-locked either way (shared memory: registered in place)
         for i in range(n):
             np.testing.assert_array_equal(r0["frames"][i], dh.hologram_to_grey(ref_h[i], mask, 256))
