@@ -103,3 +103,44 @@ def test_two_rank_uint8_frames_from_device_rasterised_targets(tmp_path):
     for i in range(n_frames):
         np.testing.assert_array_equal(r0["frames"][i], P.quantize_q3(holos[i], mask, 200))
     assert sorted(zip(r0["seen_lo"], r0["seen_hi"])) == [(0, 2), (2, 3), (3, 5)]     # every rank's batches reached the callback
+
+
+def _shared_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from spatial_light_modulator_module_b200 import shared_host
+    os.environ["SLM_SHARED_RESULT_BYTES"] = str(3 << 20)               # room for three 1 MiB segments
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        log = []
+        keep = []
+        for n in (1, 1, 2, 4, 1):                                      # MiB; results dropped at once except the second
+            rows = 2 * n
+            (arr,) = shared_host.shared_results(dist, [((rows, 1 << 19), np.uint8)], (rank * n, (rank + 1) * n), page_lock=False)
+            arr[rank * n:(rank + 1) * n] = rank + 1 + 10 * len(log)     # every rank fills its rows ...
+            dist.barrier()
+            if rank == 0:                                              # ... and rank 0 sees all of them
+                assert (arr[:n] == 1 + 10 * len(log)).all() and (arr[n:] == 2 + 10 * len(log)).all()
+            if len(log) == 1:
+                keep.append(arr)
+            log.append((len(shared_host._POOL), sum(e["nbytes"] for e in shared_host._POOL) >> 20))
+            del arr
+            dist.barrier()
+        np.save(os.path.join(out_dir, f"pool{rank}.npy"), np.array(log))
+        names = [e["name"] for e in shared_host._POOL]
+        np.save(os.path.join(out_dir, f"names{rank}.npy"), np.array(names))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shared_result_pool(tmp_path):
+    """shared_host: segments are used again once their array is gone, never while it lives, given back beyond the
+    byte limit, and none is left in /dev/shm when the processes end."""
+    mp.spawn(_shared_worker, args=(2, free_port(), str(tmp_path)), nprocs=2, join=True)
+    p0, p1 = np.load(tmp_path / "pool0.npy"), np.load(tmp_path / "pool1.npy")
+    # call 1: one 1 MiB segment; call 2 re-uses it (kept alive afterwards); call 3: + 2 MiB; call 4: + 4 MiB, over the limit, so the
+    # free 2 MiB one goes (the 1 MiB one is held); call 5: a new 1 MiB segment beside the held one, and the free 4 MiB one goes
+    assert [list(r) for r in p0] == [[1, 1], [1, 1], [2, 3], [2, 5], [2, 2]]
+    np.testing.assert_array_equal(p0, p1)                              # the other rank maps and drops the same segments
+    for name in np.load(tmp_path / "names0.npy"):
+        assert not os.path.exists(os.path.join("/dev/shm", str(name).lstrip("/")))
