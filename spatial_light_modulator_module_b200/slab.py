@@ -30,7 +30,6 @@ from __future__ import annotations
 import ctypes as C
 import os
 import time
-from typing import List, Optional, Tuple
 
 import numpy as np
 
