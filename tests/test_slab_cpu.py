@@ -198,32 +198,36 @@ def test_gradient_descent_slab_entry_point():
         slab.gradient_descent_slab(t, loops, initial_guess="fourier", engine_factory=_slab_factory)
 
 
-@pytest.mark.parametrize("first,count", [(0, 0), (32, 32)])
-def test_peer_store_kernel_is_the_all_to_all(first, count):
+@pytest.mark.parametrize("first,count,dtype", [(0, 0, np.complex64), (32, 32, np.complex64), (0, 0, np.complex128), (32, 32, np.uint8)])
+def test_peer_store_kernel_is_the_all_to_all(first, count, dtype):
     """slm_transpose_blocks_peer with every "peer" a buffer of this process: the stores of all ranks together are the
     all-to-all of the transposed blocks, on the way out and on the way back (whole blocks and one part)."""
     from tests.emu.emu_engine import EmuSlabEngine
     n, world = 256, 4
     h = n // world
     rng = np.random.default_rng(4)
-    slabs = [(rng.standard_normal((h, n)) + 1j * rng.standard_normal((h, n))).astype(np.complex64) for _ in range(world)]
+    eb = np.dtype(dtype).itemsize
+    if dtype == np.uint8:
+        slabs = [rng.integers(0, 256, (h, n)).astype(np.uint8) for _ in range(world)]
+    else:
+        slabs = [(rng.standard_normal((h, n)) + 1j * rng.standard_normal((h, n))).astype(dtype) for _ in range(world)]
     engs = [EmuSlabEngine(n, world, r, "fp32") for r in range(world)]
-    recv = [engs[r]._mem_upload(np.zeros((world, h, h), np.complex64)) for r in range(world)]
+    recv = [engs[r]._mem_upload(np.zeros((world, h, h), dtype)) for r in range(world)]
     table = (C.c_void_p * world)(*[b.ctypes.data for b in recv])
     for r, eng in enumerate(engs):
         src = eng._mem_upload(slabs[r])
-        eng._check(eng._lib.slm_transpose_blocks_peer(eng._ctx, eng._mem_ptr(src), table, world, r, h, n, 8, 0, first, count))
+        eng._check(eng._lib.slm_transpose_blocks_peer(eng._ctx, eng._mem_ptr(src), table, world, r, h, n, eb, 0, first, count))
     i = slice(first, first + count) if count else slice(None)
     for q in range(world):
         for p in range(world):                                    # rank q's block p = rank p's columns q*h.., transposed
             np.testing.assert_array_equal(np.asarray(recv[q])[p][:, i], slabs[p][i, q * h:(q + 1) * h].T)
     # way back: lines (a part of them) into the peers' row slabs
-    back = [engs[r]._mem_upload(np.zeros((h, n), np.complex64)) for r in range(world)]
+    back = [engs[r]._mem_upload(np.zeros((h, n), dtype)) for r in range(world)]
     table = (C.c_void_p * world)(*[b.ctypes.data for b in back])
     lines = [np.ascontiguousarray(np.stack([slabs[p][:, q * h:(q + 1) * h].T for p in range(world)])) for q in range(world)]
     for q, eng in enumerate(engs):
         src = eng._mem_upload(lines[q])
-        eng._check(eng._lib.slm_transpose_blocks_peer(eng._ctx, eng._mem_ptr(src), table, world, q, h, n, 8, 1, first, count))
+        eng._check(eng._lib.slm_transpose_blocks_peer(eng._ctx, eng._mem_ptr(src), table, world, q, h, n, eb, 1, first, count))
     for p in range(world):
         got = np.asarray(back[p])
         for q in range(world):
