@@ -127,6 +127,10 @@ class Engine:
     def _mem_contiguous(self, dev):
         return dev.contiguous()
 
+    def _mem_repeat(self, plane, n: int):
+        """[1,H,W] device plane -> [n,H,W] copies (every target of a batch starts from the same guess)"""
+        return plane.expand(n, -1, -1).contiguous()
+
     def _mem_is_device(self, obj) -> bool:
         return hasattr(obj, "data_ptr")
 

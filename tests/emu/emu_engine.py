@@ -65,6 +65,9 @@ class EmuEngine(Engine):
     def _mem_contiguous(self, dev):
         return np.ascontiguousarray(dev).view(HostBuf)
 
+    def _mem_repeat(self, plane, n):
+        return np.repeat(np.asarray(plane), n, axis=0).view(HostBuf)
+
     def _mem_host_empty(self, shape, dtype):
         return np.empty(shape, dtype=dtype)
 

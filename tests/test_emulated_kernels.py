@@ -179,3 +179,25 @@ def test_sequence_driver_warm_start():
     cold, _, cold_errors, _ = ghs.sequence_holograms(frames, 5, precision="fp64", engine_factory=make_engine)
     assert errors[2][0] < cold_errors[2][0]
     eng.close()
+
+
+def test_batched_algorithm_comparison_matches_single_runs():
+    """compare_error_evolution_algorithms.error_evolution_curves (BASELINE config 4) at reduced size: chunks of two
+    targets, a ragged last chunk -- the curves of the one-target-at-a-time runs."""
+    import argparse
+    import numpy as np
+    from spatial_light_modulator_module_b200 import compare_error_evolution_algorithms as cmp, host_logic as hl, synthetic
+    shape = (128, 128)
+    targets = np.stack([synthetic.noise_target(shape, seed=1), synthetic.shapes_target(shape), synthetic.traps_target(shape)])
+    a = argparse.Namespace(max_loops=5, precision="fp64", tolerance=0, learning_rate=0.005, unsettle=0, initial_guess="random",
+                           random_seed=42, white_attention=1)
+    cmp.fill_unnecessary_args(a)
+    gd, gs = cmp.error_evolution_curves(targets, a, batch=2, engine_factory=make_engine)
+    assert len(gd) == len(gs) == 3
+    eng = make_engine(shape, "fp64", 1)
+    during, _ = hl.learning_rate_schedule(0.005, 0, 5)
+    for i, t in enumerate(targets):
+        r, _ = eng.gd(t, hl.host_initial_guess("random", shape, 42), during, 5)
+        np.testing.assert_allclose(gd[i], r.errors[0], rtol=1e-12)
+        np.testing.assert_allclose(gs[i], eng.gs(t, 5).errors[0], rtol=1e-12)
+    eng.close()
