@@ -629,7 +629,7 @@ extern "C" int slm_gs_run(slm_ctx* c, int batch, const uint8_t* T8, const void* 
         else SLM_TIMED(K_COL_PASS, c->col->col_pass(ALG_GS, ca, c->stream));
         return 0;
     };
-    std::string key("gs");                                          // every argument the loop's launches are made of
+    std::string key(groups ? "gs/pipeline" : "gs/plain");           // the kernel family and every argument the loop's launches are made of
     RowArgs ra_key = ra;
     ra_key.hologram = nullptr;                                      // (only the final pass -- outside the loop -- writes the hologram)
     key.append(reinterpret_cast<const char*>(&ra_key), sizeof ra_key).append(reinterpret_cast<const char*>(&ca), sizeof ca);
