@@ -388,6 +388,10 @@ def batched_loop_record(h, a, alg, precision, shape, batch, loops, steps, warmup
         kernels, roof = profile_kernels(eng, step, min(steps, 3), alg, precision, npx * batch, peak, peak_src, form, names,
                                         f"{alg}|{precision}|{shape[0]}x{shape[1]}|batch{batch}")
         rec["kernels"], rec["roofline"] = kernels, roof
+        if alg == "gd" and form == "pipe" and roof:
+            roof["note"] = ("one launch does what round 1's two did (max pass: read + write the transform, 16 B/px; gradient pass: 20 B/px -- "
+                            "0.104 + 0.164 = 0.268 ms): it moves 20 B/px in 0.24 ms and is bound by the planes' barriers and the SM "
+                            "(issue slots 32 % busy), not by DRAM; the whole iteration's fractions are in iteration_roofline")
     state.update(eng=eng, targets=targets, norms=norms, during=during, x0=x0, x=x, out=out, step=step)
     return rec, state
 
