@@ -86,6 +86,13 @@ def _worker_frames(rank, world, port, n_frames, out_dir):
                  seen_hi=np.array([s[1] for s in seen]))
         for a, b, h in seen:
             np.testing.assert_array_equal(h, frames[a:b])
+        # without a callback the same frames are gathered through shared host memory: the same bytes on rank 0
+        again, _, errors2, (lo2, hi2) = ghs.sequence_holograms(
+            None, 4, precision="fp64", batch=2, engine_factory=_factory, output="uint8", mask=mask, ct2pi=200,
+            trap_dots=(dots, n_frames, shape))
+        assert (lo2, hi2) == (lo, hi) and len(errors2) == len(errors)
+        if rank == 0:
+            np.testing.assert_array_equal(again, frames)
     finally:
         dist.destroy_process_group()
 
