@@ -338,8 +338,10 @@ class SlabEngine(Engine):
                                            int(inverse), int(block_in), int(block_out)))
 
     # ---- Gerchberg-Saxton on the distributed plane --------------------------------------------------------------
-    def gs(self, target_slab, max_loops: int, tolerance: float = 0.0, want_expected: bool = True, on_device: bool = False):
+    def gs(self, target_slab, max_loops: int, tolerance: float = 0.0, want_expected: bool = True, on_device: bool = False,
+           inc_amp_slab=None):
         """``target_slab``: this rank's uint8 rows [rows, N] of the target (host array or device buffer).
+        ``inc_amp_slab``: this rank's rows of the illumination amplitude (algorithms.py:14-19,30; None: uniform).
         Returns ``(hologram_slab float64 [rows, N], expected_slab or None, error_evolution list)``; the error
         curve is identical on every rank.  ``on_device`` leaves hologram / expected in device memory."""
         if max_loops < 1:
@@ -355,6 +357,9 @@ class SlabEngine(Engine):
                 raise ValueError(f"target slab must be uint8 {self.shape}")
             T, local_max = self._mem_upload(t), float(t.max())
         h, n, cs = self.rows, self.n, np.dtype(self.complex_dtype).itemsize
+        inc = self._as_device(inc_amp_slab, self.real_dtype, "inc_amp_slab")
+        if inc is not None and tuple(inc.shape) != self.shape:
+            raise ValueError(f"inc_amp_slab must have shape {self.shape}")
         norm = float(self._all_reduce(np.array([local_max]), "max")[0])
         peer = self._peer is not None
         blocks = (self.world, h, h)
@@ -395,14 +400,14 @@ class SlabEngine(Engine):
         t_loop = time.perf_counter()
         for k in range(max_loops):
             cur = X if src is Y else Y                                        # receives the row-transformed B
-            overlap = peer and getattr(self, "_parts", 1) > 1
+            overlap = peer and getattr(self, "_parts", 1) > 1 and inc is None   # (the passes in parts take no illumination plane)
             by_copy = overlap and self._how == "copy"
             if by_copy:
                 self._row_pass_and_copy(src, cur, field, S, cs)
             elif overlap:
                 self._row_pass_and_push(src, cur, field, cs)
             else:
-                self._check(self._lib.slm_rows_gs_row_pass(self._ctx, self._mem_ptr(src), self._mem_ptr(cur), None, int(field), 0, None))
+                self._check(self._lib.slm_rows_gs_row_pass(self._ctx, self._mem_ptr(src), self._mem_ptr(cur), self._mem_ptr(inc), int(field), 0, None))
                 self._exchange(cur, S, Rv, cs, "Rv")
             if k == 0:                                                        # exact scale of iteration 0: max pre-pass
                 self._fourier(Rv, S, Tx, state, partial, None)

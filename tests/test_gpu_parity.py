@@ -541,6 +541,23 @@ def test_slab_gd_single_rank_equals_plane_engine(precision, n):
     eng.close(); ref.close()
 
 
+def test_slab_gs_with_illumination_plane():
+    """A non-uniform illumination amplitude on the slab path: the ordinary engine's result (fp64: the same bits)."""
+    from spatial_light_modulator_module_b200.slab import SlabEngine
+    n = 1024
+    t = synthetic.shapes_target((n, n))
+    yy, xx = np.mgrid[0:n, 0:n]
+    inc = np.exp(-((yy - n / 2) ** 2 + (xx - n / 2) ** 2) / (2 * (n / 3) ** 2))
+    ref = make_engine((n, n), "fp64", 1)
+    r = ref.gs(t, 5, inc_amp=inc)
+    eng = SlabEngine(n, 1, 0, "fp64")
+    h, e, errs = eng.gs(t, 5, inc_amp_slab=inc)
+    np.testing.assert_array_equal(h, ref.to_host(r.hologram)[0])
+    np.testing.assert_allclose(e, ref.to_host(r.expected)[0], rtol=1e-12)
+    assert np.max(np.abs(np.array(errs) - r.errors[0]) / r.errors[0]) < 1e-12
+    eng.close(); ref.close()
+
+
 def _golden_slab(name):
     import os
     return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))

@@ -234,3 +234,23 @@ def test_peer_store_kernel_is_the_all_to_all(first, count, dtype):
             np.testing.assert_array_equal(got[:, q * h:(q + 1) * h][:, i], slabs[p][:, q * h:(q + 1) * h][:, i])
     for eng in engs:
         eng.close()
+
+
+def test_slab_gs_with_illumination_plane():
+    """A non-uniform illumination amplitude (algorithms.py:14-19,30) on the slab path: the ordinary engine's bits."""
+    from spatial_light_modulator_module_b200 import synthetic
+    from tests.emu.emu_engine import EmuEngine, EmuSlabEngine
+    n = 256
+    t = synthetic.shapes_target((n, n))
+    yy, xx = np.mgrid[0:n, 0:n]
+    inc = np.exp(-((yy - n / 2) ** 2 + (xx - n / 2) ** 2) / (2 * (n / 3) ** 2))
+    ref = EmuEngine((n, n), "fp64", 1)
+    r = ref.gs(t, 4, inc_amp=inc)
+    eng = EmuSlabEngine(n, 1, 0, "fp64")
+    h, e, errs = eng.gs(t, 4, inc_amp_slab=inc)
+    np.testing.assert_array_equal(h, ref.to_host(r.hologram)[0])
+    np.testing.assert_array_equal(e, ref.to_host(r.expected)[0])
+    assert np.max(np.abs(np.array(errs) - r.errors[0]) / r.errors[0]) < 1e-12
+    h0, _, errs0 = eng.gs(t, 4)
+    assert not np.array_equal(h0, h)                                   # (the plane does change the result)
+    eng.close(); ref.close()
