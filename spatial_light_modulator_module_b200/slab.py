@@ -639,9 +639,10 @@ def gradient_descent_slab(target, max_loops: int, learning_rate: float = 0.005, 
     eng = (engine_factory or SlabEngine)(n, world, rank, precision)
     try:
         if initial_guess in ("random", "zeros"):
-            # the MT19937 stream continued on the device (Engine.python_random_uniform); every rank draws the plane's
-            # stream up to the end of its own rows and keeps those
-            u = eng.python_random_uniform(random_seed, (hi, n))
+            # the MT19937 stream continued on the device (Engine.python_random_uniform); every rank draws the whole plane's
+            # stream -- the last rank needs all of it anyway, and Python's generator is then left where the reference's
+            # per-pixel loop leaves it (algorithms.py:117-124) on every rank -- and keeps its own rows
+            u = eng.python_random_uniform(random_seed, (n, n))
             x0 = eng._mem_empty(eng.shape, eng.complex_dtype)
             eng._check(eng._lib.slm_random_phasor(eng._ctx, eng._mem_ptr(u[lo:hi]), eng._mem_ptr(x0), (hi - lo) * n,
                                                   100.0 if initial_guess == "zeros" else 1.0))
